@@ -1,0 +1,83 @@
+"""ctypes binding of libancsh_b200.so (include/ancsh_b200.h).
+
+There is NO fallback: if the CUDA library has not been built, importing this module raises.
+Build it with `python -m articulated_pose_b200.build` (or __graft_entry__.build()).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libancsh_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "articulated_pose_b200: %s is missing. This package has no CPU/PyTorch fallback; build the sm_100a "
+        "library first: python -m articulated_pose_b200.build" % LIB_PATH)
+
+lib = ctypes.CDLL(LIB_PATH)
+
+c_float_p = ctypes.c_void_p  # device pointers are passed as raw addresses
+c_int = ctypes.c_int
+c_size_t = ctypes.c_size_t
+
+OK = 0
+ERRORS = {-1: "ANCSH_ERR_INVALID_ARG", -2: "ANCSH_ERR_CUDA", -3: "ANCSH_ERR_UNSUPPORTED", -4: "ANCSH_ERR_WORKSPACE"}
+
+
+class AncshError(RuntimeError):
+    pass
+
+
+def check(rc, what):
+    if rc != OK:
+        raise AncshError("%s failed: %s (%d)" % (what, ERRORS.get(rc, "unknown"), rc))
+
+
+class Layer(ctypes.Structure):
+    _fields_ = [("W", ctypes.c_void_p), ("b", ctypes.c_void_p), ("cin", c_int), ("cout", c_int),
+                ("cin_pad", c_int), ("cout_pad", c_int), ("relu", c_int)]
+
+
+class Net(ctypes.Structure):
+    _fields_ = [("n_parts", c_int), ("mixed_pred", c_int),
+                ("npoint1", c_int), ("nsample1", c_int), ("radius1", ctypes.c_float),
+                ("npoint2", c_int), ("nsample2", c_int), ("radius2", ctypes.c_float),
+                ("sa1", Layer * 3), ("sa2", Layer * 3), ("sa3", Layer * 3),
+                ("fp1_global", Layer), ("fp1", Layer * 2), ("fp2", Layer * 2), ("fp3", Layer * 3),
+                ("fc1", Layer), ("nocs_heads", Layer), ("fc3", Layer * 2), ("joint_heads", Layer)]
+
+
+PRED_FIELDS = ("W", "nocs_per_point", "confi_per_point", "heatmap_per_point", "unitvec_per_point",
+               "joint_axis_per_point", "index_per_point", "gocs_per_point", "global_scale", "global_translation")
+
+
+class Pred(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_void_p) for k in PRED_FIELDS]
+
+
+WS_FIELDS = ("fps_idx1", "l1_xyz", "fps_idx2", "l2_xyz", "ball_idx1", "ball_cnt1", "ball_idx2", "ball_cnt2",
+             "l1_points", "l2_points", "l3_points", "fp1_bias", "l2_points_fp", "l1_points_fp", "total_bytes")
+
+
+class WsLayout(ctypes.Structure):
+    _fields_ = [(k, c_size_t) for k in WS_FIELDS]
+
+
+def _sig(name, argtypes, restype=c_int):
+    fn = getattr(lib, name)
+    fn.argtypes = argtypes
+    fn.restype = restype
+    return fn
+
+
+vp = ctypes.c_void_p
+ancsh_version = _sig("ancsh_version", [], ctypes.c_char_p)
+ancsh_fps = _sig("ancsh_fps", [c_int, c_int, c_int, vp, vp, vp, vp])
+ancsh_gather_point = _sig("ancsh_gather_point", [c_int, c_int, c_int, vp, vp, vp, vp])
+ancsh_ball_query = _sig("ancsh_ball_query", [c_int, c_int, c_int, ctypes.c_float, c_int, vp, vp, vp, vp, vp])
+ancsh_group_point = _sig("ancsh_group_point", [c_int, c_int, c_int, c_int, c_int, vp, vp, vp, vp])
+ancsh_three_nn = _sig("ancsh_three_nn", [c_int, c_int, c_int, vp, vp, vp, vp, vp])
+ancsh_three_interpolate = _sig("ancsh_three_interpolate", [c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp])
+ancsh_net_plan = _sig("ancsh_net_plan", [ctypes.POINTER(Net), c_int, c_int, ctypes.POINTER(WsLayout)])
+ancsh_net_forward = _sig("ancsh_net_forward", [ctypes.POINTER(Net), c_int, c_int, vp, vp, c_size_t,
+                                               ctypes.POINTER(Pred), vp])

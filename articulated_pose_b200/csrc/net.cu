@@ -1,0 +1,461 @@
+// net.cu -- ANCSH network forward (PointNet++ trunk + heads) as fused row-tile kernels.
+//
+//   sa_kernel   : [ball-query indices] -> gather(xyz - centroid, features) -> 3 x (1x1 conv + BN + ReLU)
+//                 -> max over nsample        (pointnet_util.py:29-63, 94-161; the grouped tensor that the
+//                 reference materialises in HBM -- tf_grouping_g.cu:40-57 -- never leaves shared memory)
+//   fp_kernel   : three_nn -> inverse-distance weights -> three_interpolate -> concat skip -> MLP
+//                 (pointnet_util.py:206-236); with HEADS also fc1 + all ANCSH heads + activations + gocs
+//                 (architectures.py:89-93, lib/architecture.py:98-159, 195-208)
+//
+// Arithmetic: f32 FMA accumulation in natural k order on the CUDA cores (this file is the exact-f32 path).
+#include "common.cuh"
+#include "ops.cuh"
+#include "mlp_simt.cuh"
+
+using namespace mlp;
+
+// ------------------------------------------------------------------------------------------------
+// dispatch helpers (NC = 64 for 64-wide layers, 128 otherwise)
+// ------------------------------------------------------------------------------------------------
+template <int TM>
+__device__ __forceinline__ void layer_to_smem(const float *Xs, int ldx, const ancsh_layer_t &L, const float *bias,
+                                              float *Ys, int ldy, float *Wsm)
+{
+    if (L.cout_pad == 64)
+        dense_layer<TM, 64>(Xs, ldx, L, Wsm, EpiSmem<TM, 64>{Ys, ldy, bias, L.relu});
+    else
+        dense_layer<TM, 128>(Xs, ldx, L, Wsm, EpiSmem<TM, 128>{Ys, ldy, bias, L.relu});
+}
+template <int TM>
+__device__ __forceinline__ void layer_to_global(const float *Xs, int ldx, const ancsh_layer_t &L, const float *bias,
+                                                float *out, int ldo, float *Wsm)
+{
+    if (L.cout_pad == 64)
+        dense_layer<TM, 64>(Xs, ldx, L, Wsm, EpiGlobal<TM, 64>{out, ldo, bias, L.relu});
+    else
+        dense_layer<TM, 128>(Xs, ldx, L, Wsm, EpiGlobal<TM, 128>{out, ldo, bias, L.relu});
+}
+template <int TM>
+__device__ __forceinline__ void layer_to_pool(const float *Xs, int ldx, const ancsh_layer_t &L, const float *bias,
+                                              float *out, long row0, int S, float *Wsm)
+{
+    if (L.cout_pad == 64)
+        dense_layer<TM, 64>(Xs, ldx, L, Wsm, EpiPool<TM, 64>{out, L.cout, bias, row0, S});
+    else
+        dense_layer<TM, 128>(Xs, ldx, L, Wsm, EpiPool<TM, 128>{out, L.cout, bias, row0, S});
+}
+
+// ================================================================================================
+// Set abstraction
+// ================================================================================================
+struct SaArgs {
+    const float *xyz;      // (B,n,3) dataset coordinates
+    const float *points;   // (B,n,C) dataset features (C may be 0)
+    const float *new_xyz;  // (B,m,3) centroids; NULL = no centring (group_all, pointnet_util.py:80-88)
+    const int *idx;        // (B,m,S) ball-query result; NULL = identity (group_all)
+    float *out;            // (B,m,cout) zero-initialised
+    ancsh_layer_t L[3];
+    int n, m, S, C;
+    int ldA, ldB;
+};
+
+template <int TM>
+__global__ void __launch_bounds__(NT) sa_kernel(const SaArgs a)
+{
+    extern __shared__ __align__(16) float smem[];
+    float *bufA = smem;
+    float *bufB = bufA + TM * a.ldA;
+    float *Wsm = bufB + TM * a.ldB;
+
+    const int tile = blockIdx.x, b = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int C = a.C, cin_pad = a.L[0].cin_pad;
+    const long row0 = (long)tile * TM;
+
+    // ---- gather the tile: channel order [features(C), xyz(3), zero pad] --------------------------
+    for (int r = warp; r < TM; r += NT / 32) {
+        const long R = row0 + r;
+        const int g = (int)(R / a.S);
+        const int id = a.idx ? __ldg(a.idx + (size_t)b * a.m * a.S + R) : (int)R;
+        float *xr = bufA + r * a.ldA;
+        if (C > 0) {
+            const float *prow = a.points + ((size_t)b * a.n + id) * C;
+            for (int c4 = lane; c4 < C / 4; c4 += 32) *reinterpret_cast<float4 *>(xr + c4 * 4) = ldg4(prow + c4 * 4);
+        }
+        for (int c = C + lane; c < cin_pad; c += 32) {
+            float v = 0.f;
+            if (c < C + 3) {
+                v = __ldg(a.xyz + ((size_t)b * a.n + id) * 3 + (c - C));
+                if (a.new_xyz) v = __fsub_rn(v, __ldg(a.new_xyz + ((size_t)b * a.m + g) * 3 + (c - C)));   // :53
+            }
+            xr[c] = v;
+        }
+    }
+    // (dense_layer starts with __syncthreads)
+    layer_to_smem<TM>(bufA, a.ldA, a.L[0], a.L[0].b, bufB, a.ldB, Wsm);
+    layer_to_smem<TM>(bufB, a.ldB, a.L[1], a.L[1].b, bufA, a.ldA, Wsm);
+    layer_to_pool<TM>(bufA, a.ldA, a.L[2], a.L[2].b, a.out + (size_t)b * a.m * a.L[2].cout, row0, a.S, Wsm);
+}
+
+template <int TM>
+static int sa_launch(const SaArgs &a0, int B, cudaStream_t st)
+{
+    SaArgs a = a0;
+    const long rows = (long)a.m * a.S;
+    if (rows % TM != 0 || a.S % 8 != 0 || a.C % 4 != 0) return ANCSH_ERR_UNSUPPORTED;
+    if (a.L[2].cout != a.L[2].cout_pad || !a.L[2].relu) return ANCSH_ERR_INVALID_ARG;
+    if (a.L[0].cin != a.C + 3) return ANCSH_ERR_INVALID_ARG;
+    if (a.L[1].cin_pad != a.L[0].cout_pad || a.L[2].cin_pad != a.L[1].cout_pad) return ANCSH_ERR_INVALID_ARG;
+    a.ldA = (a.L[0].cin_pad > a.L[1].cout_pad ? a.L[0].cin_pad : a.L[1].cout_pad) + 4;
+    a.ldB = a.L[0].cout_pad + 4;
+    size_t smem = ((size_t)TM * (a.ldA + a.ldB) + WS_FLOATS) * sizeof(float);
+    if (smem > 227 * 1024) return ANCSH_ERR_UNSUPPORTED;
+    ANCSH_CUDA(cudaFuncSetAttribute(sa_kernel<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ANCSH_CUDA(cudaMemsetAsync(a.out, 0, (size_t)B * a.m * a.L[2].cout * sizeof(float), st));
+    dim3 grid((unsigned)(rows / TM), B);
+    sa_kernel<TM><<<grid, NT, smem, st>>>(a);
+    ANCSH_CHECK_LAUNCH();
+    return ANCSH_OK;
+}
+
+// ================================================================================================
+// fa_layer1's global-feature term: the single "known" point of FP1 makes three_interpolate a broadcast
+// (weights 1,0,0 -- tf_interpolate.cpp:60-103 with m=1), so conv_0 splits into a per-cloud bias
+//   cb[b][o] = b[o] + sum_k l3[b][k] * W[k][o]          (rows of W that multiply the interpolated part)
+// plus the skip-feature rows handled by fp_kernel.
+// ================================================================================================
+__global__ void __launch_bounds__(256) cloud_bias_kernel(const float *__restrict__ feat, int cin,
+                                                         const float *__restrict__ W, const float *__restrict__ bias,
+                                                         int cout_pad, float *__restrict__ out)
+{
+    extern __shared__ float s_f[];
+    const int b = blockIdx.x;
+    for (int k = threadIdx.x; k < cin; k += blockDim.x) s_f[k] = feat[(size_t)b * cin + k];
+    __syncthreads();
+    for (int o = threadIdx.x; o < cout_pad; o += blockDim.x) {
+        float acc = 0.f;
+        for (int k = 0; k < cin; ++k) acc = fmaf(s_f[k], __ldg(W + (size_t)k * cout_pad + o), acc);
+        out[(size_t)b * cout_pad + o] = acc + bias[o];
+    }
+}
+
+// ================================================================================================
+// Feature propagation (+ optional fc1 / heads)
+// ================================================================================================
+struct FpArgs {
+    const float *xyz1;     // (B,n1,3) query points = rows
+    const float *xyz2;     // (B,m2,3) known points; NULL = no interpolated part
+    const float *points2;  // (B,m2,C2)
+    const float *skip;     // (B,n1,C1)
+    int n1, m2, C2, C1;
+    ancsh_layer_t L[3];
+    int nl;
+    const float *bias0;    // bias of L[0]; per cloud when bias0_stride != 0
+    long bias0_stride;
+    float *out;            // (B,n1,cout_last)  (unused with HEADS)
+    // HEADS only
+    ancsh_layer_t fc1, nocs_heads, fc3[2], joint_heads;
+    ancsh_pred_t pred;
+    int K, mixed;
+    int ldA, ldB, ldC;
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ void copy_tile_out(float *dst, int w, const float *src, int ld, int off, int TM)
+{
+    if (!dst) return;
+    for (int e = threadIdx.x; e < TM * w; e += NT) {
+        int r = e / w, c = e - r * w;
+        dst[e] = src[r * ld + off + c];
+    }
+}
+
+template <int TM, bool HEADS>
+__global__ void __launch_bounds__(NT) fp_kernel(const FpArgs a)
+{
+    extern __shared__ __align__(16) float smem[];
+    float *bufA = smem;
+    float *bufB = bufA + TM * a.ldA;
+    float *bufC = bufB + TM * a.ldB;                 // HEADS only (ldC == 0 otherwise)
+    float *Wsm = bufC + TM * a.ldC;
+    float *s_known = Wsm + WS_FLOATS;                // m2*3
+    float *s_w = s_known + a.m2 * 3;                 // TM*3
+    int *s_i = reinterpret_cast<int *>(s_w + TM * 3);  // TM*3
+
+    const int tile = blockIdx.x, b = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long row0 = (long)tile * TM;
+    const int cin_pad = a.L[0].cin_pad;
+
+    // ---- three_nn + weights (pointnet_util.py:217-222) ---------------------------------------------
+    if (a.xyz2) {
+        constexpr int PARTS = NT / TM;
+        for (int i = tid; i < a.m2 * 3; i += NT) s_known[i] = __ldg(a.xyz2 + (size_t)b * a.m2 * 3 + i);
+        __syncthreads();
+        const int row = tid / PARTS, part = tid % PARTS;
+        const float *q = a.xyz1 + ((size_t)b * a.n1 + row0 + row) * 3;
+        const float x1 = __ldg(q), y1 = __ldg(q + 1), z1 = __ldg(q + 2);
+        const int chunk = (a.m2 + PARTS - 1) / PARTS;
+        const int k0 = part * chunk, k1 = min(a.m2, k0 + chunk);
+        Best3 best;
+        best.init();
+        for (int k = k0; k < k1; ++k)
+            best.insert(nn_dist_unfused(s_known[k * 3], s_known[k * 3 + 1], s_known[k * 3 + 2], x1, y1, z1), k);
+#pragma unroll
+        for (int off = 1; off < PARTS; off <<= 1) {
+            Best3 o;
+            o.d1 = __shfl_xor_sync(0xFFFFFFFFu, best.d1, off); o.i1 = __shfl_xor_sync(0xFFFFFFFFu, best.i1, off);
+            o.d2 = __shfl_xor_sync(0xFFFFFFFFu, best.d2, off); o.i2 = __shfl_xor_sync(0xFFFFFFFFu, best.i2, off);
+            o.d3 = __shfl_xor_sync(0xFFFFFFFFu, best.d3, off); o.i3 = __shfl_xor_sync(0xFFFFFFFFu, best.i3, off);
+            if ((part & off) == 0) {
+                best.merge_higher(o);
+            } else {
+                o.merge_higher(best);
+                best = o;
+            }
+        }
+        if (part == 0) {
+            float w1, w2, w3;
+            three_weights(best.d1, best.d2, best.d3, w1, w2, w3);
+            s_w[row * 3 + 0] = w1; s_w[row * 3 + 1] = w2; s_w[row * 3 + 2] = w3;
+            s_i[row * 3 + 0] = best.i1; s_i[row * 3 + 1] = best.i2; s_i[row * 3 + 2] = best.i3;
+        }
+        __syncthreads();
+    }
+    // ---- build the tile: [interpolated(C2), skip(C1), zero pad] (pointnet_util.py:223-229) ---------
+    for (int r = warp; r < TM; r += NT / 32) {
+        float *xr = bufA + r * a.ldA;
+        if (a.xyz2) {
+            const float w1 = s_w[r * 3], w2 = s_w[r * 3 + 1], w3 = s_w[r * 3 + 2];
+            const float *p1 = a.points2 + ((size_t)b * a.m2 + s_i[r * 3 + 0]) * a.C2;
+            const float *p2 = a.points2 + ((size_t)b * a.m2 + s_i[r * 3 + 1]) * a.C2;
+            const float *p3 = a.points2 + ((size_t)b * a.m2 + s_i[r * 3 + 2]) * a.C2;
+            for (int c4 = lane; c4 < a.C2 / 4; c4 += 32) {
+                const float4 u = ldg4(p1 + c4 * 4), v = ldg4(p2 + c4 * 4), w = ldg4(p3 + c4 * 4);
+                float4 o;
+                o.x = interp3_unfused(u.x, v.x, w.x, w1, w2, w3);
+                o.y = interp3_unfused(u.y, v.y, w.y, w1, w2, w3);
+                o.z = interp3_unfused(u.z, v.z, w.z, w1, w2, w3);
+                o.w = interp3_unfused(u.w, v.w, w.w, w1, w2, w3);
+                *reinterpret_cast<float4 *>(xr + c4 * 4) = o;
+            }
+        }
+        const float *srow = a.skip + ((size_t)b * a.n1 + row0 + r) * a.C1;
+        for (int c = a.C2 + lane; c < cin_pad; c += 32) xr[c] = (c - a.C2 < a.C1) ? __ldg(srow + (c - a.C2)) : 0.f;
+    }
+
+    const float *bias0 = a.bias0 + (size_t)b * a.bias0_stride;
+    if (!HEADS) {
+        // two-layer chain: A -> B -> global
+        layer_to_smem<TM>(bufA, a.ldA, a.L[0], bias0, bufB, a.ldB, Wsm);
+        layer_to_global<TM>(bufB, a.ldB, a.L[1], a.L[1].b, a.out + ((size_t)b * a.n1 + row0) * a.L[1].cout, a.L[1].cout,
+                            Wsm);
+    } else {
+        // fa_layer3 (3 layers) -> fc1 -> heads
+        layer_to_smem<TM>(bufA, a.ldA, a.L[0], bias0, bufB, a.ldB, Wsm);
+        layer_to_smem<TM>(bufB, a.ldB, a.L[1], a.L[1].b, bufA, a.ldA, Wsm);
+        layer_to_smem<TM>(bufA, a.ldA, a.L[2], a.L[2].b, bufB, a.ldB, Wsm);
+        layer_to_smem<TM>(bufB, a.ldB, a.fc1, a.fc1.b, bufA, a.ldA, Wsm);                    // net
+        layer_to_smem<TM>(bufA, a.ldA, a.nocs_heads, a.nocs_heads.b, bufC, a.ldC, Wsm);      // raw nocs_net outputs
+        layer_to_smem<TM>(bufA, a.ldA, a.fc3[0], a.fc3[0].b, bufB, a.ldB, Wsm);
+        layer_to_smem<TM>(bufB, a.ldB, a.fc3[1], a.fc3[1].b, bufA, a.ldA, Wsm);
+        layer_to_smem<TM>(bufA, a.ldA, a.joint_heads, a.joint_heads.b, bufB, a.ldC, Wsm);    // raw joint_net outputs
+        __syncthreads();
+        // ---- activations (lib/architecture.py:122-139, 150-157), one thread per row and head group --
+        const int K = a.K;
+        if (tid < TM) {
+            float *x = bufC + tid * a.ldC;
+            float mx = x[0];
+            for (int k = 1; k < K; ++k) mx = fmaxf(mx, x[k]);
+            float s = 0.f;
+            for (int k = 0; k < K; ++k) { float e = expf(x[k] - mx); x[k] = e; s += e; }
+            for (int k = 0; k < K; ++k) x[k] = x[k] / s;                                   // W softmax
+            for (int k = K; k < 4 * K; ++k) x[k] = sigmoidf_(x[k]);                        // nocs
+            if (a.mixed) {
+                for (int k = 4 * K; k < 5 * K; ++k) x[k] = sigmoidf_(x[k]);                // scale
+                for (int k = 5 * K; k < 8 * K; ++k) x[k] = tanhf(x[k]);                    // translation
+                x[8 * K] = sigmoidf_(x[8 * K]);                                            // confidence
+                for (int k = 0; k < 3 * K; ++k)                                            // gocs :154-157
+                    x[8 * K + 1 + k] = __fadd_rn(__fmul_rn(x[K + k], x[4 * K + k / 3]), x[5 * K + k]);
+            } else {
+                x[4 * K] = sigmoidf_(x[4 * K]);
+            }
+        } else if (tid < 2 * TM) {
+            float *x = bufB + (tid - TM) * a.ldC;
+            for (int k = 0; k < 6; ++k) x[k] = tanhf(x[k]);                                // joint_axis, unitvec
+            x[6] = sigmoidf_(x[6]);                                                        // heatmap
+            float mx = fmaxf(x[7], fmaxf(x[8], x[9]));
+            float e0 = expf(x[7] - mx), e1 = expf(x[8] - mx), e2 = expf(x[9] - mx);
+            float s = e0 + e1 + e2;
+            x[7] = e0 / s; x[8] = e1 / s; x[9] = e2 / s;                                   // index softmax
+        }
+        __syncthreads();
+        const size_t p0 = (size_t)b * a.n1 + row0;
+        const ancsh_pred_t &o = a.pred;
+        copy_tile_out(o.W ? o.W + p0 * K : nullptr, K, bufC, a.ldC, 0, TM);
+        copy_tile_out(o.nocs_per_point ? o.nocs_per_point + p0 * 3 * K : nullptr, 3 * K, bufC, a.ldC, K, TM);
+        if (a.mixed) {
+            copy_tile_out(o.global_scale ? o.global_scale + p0 * K : nullptr, K, bufC, a.ldC, 4 * K, TM);
+            copy_tile_out(o.global_translation ? o.global_translation + p0 * 3 * K : nullptr, 3 * K, bufC, a.ldC, 5 * K, TM);
+            copy_tile_out(o.confi_per_point ? o.confi_per_point + p0 : nullptr, 1, bufC, a.ldC, 8 * K, TM);
+            copy_tile_out(o.gocs_per_point ? o.gocs_per_point + p0 * 3 * K : nullptr, 3 * K, bufC, a.ldC, 8 * K + 1, TM);
+        } else {
+            copy_tile_out(o.confi_per_point ? o.confi_per_point + p0 : nullptr, 1, bufC, a.ldC, 4 * K, TM);
+        }
+        copy_tile_out(o.joint_axis_per_point ? o.joint_axis_per_point + p0 * 3 : nullptr, 3, bufB, a.ldC, 0, TM);
+        copy_tile_out(o.unitvec_per_point ? o.unitvec_per_point + p0 * 3 : nullptr, 3, bufB, a.ldC, 3, TM);
+        copy_tile_out(o.heatmap_per_point ? o.heatmap_per_point + p0 : nullptr, 1, bufB, a.ldC, 6, TM);
+        copy_tile_out(o.index_per_point ? o.index_per_point + p0 * 3 : nullptr, 3, bufB, a.ldC, 7, TM);
+    }
+}
+
+template <int TM, bool HEADS>
+static int fp_launch(const FpArgs &a0, int B, cudaStream_t st)
+{
+    FpArgs a = a0;
+    if (a.n1 % TM != 0 || a.C2 % 4 != 0) return ANCSH_ERR_UNSUPPORTED;
+    if (a.L[0].cin != a.C2 + a.C1) return ANCSH_ERR_INVALID_ARG;
+    int maxA = a.L[0].cin_pad, maxB = a.L[0].cout_pad;
+    if (HEADS) {
+        if (a.nl != 3) return ANCSH_ERR_INVALID_ARG;
+        const int wa[] = {a.L[1].cout_pad, a.fc1.cout_pad, a.fc3[1].cout_pad};
+        const int wb[] = {a.L[2].cout_pad, a.fc3[0].cout_pad};
+        for (int v : wa) maxA = v > maxA ? v : maxA;
+        for (int v : wb) maxB = v > maxB ? v : maxB;
+        if (a.nocs_heads.cout_pad != 64 || a.joint_heads.cout_pad != 64) return ANCSH_ERR_INVALID_ARG;
+        if (11 * a.K + 1 > 64 || a.K < 1) return ANCSH_ERR_UNSUPPORTED;
+        a.ldC = 64 + 4;
+    } else {
+        if (a.nl != 2 || a.L[1].cout != a.L[1].cout_pad) return ANCSH_ERR_INVALID_ARG;
+        a.ldC = 0;
+    }
+    a.ldA = maxA + 4;
+    a.ldB = maxB + 4;
+    size_t smem = ((size_t)TM * (a.ldA + a.ldB + a.ldC) + WS_FLOATS + (size_t)a.m2 * 3 + (size_t)TM * 6) * sizeof(float);
+    if (smem > 227 * 1024) return ANCSH_ERR_UNSUPPORTED;
+    ANCSH_CUDA(cudaFuncSetAttribute(fp_kernel<TM, HEADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(a.n1 / TM, B);
+    fp_kernel<TM, HEADS><<<grid, NT, smem, st>>>(a);
+    ANCSH_CHECK_LAUNCH();
+    return ANCSH_OK;
+}
+
+// ================================================================================================
+// plan + forward
+// ================================================================================================
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" int ancsh_net_plan(const ancsh_net_t *net, int B, int N, ancsh_ws_layout_t *L)
+{
+    if (!net || !L || B <= 0 || N <= 0) return ANCSH_ERR_INVALID_ARG;
+    if (N % 128 != 0) return ANCSH_ERR_UNSUPPORTED;
+    const size_t m1 = net->npoint1, m2 = net->npoint2, s1 = net->nsample1, s2 = net->nsample2, b = B;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align256(off + bytes); return o; };
+    L->fps_idx1 = take(b * m1 * 4);
+    L->l1_xyz = take(b * m1 * 3 * 4);
+    L->fps_idx2 = take(b * m2 * 4);
+    L->l2_xyz = take(b * m2 * 3 * 4);
+    L->ball_idx1 = take(b * m1 * s1 * 4);
+    L->ball_cnt1 = take(b * m1 * 4);
+    L->ball_idx2 = take(b * m2 * s2 * 4);
+    L->ball_cnt2 = take(b * m2 * 4);
+    L->l1_points = take(b * m1 * net->sa1[2].cout * 4);
+    L->l2_points = take(b * m2 * net->sa2[2].cout * 4);
+    L->l3_points = take(b * net->sa3[2].cout * 4);
+    L->fp1_bias = take(b * net->fp1_global.cout_pad * 4);
+    L->l2_points_fp = take(b * m2 * net->fp1[1].cout * 4);
+    L->l1_points_fp = take(b * m1 * net->fp2[1].cout * 4);
+    L->total_bytes = off;
+    return ANCSH_OK;
+}
+
+extern "C" int ancsh_net_forward(const ancsh_net_t *net, int B, int N, const float *P, void *workspace,
+                                 size_t workspace_bytes, const ancsh_pred_t *pred, void *stream)
+{
+    if (!net || !P || !workspace || !pred) return ANCSH_ERR_INVALID_ARG;
+    if (B > 65535) return ANCSH_ERR_UNSUPPORTED;
+    ancsh_ws_layout_t L;
+    int rc = ancsh_net_plan(net, B, N, &L);
+    if (rc != ANCSH_OK) return rc;
+    if (workspace_bytes < L.total_bytes) return ANCSH_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)workspace;
+    int *fps1 = (int *)(ws + L.fps_idx1), *fps2 = (int *)(ws + L.fps_idx2);
+    float *l1_xyz = (float *)(ws + L.l1_xyz), *l2_xyz = (float *)(ws + L.l2_xyz);
+    int *bidx1 = (int *)(ws + L.ball_idx1), *bcnt1 = (int *)(ws + L.ball_cnt1);
+    int *bidx2 = (int *)(ws + L.ball_idx2), *bcnt2 = (int *)(ws + L.ball_cnt2);
+    float *l1_points = (float *)(ws + L.l1_points), *l2_points = (float *)(ws + L.l2_points);
+    float *l3_points = (float *)(ws + L.l3_points), *fp1_bias = (float *)(ws + L.fp1_bias);
+    float *l2_fp = (float *)(ws + L.l2_points_fp), *l1_fp = (float *)(ws + L.l1_points_fp);
+    const int m1 = net->npoint1, m2 = net->npoint2;
+
+    // sampling (pointnet_util.py:47) -- level 2 samples the level-1 centroids
+    if ((rc = ancsh_fps_impl(B, N, m1, P, fps1, l1_xyz, st))) return rc;
+    if ((rc = ancsh_fps_impl(B, m1, m2, l1_xyz, fps2, l2_xyz, st))) return rc;
+
+    // layer1
+    if ((rc = ancsh_ball_query_impl(B, N, m1, net->radius1, net->nsample1, P, l1_xyz, bidx1, bcnt1, st))) return rc;
+    {
+        SaArgs a{};
+        a.xyz = P; a.points = nullptr; a.new_xyz = l1_xyz; a.idx = bidx1; a.out = l1_points;
+        a.L[0] = net->sa1[0]; a.L[1] = net->sa1[1]; a.L[2] = net->sa1[2];
+        a.n = N; a.m = m1; a.S = net->nsample1; a.C = 0;
+        if ((rc = sa_launch<128>(a, B, st))) return rc;
+    }
+    // layer2
+    if ((rc = ancsh_ball_query_impl(B, m1, m2, net->radius2, net->nsample2, l1_xyz, l2_xyz, bidx2, bcnt2, st))) return rc;
+    {
+        SaArgs a{};
+        a.xyz = l1_xyz; a.points = l1_points; a.new_xyz = l2_xyz; a.idx = bidx2; a.out = l2_points;
+        a.L[0] = net->sa2[0]; a.L[1] = net->sa2[1]; a.L[2] = net->sa2[2];
+        a.n = m1; a.m = m2; a.S = net->nsample2; a.C = net->sa1[2].cout;
+        if ((rc = sa_launch<128>(a, B, st))) return rc;
+    }
+    // layer3 (group_all)
+    {
+        SaArgs a{};
+        a.xyz = l2_xyz; a.points = l2_points; a.new_xyz = nullptr; a.idx = nullptr; a.out = l3_points;
+        a.L[0] = net->sa3[0]; a.L[1] = net->sa3[1]; a.L[2] = net->sa3[2];
+        a.n = m2; a.m = 1; a.S = m2; a.C = net->sa2[2].cout;
+        if ((rc = sa_launch<64>(a, B, st))) return rc;
+    }
+    // fa_layer1
+    {
+        const ancsh_layer_t &G = net->fp1_global;
+        if (G.cin != net->sa3[2].cout || G.cout_pad != net->fp1[0].cout_pad) return ANCSH_ERR_INVALID_ARG;
+        cloud_bias_kernel<<<B, 256, G.cin * sizeof(float), st>>>(l3_points, G.cin, G.W, G.b, G.cout_pad, fp1_bias);
+        ANCSH_CHECK_LAUNCH();
+        FpArgs a{};
+        a.xyz1 = l2_xyz; a.xyz2 = nullptr; a.points2 = nullptr; a.skip = l2_points;
+        a.n1 = m2; a.m2 = 0; a.C2 = 0; a.C1 = net->sa2[2].cout;
+        a.L[0] = net->fp1[0]; a.L[1] = net->fp1[1]; a.nl = 2;
+        a.bias0 = fp1_bias; a.bias0_stride = G.cout_pad;
+        a.out = l2_fp;
+        if ((rc = fp_launch<64, false>(a, B, st))) return rc;
+    }
+    // fa_layer2
+    {
+        FpArgs a{};
+        a.xyz1 = l1_xyz; a.xyz2 = l2_xyz; a.points2 = l2_fp; a.skip = l1_points;
+        a.n1 = m1; a.m2 = m2; a.C2 = net->fp1[1].cout; a.C1 = net->sa1[2].cout;
+        a.L[0] = net->fp2[0]; a.L[1] = net->fp2[1]; a.nl = 2;
+        a.bias0 = net->fp2[0].b; a.bias0_stride = 0;
+        a.out = l1_fp;
+        if ((rc = fp_launch<64, false>(a, B, st))) return rc;
+    }
+    // fa_layer3 + fc1 + heads
+    {
+        FpArgs a{};
+        a.xyz1 = P; a.xyz2 = l1_xyz; a.points2 = l1_fp; a.skip = P;
+        a.n1 = N; a.m2 = m1; a.C2 = net->fp2[1].cout; a.C1 = 3;
+        a.L[0] = net->fp3[0]; a.L[1] = net->fp3[1]; a.L[2] = net->fp3[2]; a.nl = 3;
+        a.bias0 = net->fp3[0].b; a.bias0_stride = 0;
+        a.fc1 = net->fc1; a.nocs_heads = net->nocs_heads; a.fc3[0] = net->fc3[0]; a.fc3[1] = net->fc3[1];
+        a.joint_heads = net->joint_heads;
+        a.pred = *pred; a.K = net->n_parts; a.mixed = net->mixed_pred;
+        if ((rc = fp_launch<128, true>(a, B, st))) return rc;
+    }
+    return ANCSH_OK;
+}

@@ -1,0 +1,323 @@
+// ops.cu -- op-level kernels of the PointNet++ hot path (sm_100a): farthest point sampling, gather,
+// ball query, group, three_nn, three_interpolate.  Arithmetic contracts: SURVEY.md section 8(a).
+#include "common.cuh"
+#include "ops.cuh"
+
+// =====================================================================================================
+// Farthest point sampling.  Reference: tf_sampling_g.cu:105-170 (one 512-thread block per cloud, running
+// min-distance array in GLOBAL memory, shared-memory tree reduce, 2 barriers per tree level).
+// Here: one block per cloud, every point and its running min-distance live in REGISTERS (PPT points per
+// thread), the arg-max is two warp `redux.sync` ops plus one shared-memory exchange -> one __syncthreads
+// per round.  The reference's tie rule (smallest (k mod 512, k div 512) among equal maxima) is reproduced
+// exactly by reducing the pair (distance bits, tie key).
+// =====================================================================================================
+__device__ __forceinline__ uint32_t fps_tie_key(int k) { return ((uint32_t)(k & 511) << 20) | (uint32_t)(k >> 9); }
+__device__ __forceinline__ int fps_key_to_index(uint32_t key) { return (int)((key >> 20) | ((key & 0xFFFFFu) << 9)); }
+
+template <int NT, int PPT>
+__global__ void __launch_bounds__(NT) fps_kernel(int n, int m, const float *__restrict__ xyz, int *__restrict__ idx_out,
+                                                 float *__restrict__ new_xyz)
+{
+    extern __shared__ float s_xyz[];  // n*3 floats
+    __shared__ uint32_t s_val[2][NT / 32];
+    __shared__ uint32_t s_key[2][NT / 32];
+
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const float *p = xyz + (size_t)b * n * 3;
+
+    for (int i = tid; i < n * 3; i += NT) s_xyz[i] = p[i];
+    __syncthreads();
+
+    float px[PPT], py[PPT], pz[PPT], pd[PPT];
+    uint32_t pkey[PPT];
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+        int k = tid + i * NT;
+        bool v = k < n;
+        px[i] = v ? s_xyz[k * 3 + 0] : 0.f;
+        py[i] = v ? s_xyz[k * 3 + 1] : 0.f;
+        pz[i] = v ? s_xyz[k * 3 + 2] : 0.f;
+        pd[i] = 1e38f;                           // tf_sampling_g.cu:117-119
+        pkey[i] = v ? fps_tie_key(k) : 0xFFFFFFFFu;
+    }
+
+    int old = 0;
+    if (tid == 0) {
+        idx_out[(size_t)b * m] = 0;
+        if (new_xyz) {
+            new_xyz[((size_t)b * m) * 3 + 0] = s_xyz[0];
+            new_xyz[((size_t)b * m) * 3 + 1] = s_xyz[1];
+            new_xyz[((size_t)b * m) * 3 + 2] = s_xyz[2];
+        }
+    }
+    for (int j = 1; j < m; ++j) {
+        const float x1 = s_xyz[old * 3 + 0], y1 = s_xyz[old * 3 + 1], z1 = s_xyz[old * 3 + 2];
+        uint32_t bv = 0u, bk = 0xFFFFFFFFu;
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+            float dx = px[i] - x1, dy = py[i] - y1, dz = pz[i] - z1;
+            float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));   // SASS contract of :142
+            float d2 = fminf(d, pd[i]);
+            pd[i] = d2;
+            uint32_t u = __float_as_uint(d2);                                     // d2 >= 0: bits are monotone
+            bool valid = pkey[i] != 0xFFFFFFFFu;
+            bool better = valid && (!any || u > bv || (u == bv && pkey[i] < bk));
+            if (better) { bv = u; bk = pkey[i]; any = true; }
+        }
+        // warp arg-max of (bv, smallest bk)
+        uint32_t wv = __reduce_max_sync(0xFFFFFFFFu, any ? bv : 0u);
+        uint32_t wk = __reduce_min_sync(0xFFFFFFFFu, (any && bv == wv) ? bk : 0xFFFFFFFFu);
+        const int buf = j & 1;
+        if (lane == 0) { s_val[buf][warp] = wv; s_key[buf][warp] = wk; }
+        __syncthreads();
+        uint32_t fv = 0u, fk = 0xFFFFFFFFu;
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) {
+            uint32_t v = s_val[buf][w], k = s_key[buf][w];
+            if (k != 0xFFFFFFFFu && (fk == 0xFFFFFFFFu || v > fv || (v == fv && k < fk))) { fv = v; fk = k; }
+        }
+        old = fps_key_to_index(fk);
+        if (tid == 0) {
+            idx_out[(size_t)b * m + j] = old;
+            if (new_xyz) {
+                new_xyz[((size_t)b * m + j) * 3 + 0] = s_xyz[old * 3 + 0];
+                new_xyz[((size_t)b * m + j) * 3 + 1] = s_xyz[old * 3 + 1];
+                new_xyz[((size_t)b * m + j) * 3 + 2] = s_xyz[old * 3 + 2];
+            }
+        }
+    }
+}
+
+template <int NT, int PPT>
+static int fps_launch(int b, int n, int m, const float *xyz, int *idx, float *new_xyz, cudaStream_t st)
+{
+    size_t smem = (size_t)n * 3 * sizeof(float);
+    if (smem > 48 * 1024) {
+        if (cudaFuncSetAttribute(fps_kernel<NT, PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess)
+            return ANCSH_ERR_CUDA;
+    }
+    fps_kernel<NT, PPT><<<b, NT, smem, st>>>(n, m, xyz, idx, new_xyz);
+    ANCSH_CHECK_LAUNCH();
+    return ANCSH_OK;
+}
+
+int ancsh_fps_impl(int b, int n, int m, const float *xyz, int *idx, float *new_xyz, cudaStream_t st)
+{
+    if (b < 0 || n <= 0 || m < 0 || !xyz || !idx) return ANCSH_ERR_INVALID_ARG;
+    if (b == 0 || m == 0) return ANCSH_OK;
+    if (n <= 256) return fps_launch<128, 2>(b, n, m, xyz, idx, new_xyz, st);
+    if (n <= 512) return fps_launch<128, 4>(b, n, m, xyz, idx, new_xyz, st);
+    if (n <= 1024) return fps_launch<256, 4>(b, n, m, xyz, idx, new_xyz, st);
+    if (n <= 2048) return fps_launch<256, 8>(b, n, m, xyz, idx, new_xyz, st);
+    if (n <= 4096) return fps_launch<512, 8>(b, n, m, xyz, idx, new_xyz, st);
+    if (n <= 8192) return fps_launch<512, 16>(b, n, m, xyz, idx, new_xyz, st);
+    return ANCSH_ERR_UNSUPPORTED;
+}
+
+// =====================================================================================================
+// gather_point -- tf_sampling_g.cu:172-181
+// =====================================================================================================
+__global__ void gather_point_kernel(int n, int m, long total, const float *__restrict__ inp, const int *__restrict__ idx,
+                                    float *__restrict__ out)
+{
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;   // over b*m*3
+    if (t >= total) return;
+    long bj = t / 3;
+    int c = (int)(t - bj * 3);
+    long b = bj / m;
+    int a = idx[bj];
+    out[t] = inp[((size_t)b * n + a) * 3 + c];
+}
+
+// =====================================================================================================
+// query_ball_point -- tf_grouping_g.cu:3-36 (one 256-thread block per CLOUD, each thread serially scans all
+// n points for its centroids).  Here: one warp per centroid, 32 points per step, ordered compaction with
+// ballot + popc so the "first nsample in index order" contract stays bit-exact; warp-uniform early exit.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) ball_query_kernel(int n, int m, float radius, int nsample,
+                                                         const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                                                         int *__restrict__ idx, int *__restrict__ pts_cnt)
+{
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= m) return;
+    const float *p1 = xyz1 + (size_t)b * n * 3;
+    const float *c = xyz2 + ((size_t)b * m + j) * 3;
+    int *out = idx + ((size_t)b * m + j) * nsample;
+    const float x2 = __ldg(c + 0), y2 = __ldg(c + 1), z2 = __ldg(c + 2);
+    int cnt = 0, first = 0;
+    for (int base = 0; base < n; base += 32) {
+        int k = base + lane;
+        bool in = false;
+        if (k < n) {
+            float dx = x2 - __ldg(p1 + k * 3 + 0);
+            float dy = y2 - __ldg(p1 + k * 3 + 1);
+            float dz = z2 - __ldg(p1 + k * 3 + 2);
+            float d = __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))));   // :24 as compiled
+            d = fmaxf(d, 1e-20f);
+            in = d < radius;
+        }
+        unsigned mask = __ballot_sync(0xFFFFFFFFu, in);
+        if (mask) {
+            if (cnt == 0) first = base + __ffs(mask) - 1;
+            int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+            if (in && pos < nsample) out[pos] = k;
+            cnt += __popc(mask);
+            if (cnt >= nsample) break;
+        }
+    }
+    cnt = min(cnt, nsample);
+    for (int l = cnt + lane; l < nsample; l += 32) out[l] = first;   // :26-29 (first hit pads the row)
+    if (lane == 0 && pts_cnt) pts_cnt[(size_t)b * m + j] = cnt;
+}
+
+int ancsh_ball_query_impl(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2, int *idx,
+                          int *pts_cnt, cudaStream_t st)
+{
+    if (b < 0 || n <= 0 || m < 0 || nsample <= 0 || !xyz1 || !xyz2 || !idx) return ANCSH_ERR_INVALID_ARG;
+    if (b == 0 || m == 0) return ANCSH_OK;
+    if (b > 65535) return ANCSH_ERR_UNSUPPORTED;
+    dim3 grid(ancsh_cdiv(m, 8), b);
+    ball_query_kernel<<<grid, 256, 0, st>>>(n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt);
+    ANCSH_CHECK_LAUNCH();
+    return ANCSH_OK;
+}
+
+// =====================================================================================================
+// group_point -- tf_grouping_g.cu:40-57.  One warp per (centroid, sample) row, coalesced over channels.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) group_point_kernel(int n, int c, long rows_per_cloud, long total_rows,
+                                                          const float *__restrict__ points, const int *__restrict__ idx,
+                                                          float *__restrict__ out)
+{
+    long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= total_rows) return;
+    int lane = threadIdx.x & 31;
+    long b = row / rows_per_cloud;
+    int ii = __ldg(idx + row);
+    const float *src = points + ((size_t)b * n + ii) * c;
+    float *dst = out + (size_t)row * c;
+    for (int l = lane; l < c; l += 32) dst[l] = __ldg(src + l);
+}
+
+// =====================================================================================================
+// three_nn -- tf_interpolate.cpp:60-103 (a single CPU thread in the reference).  One thread per query,
+// known points staged through shared memory.  Un-fused f32 distance, strict '<' insertion chain.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) three_nn_kernel(int n, int m, const float *__restrict__ xyz1,
+                                                       const float *__restrict__ xyz2, float *__restrict__ dist,
+                                                       int *__restrict__ idx)
+{
+    __shared__ float s_k[512 * 3];
+    const int b = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const float *q = xyz1 + ((size_t)b * n + (j < n ? j : 0)) * 3;
+    const float x1 = q[0], y1 = q[1], z1 = q[2];
+    Best3 best;
+    best.init();
+    for (int base = 0; base < m; base += 512) {
+        int cnt = min(512, m - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt * 3; i += blockDim.x) s_k[i] = xyz2[((size_t)b * m + base) * 3 + i];
+        __syncthreads();
+        for (int k = 0; k < cnt; ++k)
+            best.insert(nn_dist_unfused(s_k[k * 3], s_k[k * 3 + 1], s_k[k * 3 + 2], x1, y1, z1), base + k);
+    }
+    if (j < n) {
+        size_t o = ((size_t)b * n + j) * 3;
+        dist[o + 0] = best.d1; dist[o + 1] = best.d2; dist[o + 2] = best.d3;
+        idx[o + 0] = best.i1; idx[o + 1] = best.i2; idx[o + 2] = best.i3;
+    }
+}
+
+// three_interpolate -- tf_interpolate.cpp:107-127 (f32, left-to-right, no fma)
+__global__ void __launch_bounds__(256) three_interp_kernel(int m, int c, long rows_per_cloud, long total_rows,
+                                                           const float *__restrict__ points, const int *__restrict__ idx,
+                                                           const float *__restrict__ weight, float *__restrict__ out)
+{
+    long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= total_rows) return;
+    int lane = threadIdx.x & 31;
+    long b = row / rows_per_cloud;
+    const float w1 = __ldg(weight + row * 3), w2 = __ldg(weight + row * 3 + 1), w3 = __ldg(weight + row * 3 + 2);
+    const float *p1 = points + ((size_t)b * m + __ldg(idx + row * 3 + 0)) * c;
+    const float *p2 = points + ((size_t)b * m + __ldg(idx + row * 3 + 1)) * c;
+    const float *p3 = points + ((size_t)b * m + __ldg(idx + row * 3 + 2)) * c;
+    float *dst = out + (size_t)row * c;
+    for (int l = lane; l < c; l += 32)
+        dst[l] = interp3_unfused(__ldg(p1 + l), __ldg(p2 + l), __ldg(p3 + l), w1, w2, w3);
+}
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+const char *ancsh_version(void) { return "ancsh_b200 0.1 sm_100a"; }
+
+int ancsh_fps(int b, int n, int m, const float *inp, float *temp, int *out, void *stream)
+{
+    (void)temp;
+    if (m > n && n > 0) { /* the reference happily re-picks points; so do we */ }
+    return ancsh_fps_impl(b, n, m, inp, out, nullptr, (cudaStream_t)stream);
+}
+
+int ancsh_gather_point(int b, int n, int m, const float *inp, const int *idx, float *out, void *stream)
+{
+    if (b < 0 || n <= 0 || m < 0 || !inp || !idx || !out) return ANCSH_ERR_INVALID_ARG;
+    long total = (long)b * m * 3;
+    if (total == 0) return ANCSH_OK;
+    gather_point_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, m, total, inp, idx, out);
+    ANCSH_CHECK_LAUNCH();
+    return ANCSH_OK;
+}
+
+int ancsh_ball_query(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2, int *idx,
+                     int *pts_cnt, void *stream)
+{
+    return ancsh_ball_query_impl(b, n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt, (cudaStream_t)stream);
+}
+
+int ancsh_group_point(int b, int n, int c, int m, int nsample, const float *points, const int *idx, float *out,
+                      void *stream)
+{
+    if (b < 0 || n <= 0 || c < 0 || m < 0 || nsample < 0 || !idx) return ANCSH_ERR_INVALID_ARG;
+    long rows = (long)b * m * nsample;
+    if (rows == 0 || c == 0) return ANCSH_OK;
+    if (!points || !out) return ANCSH_ERR_INVALID_ARG;
+    group_point_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(n, c, (long)m * nsample, rows, points,
+                                                                                      idx, out);
+    ANCSH_CHECK_LAUNCH();
+    return ANCSH_OK;
+}
+
+int ancsh_three_nn(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx, void *stream)
+{
+    if (b < 0 || n < 0 || m < 0 || !xyz1 || !xyz2 || !dist || !idx) return ANCSH_ERR_INVALID_ARG;
+    if (b == 0 || n == 0) return ANCSH_OK;
+    if (b > 65535) return ANCSH_ERR_UNSUPPORTED;
+    dim3 grid(ancsh_cdiv(n, 256), b);
+    three_nn_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, m, xyz1, xyz2, dist, idx);
+    ANCSH_CHECK_LAUNCH();
+    return ANCSH_OK;
+}
+
+int ancsh_three_interpolate(int b, int m, int c, int n, const float *points, const int *idx, const float *weight,
+                            float *out, void *stream)
+{
+    if (b < 0 || m <= 0 || c < 0 || n < 0 || !idx || !weight) return ANCSH_ERR_INVALID_ARG;
+    long rows = (long)b * n;
+    if (rows == 0 || c == 0) return ANCSH_OK;
+    if (!points || !out) return ANCSH_ERR_INVALID_ARG;
+    three_interp_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(m, c, (long)n, rows, points, idx,
+                                                                                       weight, out);
+    ANCSH_CHECK_LAUNCH();
+    return ANCSH_OK;
+}
+
+}  // extern "C"

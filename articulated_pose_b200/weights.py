@@ -1,0 +1,189 @@
+"""Weight import for the ANCSH network: TF variable names -> BN-folded, padded layer matrices.
+
+The import contract is the TF1 checkpoint's variable names:
+  scopes from pointnet_plusplus/utils/pointnet_util.py:128,234 and
+  pointnet_plusplus/architectures.py:65,70,75,79,82,86,90; variable names from
+  pointnet_plusplus/utils/tf_util.py:164,174 (`weights`, `biases`) and :527-531
+  (`bn/{beta,gamma,moving_mean,moving_variance}`); heads from lib/architecture.py:105-120,195-208.
+
+No pretrained checkpoint ships with the reference (README.md:95-105), so `synthetic_weights`
+provides seeded random variables of the right shapes for parity tests and benchmarks.
+"""
+from collections import OrderedDict
+
+import numpy as np
+
+BN_EPS = 1e-3  # tf.contrib.layers.batch_norm default, tf_util.py:527-531
+
+
+def variable_shapes(n_parts, mixed_pred=True, early_split_nocs=True, prefix="SPFN"):
+    """OrderedDict name -> shape of every variable the inference graph reads."""
+    K = n_parts
+    s = OrderedDict()
+
+    def conv(scope, shape, bn):
+        s[scope + "/weights"] = tuple(shape)
+        s[scope + "/biases"] = (shape[-1],)
+        if bn:
+            for v in ("beta", "gamma", "moving_mean", "moving_variance"):
+                s[scope + "/bn/" + v] = (shape[-1],)
+
+    e = prefix + "/est_net/"
+    for scope, dims in (("layer1", [3, 64, 64, 128]), ("layer2", [131, 128, 128, 256]),
+                        ("layer3", [259, 256, 512, 1024])):
+        for i in range(3):
+            conv("%s%s/conv%d" % (e, scope, i), [1, 1, dims[i], dims[i + 1]], True)
+    for scope, dims in (("fa_layer1", [1280, 256, 256]), ("fa_layer2", [384, 256, 128]),
+                        ("fa_layer3", [131, 128, 128, 128])):
+        for i in range(len(dims) - 1):
+            conv("%s%s/conv_%d" % (e, scope, i), [1, 1, dims[i], dims[i + 1]], True)
+    conv(e + "fc1", [1, 128, 128], True)
+
+    n = prefix + "/nocs_net/"
+    out_dims = [K, 3 * K] + ([K, 3 * K] if mixed_pred else []) + [1]      # lib/architecture.py:98-102
+    for i, d in enumerate(out_dims):
+        if early_split_nocs and i == 1:
+            conv(n + "fc11_1", [1, 128, 128], False)
+        conv(n + "fc2_%d" % i, [1, 128, d], False)
+
+    j = prefix + "/joint_net/"
+    conv(j + "fc3_0", [1, 128, 128], True)
+    conv(j + "fc3_1", [1, 128, 128], True)
+    for i, d in enumerate((3, 3, 1, 3)):                                   # n_max_parts=3 default, architecture.py:195
+        conv(j + "fc4_%d" % i, [1, 128, d], False)
+    return s
+
+
+def synthetic_weights(n_parts, mixed_pred=True, early_split_nocs=True, seed=7, prefix="SPFN"):
+    """Seeded variables: Xavier-uniform W, small biases, BN gamma~U(.5,1.5), beta~N(0,.1),
+    mean~N(0,.1), var~U(.5,1.5)."""
+    rng = np.random.default_rng(seed)
+    out = OrderedDict()
+    for name, shape in variable_shapes(n_parts, mixed_pred, early_split_nocs, prefix).items():
+        leaf = name.rsplit("/", 1)[-1]
+        if leaf == "weights":
+            fan_in, fan_out = shape[-2], shape[-1]
+            lim = np.sqrt(6.0 / (fan_in + fan_out))
+            v = rng.uniform(-lim, lim, size=shape)
+        elif leaf == "biases":
+            v = rng.normal(0.0, 0.05, size=shape)
+        elif leaf == "gamma":
+            v = rng.uniform(0.5, 1.5, size=shape)
+        elif leaf in ("beta", "moving_mean"):
+            v = rng.normal(0.0, 0.1, size=shape)
+        elif leaf == "moving_variance":
+            v = rng.uniform(0.5, 1.5, size=shape)
+        else:
+            raise AssertionError(name)
+        out[name] = v.astype(np.float32)
+    return out
+
+
+def _fold(weights, scope, bn):
+    """conv + bias (+ inference BN) -> (W[cin,cout], b[cout]) in float64."""
+    W = np.asarray(weights[scope + "/weights"], np.float64)
+    W = W.reshape(-1, W.shape[-1])
+    b = np.asarray(weights[scope + "/biases"], np.float64)
+    if bn:
+        g = np.asarray(weights[scope + "/bn/gamma"], np.float64)
+        beta = np.asarray(weights[scope + "/bn/beta"], np.float64)
+        mu = np.asarray(weights[scope + "/bn/moving_mean"], np.float64)
+        var = np.asarray(weights[scope + "/bn/moving_variance"], np.float64)
+        s = g / np.sqrt(var + BN_EPS)
+        W = W * s[None, :]
+        b = (b - mu) * s + beta
+    return W, b
+
+
+def _pad16(c):
+    return (c + 15) // 16 * 16
+
+
+def _pad_out(c):
+    return 64 if c <= 64 else (c + 127) // 128 * 128
+
+
+class PackedLayer:
+    def __init__(self, W, b, relu):
+        cin, cout = W.shape
+        self.cin, self.cout, self.relu = cin, cout, int(relu)
+        self.cin_pad, self.cout_pad = _pad16(cin), _pad_out(cout)
+        self.W = np.zeros((self.cin_pad, self.cout_pad), np.float32)
+        self.W[:cin, :cout] = W
+        self.b = np.zeros((self.cout_pad,), np.float32)
+        self.b[:cout] = b
+
+
+def pack_network(weights, n_parts, mixed_pred=True, early_split_nocs=True, prefix="SPFN"):
+    """Returns OrderedDict slot -> PackedLayer, slots named after the fields of ancsh_net_t
+    (include/ancsh_b200.h).  First-layer rows are permuted from the reference's [xyz, features]
+    (pointnet_util.py:57,84) to the kernels' [features, xyz]."""
+    K = n_parts
+    e = prefix + "/est_net/"
+    L = OrderedDict()
+
+    def xyz_last(W):
+        return np.concatenate([W[3:], W[:3]], axis=0)
+
+    for lvl, scope in ((1, "layer1"), (2, "layer2"), (3, "layer3")):
+        for i in range(3):
+            W, b = _fold(weights, "%s%s/conv%d" % (e, scope, i), True)
+            if i == 0:
+                W = xyz_last(W)
+            L["sa%d[%d]" % (lvl, i)] = PackedLayer(W, b, True)
+
+    W, b = _fold(weights, e + "fa_layer1/conv_0", True)
+    n_glob = L["sa3[2]"].cout                                   # interpolated part = global feature (1024)
+    L["fp1_global"] = PackedLayer(W[:n_glob], b, False)
+    L["fp1[0]"] = PackedLayer(W[n_glob:], np.zeros_like(b), True)   # bias comes per cloud from fp1_global
+    W, b = _fold(weights, e + "fa_layer1/conv_1", True)
+    L["fp1[1]"] = PackedLayer(W, b, True)
+    for i in range(2):
+        W, b = _fold(weights, e + "fa_layer2/conv_%d" % i, True)
+        L["fp2[%d]" % i] = PackedLayer(W, b, True)
+    for i in range(3):
+        W, b = _fold(weights, e + "fa_layer3/conv_%d" % i, True)
+        L["fp3[%d]" % i] = PackedLayer(W, b, True)
+    W, b = _fold(weights, e + "fc1", True)
+    L["fc1"] = PackedLayer(W, b, True)
+
+    n = prefix + "/nocs_net/"
+    out_dims = [K, 3 * K] + ([K, 3 * K] if mixed_pred else []) + [1]
+    Ws, bs = [], []
+    for i, _d in enumerate(out_dims):
+        W, b = _fold(weights, n + "fc2_%d" % i, False)
+        if early_split_nocs and i == 1:
+            # fc11_1 is linear (activation_fn=None, lib/architecture.py:112): fold the pair into one matrix
+            W1, b1 = _fold(weights, n + "fc11_1", False)
+            b = b1 @ W + b
+            W = W1 @ W
+        Ws.append(W)
+        bs.append(b)
+    L["nocs_heads"] = PackedLayer(np.concatenate(Ws, axis=1), np.concatenate(bs), False)
+
+    j = prefix + "/joint_net/"
+    for i in range(2):
+        W, b = _fold(weights, j + "fc3_%d" % i, True)
+        L["fc3[%d]" % i] = PackedLayer(W, b, True)
+    Ws, bs = zip(*[_fold(weights, j + "fc4_%d" % i, False) for i in range(4)])
+    L["joint_heads"] = PackedLayer(np.concatenate(Ws, axis=1), np.concatenate(bs), False)
+    return L
+
+
+def flatten_packed(layers):
+    """Lay all W/b arrays out in one f32 buffer with 256-byte aligned offsets.
+    Returns (flat float32 array, {slot: (w_offset_floats, b_offset_floats)})."""
+    off = 0
+    offs = {}
+    for slot, pl in layers.items():
+        wo = off
+        off = (off + pl.W.size + 63) // 64 * 64
+        bo = off
+        off = (off + pl.b.size + 63) // 64 * 64
+        offs[slot] = (wo, bo)
+    flat = np.zeros((off,), np.float32)
+    for slot, pl in layers.items():
+        wo, bo = offs[slot]
+        flat[wo:wo + pl.W.size] = pl.W.ravel()
+        flat[bo:bo + pl.b.size] = pl.b
+    return flat, offs

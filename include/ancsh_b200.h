@@ -1,0 +1,151 @@
+/*
+ * ancsh_b200.h -- C ABI of libancsh_b200.so: the B200 (sm_100a) implementation of the ANCSH
+ * per-point-cloud hot path (PointNet++ forward -> per-part RANSAC -> joint-constrained solve).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all memory;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); no call synchronises;
+ *   - dense row-major layouts identical to the reference's TF tensors, f32 / int32;
+ *   - return value: ANCSH_OK or a negative ANCSH_ERR_* (the reference's ops raise InvalidArgument via
+ *     OP_REQUIRES, tf_sampling.cpp:105, tf_grouping.cpp:79-84; its launchers never check CUDA errors);
+ *   - no global state: every entry point is re-entrant and may be called from several host threads on
+ *     different streams.
+ *
+ * Citations are relative to /root/reference (dragonlong/articulated-pose @ 267b70a4).
+ */
+#ifndef ANCSH_B200_H
+#define ANCSH_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ANCSH_OK 0
+#define ANCSH_ERR_INVALID_ARG (-1) /* shape / size constraint violated (reference: InvalidArgument) */
+#define ANCSH_ERR_CUDA (-2)        /* a CUDA runtime call or launch failed */
+#define ANCSH_ERR_UNSUPPORTED (-3) /* legal in the reference, outside what this build covers */
+#define ANCSH_ERR_WORKSPACE (-4)   /* workspace too small */
+
+/* library / build identification: returns e.g. "ancsh_b200 0.1 sm_100a" */
+const char *ancsh_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Op level -- one entry point per native op on the path.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Replaces farthestpointsamplingLauncher(int b,int n,int m,const float*inp,float*temp,int*out)
+ * (pointnet_plusplus/utils/tf_ops/sampling/tf_sampling_g.cu:203; Python: tf_sampling.py:48
+ * farthest_point_sample(npoint, inp)).  inp (b,n,3) -> out (b,m) int32.  `temp` is the reference's
+ * 32*n-float scratch; it is accepted for signature compatibility and ignored (may be NULL).
+ * Bit-exact with the reference kernel, including its tie rule.  n <= 8192. */
+int ancsh_fps(int b, int n, int m, const float *inp, float *temp, int *out, void *stream);
+
+/* Replaces gatherpointLauncher (tf_sampling_g.cu:206; tf_sampling.py:29 gather_point(inp, idx)).
+ * inp (b,n,3), idx (b,m) -> out (b,m,3). */
+int ancsh_gather_point(int b, int n, int m, const float *inp, const int *idx, float *out, void *stream);
+
+/* Replaces queryBallPointLauncher (tf_grouping_g.cu:125; tf_grouping.py:8
+ * query_ball_point(radius, nsample, xyz1, xyz2)).  xyz1 (b,n,3) dataset, xyz2 (b,m,3) centroids ->
+ * idx (b,m,nsample), pts_cnt (b,m).  First-nsample-in-index-order semantics, bit-exact.  Rows with no
+ * point in the ball (the reference leaves them uninitialised) are filled with 0. */
+int ancsh_ball_query(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2,
+                     int *idx, int *pts_cnt, void *stream);
+
+/* Replaces groupPointLauncher (tf_grouping_g.cu:133; tf_grouping.py:33 group_point(points, idx)).
+ * points (b,n,c), idx (b,m,nsample) -> out (b,m,nsample,c). */
+int ancsh_group_point(int b, int n, int c, int m, int nsample, const float *points, const int *idx, float *out,
+                      void *stream);
+
+/* Replaces threenn_cpu (3d_interpolation/tf_interpolate.cpp:60; tf_interpolate.py:8 three_nn(xyz1,xyz2)).
+ * xyz1 (b,n,3) queries, xyz2 (b,m,3) known -> dist (b,n,3) squared f32, idx (b,n,3).  Bit-exact
+ * (un-fused f32 distance, lowest index wins ties, missing neighbours = (inf, 0)). */
+int ancsh_three_nn(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx, void *stream);
+
+/* Replaces threeinterpolate_cpu (tf_interpolate.cpp:107; tf_interpolate.py:19
+ * three_interpolate(points, idx, weight)).  points (b,m,c), idx (b,n,3), weight (b,n,3) -> out (b,n,c). */
+int ancsh_three_interpolate(int b, int m, int c, int n, const float *points, const int *idx, const float *weight,
+                            float *out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Network level -- replaces sess.run(pred_dict) of lib/network.py:292 for the graph built by
+ * lib/architecture.py:86-161 (get_per_point_model_new) on pointnet_plusplus/architectures.py:56-95.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* One 1x1-conv layer with bias, inference batch-norm already folded in, zero padded:
+ *   W  [cin_pad][cout_pad] row-major (TF weights [1,1,cin,cout] are already [cin][cout]),
+ *   b  [cout_pad] (or [B][cout_pad] when bias_stride != 0: per-cloud bias, used by fa_layer1).
+ * cin_pad % 16 == 0, cout_pad == 64 or cout_pad % 128 == 0.  The host packer
+ * (articulated_pose_b200/weights.py) produces these from the TF variable names. */
+typedef struct {
+    const float *W;
+    const float *b;
+    int cin, cout, cin_pad, cout_pad;
+    int relu;
+} ancsh_layer_t;
+
+typedef struct {
+    int n_parts;    /* K = n_max_parts (eyeglasses 3, drawer 4) */
+    int mixed_pred; /* 1: ANCSH heads [K,3K,K,3K,1] (architecture.py:98-102); 0: NPCS heads [K,3K,1] */
+    int npoint1, nsample1;
+    float radius1; /* layer1: 512, 64, 0.2 (architectures.py:62-65) */
+    int npoint2, nsample2;
+    float radius2; /* layer2: 128, 64, 0.4 (architectures.py:67-70) */
+    /* channel order inside each first layer is [features..., xyz] (rows of W permuted by the packer;
+     * the reference concatenates [xyz, features], pointnet_util.py:57,84) */
+    ancsh_layer_t sa1[3], sa2[3], sa3[3];
+    ancsh_layer_t fp1_global; /* rows of fa_layer1/conv_0 that multiply the (broadcast) global feature */
+    ancsh_layer_t fp1[2];     /* fp1[0]: remaining rows (skip features) of conv_0; fp1[1]: conv_1 */
+    ancsh_layer_t fp2[2], fp3[3];
+    ancsh_layer_t fc1;
+    ancsh_layer_t nocs_heads;  /* 128 -> [W(K) | nocs(3K) | scale(K) | trans(3K) | confi(1)], fc11_1 folded */
+    ancsh_layer_t fc3[2];      /* joint_net/fc3_0, fc3_1 */
+    ancsh_layer_t joint_heads; /* 128 -> [joint_axis(3) | unitvec(3) | heatmap(1) | index(3)] */
+} ancsh_net_t;
+
+/* Output tensors of pred_dict (architecture.py:141-159), each (B,N,width) f32 dense.  gocs_per_point,
+ * global_scale, global_translation are written only when mixed_pred (may be NULL otherwise). */
+typedef struct {
+    float *W;                    /* (B,N,K)  softmax */
+    float *nocs_per_point;       /* (B,N,3K) sigmoid */
+    float *confi_per_point;      /* (B,N,1)  sigmoid */
+    float *heatmap_per_point;    /* (B,N,1)  sigmoid */
+    float *unitvec_per_point;    /* (B,N,3)  tanh */
+    float *joint_axis_per_point; /* (B,N,3)  tanh */
+    float *index_per_point;      /* (B,N,3)  softmax */
+    float *gocs_per_point;       /* (B,N,3K) nocs*scale+trans */
+    float *global_scale;         /* (B,N,K)  sigmoid */
+    float *global_translation;   /* (B,N,3K) tanh */
+} ancsh_pred_t;
+
+/* Byte offsets of the intermediates inside the caller-provided workspace (all 256-B aligned). */
+typedef struct {
+    size_t fps_idx1;  /* int32 (B,npoint1) */
+    size_t l1_xyz;    /* f32   (B,npoint1,3) */
+    size_t fps_idx2;  /* int32 (B,npoint2) */
+    size_t l2_xyz;    /* f32   (B,npoint2,3) */
+    size_t ball_idx1; /* int32 (B,npoint1,nsample1) */
+    size_t ball_cnt1; /* int32 (B,npoint1) */
+    size_t ball_idx2; /* int32 (B,npoint2,nsample2) */
+    size_t ball_cnt2; /* int32 (B,npoint2) */
+    size_t l1_points; /* f32 (B,npoint1,128)  layer1 output */
+    size_t l2_points; /* f32 (B,npoint2,256)  layer2 output */
+    size_t l3_points; /* f32 (B,1024)         layer3 output */
+    size_t fp1_bias;  /* f32 (B,256)          per-cloud bias of fa_layer1/conv_0 */
+    size_t l2_points_fp; /* f32 (B,npoint2,256) fa_layer1 output */
+    size_t l1_points_fp; /* f32 (B,npoint1,128) fa_layer2 output */
+    size_t total_bytes;
+} ancsh_ws_layout_t;
+
+/* Fills *layout for a batch of B clouds of N points.  N % 128 == 0 is required. */
+int ancsh_net_plan(const ancsh_net_t *net, int B, int N, ancsh_ws_layout_t *layout);
+
+/* Forward pass for B clouds: P (B,N,3) -> pred.  workspace must hold layout.total_bytes. */
+int ancsh_net_forward(const ancsh_net_t *net, int B, int N, const float *P, void *workspace, size_t workspace_bytes,
+                      const ancsh_pred_t *pred, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANCSH_B200_H */

@@ -1,0 +1,47 @@
+"""The C-ABI library loads and exports every symbol include/*.h declares (no compute calls: no GPU here)."""
+import ctypes
+import glob
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    syms = set()
+    for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        text = open(h).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        for m in re.finditer(r"^\s*(?:const\s+)?(?:int|char|void|size_t)\s*\*?\s*(ancsh_\w+)\s*\(", text, re.M):
+            syms.add(m.group(1))
+    return syms
+
+
+def test_header_symbols_exported():
+    lib = ctypes.CDLL(os.path.join(ROOT, "articulated_pose_b200", "libancsh_b200.so"))
+    syms = _declared_symbols()
+    assert len(syms) >= 9, syms
+    missing = [s for s in sorted(syms) if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_version_string():
+    from articulated_pose_b200 import _lib
+    assert b"sm_100a" in _lib.ancsh_version()
+
+
+def test_struct_sizes_match_header():
+    """ctypes mirrors must have the C layout (2 pointers + 5 ints, padded to 8)."""
+    from articulated_pose_b200 import _lib
+    assert ctypes.sizeof(_lib.Layer) == 40
+    assert ctypes.sizeof(_lib.Pred) == 80
+    assert ctypes.sizeof(_lib.WsLayout) == 15 * 8
+    assert ctypes.sizeof(_lib.Net) == 32 + 22 * 40
+
+
+def test_product_does_not_import_oracle():
+    """The product package must never route through the oracle (test infrastructure)."""
+    for py in glob.glob(os.path.join(ROOT, "articulated_pose_b200", "**", "*.py"), recursive=True):
+        src = open(py).read()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), py
+        assert "liboracle" not in src, py

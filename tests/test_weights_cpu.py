@@ -1,0 +1,51 @@
+import numpy as np
+
+from articulated_pose_b200 import weights as W
+
+
+def test_variable_inventory_matches_reference_graph():
+    # 1,465,187 scalars for K=3 (ANCSH heads)
+    shapes = W.variable_shapes(3)
+    assert sum(int(np.prod(s)) for s in shapes.values()) == 1465187
+    assert shapes["SPFN/est_net/layer2/conv0/weights"] == (1, 1, 131, 128)
+    assert shapes["SPFN/est_net/fa_layer1/conv_0/weights"] == (1, 1, 1280, 256)
+    assert shapes["SPFN/nocs_net/fc2_1/weights"] == (1, 128, 9)
+    assert shapes["SPFN/joint_net/fc4_3/weights"] == (1, 128, 3)
+    npcs = W.variable_shapes(3, mixed_pred=False, early_split_nocs=False)
+    assert "SPFN/nocs_net/fc11_1/weights" not in npcs and npcs["SPFN/nocs_net/fc2_2/weights"] == (1, 128, 1)
+
+
+def test_bn_fold_and_permutation():
+    w = W.synthetic_weights(3, seed=3)
+    L = W.pack_network(w, 3)
+    rng = np.random.default_rng(0)
+    # layer2/conv0: reference input order [xyz(3), feat(128)], packed order [feat(128), xyz(3)]
+    x_ref = rng.normal(size=(5, 131))
+    s = "SPFN/est_net/layer2/conv0"
+    y = x_ref @ w[s + "/weights"].reshape(131, 128).astype(np.float64) + w[s + "/biases"]
+    y = (y - w[s + "/bn/moving_mean"]) / np.sqrt(w[s + "/bn/moving_variance"].astype(np.float64) + 1e-3) \
+        * w[s + "/bn/gamma"] + w[s + "/bn/beta"]
+    pl = L["sa2[0]"]
+    x_pk = np.zeros((5, pl.cin_pad))
+    x_pk[:, :128] = x_ref[:, 3:]
+    x_pk[:, 128:131] = x_ref[:, :3]
+    y2 = x_pk @ pl.W.astype(np.float64) + pl.b
+    assert pl.cin_pad == 144 and pl.cout_pad == 128
+    np.testing.assert_allclose(y2[:, :128], y, rtol=1e-5, atol=1e-5)
+    # folded fc11_1 -> fc2_1
+    n = "SPFN/nocs_net/"
+    h = rng.normal(size=(4, 128))
+    mid = h @ w[n + "fc11_1/weights"].reshape(128, 128).astype(np.float64) + w[n + "fc11_1/biases"]
+    ref = mid @ w[n + "fc2_1/weights"].reshape(128, 9).astype(np.float64) + w[n + "fc2_1/biases"]
+    ph = L["nocs_heads"]
+    got = h @ ph.W.astype(np.float64) + ph.b
+    np.testing.assert_allclose(got[:, 3:12], ref, rtol=1e-5, atol=1e-5)
+    assert ph.cout == 8 * 3 + 1 and ph.cout_pad == 64
+
+
+def test_flatten_alignment():
+    L = W.pack_network(W.synthetic_weights(4), 4)
+    flat, offs = W.flatten_packed(L)
+    for slot, (wo, bo) in offs.items():
+        assert wo % 64 == 0 and bo % 64 == 0
+        np.testing.assert_array_equal(flat[wo:wo + L[slot].W.size], L[slot].W.ravel())
