@@ -80,4 +80,34 @@ ancsh_three_nn = _sig("ancsh_three_nn", [c_int, c_int, c_int, vp, vp, vp, vp, vp
 ancsh_three_interpolate = _sig("ancsh_three_interpolate", [c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp])
 ancsh_net_plan = _sig("ancsh_net_plan", [ctypes.POINTER(Net), c_int, c_int, ctypes.POINTER(WsLayout)])
 ancsh_net_forward = _sig("ancsh_net_forward", [ctypes.POINTER(Net), c_int, c_int, vp, vp, c_size_t,
-                                               ctypes.POINTER(Pred), vp])
+                                               ctypes.POINTER(Pred), ctypes.POINTER(vp), vp])
+ancsh_event_create = _sig("ancsh_event_create", [ctypes.POINTER(vp)])
+ancsh_event_record = _sig("ancsh_event_record", [vp, vp])
+ancsh_event_elapsed_ms = _sig("ancsh_event_elapsed_ms", [vp, vp, ctypes.POINTER(ctypes.c_float)])
+ancsh_event_destroy = _sig("ancsh_event_destroy", [vp])
+
+NET_STAGES = ("fps1", "fps2", "ball1", "sa1", "ball2", "sa2", "sa3", "fp1", "fp2", "fp3_heads")
+
+
+class EventList:
+    """n timing-enabled CUDA events owned through the C ABI."""
+
+    def __init__(self, n):
+        self.n = n
+        self.arr = (vp * n)()
+        for i in range(n):
+            e = vp()
+            check(ancsh_event_create(ctypes.byref(e)), "ancsh_event_create")
+            self.arr[i] = e.value
+
+    def elapsed_ms(self, i, j):
+        ms = ctypes.c_float()
+        check(ancsh_event_elapsed_ms(self.arr[i], self.arr[j], ctypes.byref(ms)), "ancsh_event_elapsed_ms")
+        return float(ms.value)
+
+    def __del__(self):
+        try:
+            for i in range(self.n):
+                ancsh_event_destroy(self.arr[i])
+        except Exception:
+            pass

@@ -372,7 +372,8 @@ extern "C" int ancsh_net_plan(const ancsh_net_t *net, int B, int N, ancsh_ws_lay
 }
 
 extern "C" int ancsh_net_forward(const ancsh_net_t *net, int B, int N, const float *P, void *workspace,
-                                 size_t workspace_bytes, const ancsh_pred_t *pred, void *stream)
+                                 size_t workspace_bytes, const ancsh_pred_t *pred, void *const *stage_events,
+                                 void *stream)
 {
     if (!net || !P || !workspace || !pred) return ANCSH_ERR_INVALID_ARG;
     if (B > 65535) return ANCSH_ERR_UNSUPPORTED;
@@ -390,13 +391,23 @@ extern "C" int ancsh_net_forward(const ancsh_net_t *net, int B, int N, const flo
     float *l3_points = (float *)(ws + L.l3_points), *fp1_bias = (float *)(ws + L.fp1_bias);
     float *l2_fp = (float *)(ws + L.l2_points_fp), *l1_fp = (float *)(ws + L.l1_points_fp);
     const int m1 = net->npoint1, m2 = net->npoint2;
+    int stage = 0;
+#define STAGE_MARK()                                                                        \
+    do {                                                                                    \
+        if (stage_events) ANCSH_CUDA(cudaEventRecord((cudaEvent_t)stage_events[stage], st)); \
+        ++stage;                                                                            \
+    } while (0)
 
     // sampling (pointnet_util.py:47) -- level 2 samples the level-1 centroids
+    STAGE_MARK();
     if ((rc = ancsh_fps_impl(B, N, m1, P, fps1, l1_xyz, st))) return rc;
+    STAGE_MARK();
     if ((rc = ancsh_fps_impl(B, m1, m2, l1_xyz, fps2, l2_xyz, st))) return rc;
+    STAGE_MARK();
 
     // layer1
     if ((rc = ancsh_ball_query_impl(B, N, m1, net->radius1, net->nsample1, P, l1_xyz, bidx1, bcnt1, st))) return rc;
+    STAGE_MARK();
     {
         SaArgs a{};
         a.xyz = P; a.points = nullptr; a.new_xyz = l1_xyz; a.idx = bidx1; a.out = l1_points;
@@ -405,7 +416,9 @@ extern "C" int ancsh_net_forward(const ancsh_net_t *net, int B, int N, const flo
         if ((rc = sa_launch<128>(a, B, st))) return rc;
     }
     // layer2
+    STAGE_MARK();
     if ((rc = ancsh_ball_query_impl(B, m1, m2, net->radius2, net->nsample2, l1_xyz, l2_xyz, bidx2, bcnt2, st))) return rc;
+    STAGE_MARK();
     {
         SaArgs a{};
         a.xyz = l1_xyz; a.points = l1_points; a.new_xyz = l2_xyz; a.idx = bidx2; a.out = l2_points;
@@ -414,6 +427,7 @@ extern "C" int ancsh_net_forward(const ancsh_net_t *net, int B, int N, const flo
         if ((rc = sa_launch<128>(a, B, st))) return rc;
     }
     // layer3 (group_all)
+    STAGE_MARK();
     {
         SaArgs a{};
         a.xyz = l2_xyz; a.points = l2_points; a.new_xyz = nullptr; a.idx = nullptr; a.out = l3_points;
@@ -422,6 +436,7 @@ extern "C" int ancsh_net_forward(const ancsh_net_t *net, int B, int N, const flo
         if ((rc = sa_launch<64>(a, B, st))) return rc;
     }
     // fa_layer1
+    STAGE_MARK();
     {
         const ancsh_layer_t &G = net->fp1_global;
         if (G.cin != net->sa3[2].cout || G.cout_pad != net->fp1[0].cout_pad) return ANCSH_ERR_INVALID_ARG;
@@ -436,6 +451,7 @@ extern "C" int ancsh_net_forward(const ancsh_net_t *net, int B, int N, const flo
         if ((rc = fp_launch<64, false>(a, B, st))) return rc;
     }
     // fa_layer2
+    STAGE_MARK();
     {
         FpArgs a{};
         a.xyz1 = l1_xyz; a.xyz2 = l2_xyz; a.points2 = l2_fp; a.skip = l1_points;
@@ -446,6 +462,7 @@ extern "C" int ancsh_net_forward(const ancsh_net_t *net, int B, int N, const flo
         if ((rc = fp_launch<64, false>(a, B, st))) return rc;
     }
     // fa_layer3 + fc1 + heads
+    STAGE_MARK();
     {
         FpArgs a{};
         a.xyz1 = P; a.xyz2 = l1_xyz; a.points2 = l1_fp; a.skip = P;
@@ -457,5 +474,32 @@ extern "C" int ancsh_net_forward(const ancsh_net_t *net, int B, int N, const flo
         a.pred = *pred; a.K = net->n_parts; a.mixed = net->mixed_pred;
         if ((rc = fp_launch<128, true>(a, B, st))) return rc;
     }
+    STAGE_MARK();
+#undef STAGE_MARK
+    return ANCSH_OK;
+}
+
+extern "C" int ancsh_event_create(void **event_out)
+{
+    if (!event_out) return ANCSH_ERR_INVALID_ARG;
+    cudaEvent_t e;
+    ANCSH_CUDA(cudaEventCreate(&e));
+    *event_out = (void *)e;
+    return ANCSH_OK;
+}
+extern "C" int ancsh_event_record(void *event, void *stream)
+{
+    ANCSH_CUDA(cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream));
+    return ANCSH_OK;
+}
+extern "C" int ancsh_event_elapsed_ms(void *start, void *stop, float *ms_out)
+{
+    if (!ms_out) return ANCSH_ERR_INVALID_ARG;
+    ANCSH_CUDA(cudaEventElapsedTime(ms_out, (cudaEvent_t)start, (cudaEvent_t)stop));
+    return ANCSH_OK;
+}
+extern "C" int ancsh_event_destroy(void *event)
+{
+    ANCSH_CUDA(cudaEventDestroy((cudaEvent_t)event));
     return ANCSH_OK;
 }

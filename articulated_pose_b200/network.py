@@ -99,8 +99,9 @@ class AncshNet:
             out[k] = torch.empty((B, N, _PRED_WIDTH[k](K)), dtype=torch.float32, device=self.device)
         return out
 
-    def forward_device(self, P, out=None):
-        """P: CUDA f32 (B,N,3).  Launches on torch's current stream; returns dict of CUDA tensors."""
+    def forward_device(self, P, out=None, stage_events=None):
+        """P: CUDA f32 (B,N,3).  Launches on torch's current stream; returns dict of CUDA tensors.
+        stage_events: optional _lib.EventList(len(_lib.NET_STAGES)+1) recorded around each stage."""
         if P.dtype != torch.float32 or P.dim() != 3 or P.shape[2] != 3 or not P.is_cuda:
             raise ValueError("P must be a CUDA float32 tensor of shape (B,N,3)")
         P = P.contiguous()
@@ -112,13 +113,15 @@ class AncshNet:
         for k in _lib.PRED_FIELDS:
             setattr(pred, k, out[k].data_ptr() if k in out else None)
         rc = _lib.ancsh_net_forward(ctypes.byref(self._net), B, N, P.data_ptr(), ws.data_ptr(), lay.total_bytes,
-                                    ctypes.byref(pred), torch.cuda.current_stream().cuda_stream)
+                                    ctypes.byref(pred), stage_events.arr if stage_events is not None else None,
+                                    torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "ancsh_net_forward")
         self.last_workspace = (ws, lay, B)
         return out
 
-    def forward(self, P):
-        """P: host ndarray (B,N,3) -> dict of host ndarrays (f32), like sess.run(pred_dict)."""
+    def forward(self, P, copy=True):
+        """P: host ndarray (B,N,3) -> dict of host ndarrays (f32), like sess.run(pred_dict).
+        copy=False returns views of the pinned staging buffers (overwritten by the next call)."""
         P = np.ascontiguousarray(P, dtype=np.float32)
         B, N, _ = P.shape
         key = (B, N)
@@ -136,7 +139,7 @@ class AncshNet:
             for k, v in dev_out.items():
                 hout[k].copy_(v, non_blocking=True)
             torch.cuda.current_stream().synchronize()
-        return {k: v.numpy().copy() for k, v in hout.items()}
+        return {k: (v.numpy().copy() if copy else v.numpy()) for k, v in hout.items()}
 
     def intermediates(self):
         """Views of the last forward's workspace (indices and per-level features), for parity tests."""

@@ -141,9 +141,23 @@ typedef struct {
 /* Fills *layout for a batch of B clouds of N points.  N % 128 == 0 is required. */
 int ancsh_net_plan(const ancsh_net_t *net, int B, int N, ancsh_ws_layout_t *layout);
 
-/* Forward pass for B clouds: P (B,N,3) -> pred.  workspace must hold layout.total_bytes. */
+/* Stages of ancsh_net_forward, in launch order (for per-stage CUDA-event timing). */
+enum {
+    ANCSH_STAGE_FPS1 = 0, ANCSH_STAGE_FPS2, ANCSH_STAGE_BALL1, ANCSH_STAGE_SA1, ANCSH_STAGE_BALL2, ANCSH_STAGE_SA2,
+    ANCSH_STAGE_SA3, ANCSH_STAGE_FP1, ANCSH_STAGE_FP2, ANCSH_STAGE_FP3_HEADS, ANCSH_NET_NSTAGES
+};
+
+/* Forward pass for B clouds: P (B,N,3) -> pred.  workspace must hold layout.total_bytes.
+ * stage_events: NULL, or ANCSH_NET_NSTAGES+1 cudaEvent_t handles (ancsh_event_create); event i is recorded on
+ * `stream` before stage i and the last one after the final stage, so stage i took elapsed(ev[i], ev[i+1]). */
 int ancsh_net_forward(const ancsh_net_t *net, int B, int N, const float *P, void *workspace, size_t workspace_bytes,
-                      const ancsh_pred_t *pred, void *stream);
+                      const ancsh_pred_t *pred, void *const *stage_events, void *stream);
+
+/* Timing-enabled CUDA events for callers that have no CUDA runtime binding of their own. */
+int ancsh_event_create(void **event_out);
+int ancsh_event_record(void *event, void *stream);
+int ancsh_event_elapsed_ms(void *start, void *stop, float *ms_out); /* both events must have completed */
+int ancsh_event_destroy(void *event);
 
 #ifdef __cplusplus
 }

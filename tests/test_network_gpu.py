@@ -1,0 +1,82 @@
+"""Parity of the fused network forward (C ABI: ancsh_net_forward) against the CPU oracle on the same
+seeded clouds and weights.
+
+Bars:  FPS / ball-query / three_nn indices: bit-exact.
+       floats: |gpu - oracle| <= 1e-4 * max(|oracle|, 1e-2)   (north_star: 1e-4 relative; the absolute floor
+       covers tanh/NOCS values near zero).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+RTOL, FLOOR = 1e-4, 1e-2
+
+
+def assert_close(got, ref, name):
+    err = np.abs(got.astype(np.float64) - ref.astype(np.float64)) / np.maximum(np.abs(ref.astype(np.float64)), FLOOR)
+    assert np.isfinite(got).all(), name
+    assert err.max() <= RTOL, "%s: max rel err %.3e at %s" % (name, err.max(), np.unravel_index(err.argmax(), err.shape))
+
+
+CASES = [
+    # category, K, B, nsample, mixed(ANCSH) / NPCS
+    ("eyeglasses", 3, 4, 64, True),
+    ("eyeglasses", 3, 3, 32, True),
+    ("eyeglasses", 3, 2, 64, False),
+    ("drawer", 4, 2, 64, True),
+]
+
+
+@pytest.mark.parametrize("cat,K,B,ns,mixed", CASES)
+def test_forward_matches_oracle(cat, K, B, ns, mixed):
+    from articulated_pose_b200 import synthetic, weights
+    from articulated_pose_b200.network import AncshNet
+    from oracle import pnpp
+    P, _ = synthetic.make_batch(range(10, 10 + B), cat)
+    if B > 2:
+        P[1, P.shape[1] // 2:] = P[1, :P.shape[1] // 2]          # a tiled cloud (duplicate points, ties)
+    w = weights.synthetic_weights(K, mixed, mixed, seed=7 if mixed else 8)
+    net = AncshNet(w, K, mixed_pred=mixed, early_split_nocs=mixed, nsample=ns)
+    got = net.forward(P)
+    tr = {}
+    ref = pnpp.forward(P, w, K, nsample=ns, mixed_pred=mixed, early_split_nocs=mixed, trace=tr)
+    inter = {k: v.cpu().numpy() for k, v in net.intermediates().items()}
+    e = "SPFN/est_net/"
+    np.testing.assert_array_equal(inter["fps_idx1"], tr[e + "layer1/fps_idx"])
+    np.testing.assert_array_equal(inter["fps_idx2"], tr[e + "layer2/fps_idx"])
+    np.testing.assert_array_equal(inter["ball_idx1"], tr[e + "layer1/ball_idx"])
+    np.testing.assert_array_equal(inter["ball_idx2"], tr[e + "layer2/ball_idx"])
+    np.testing.assert_array_equal(inter["ball_cnt1"], tr[e + "layer1/pts_cnt"])
+    np.testing.assert_array_equal(inter["l1_xyz"], tr["l1_xyz"])
+    assert_close(inter["l3_points"], tr["l3_points"][:, 0], "l3_points")
+    assert_close(inter["l2_points_fp"], tr["l2_points"], "l2_points(fa_layer1)")
+    assert_close(inter["l1_points_fp"], tr["l1_points"], "l1_points(fa_layer2)")
+    assert set(got.keys()) == set(ref.keys())
+    for k in ref:
+        assert got[k].shape == ref[k].shape and got[k].dtype == np.float32, k
+        assert_close(got[k], ref[k], k)
+
+
+def test_forward_is_deterministic_and_batch_invariant():
+    from articulated_pose_b200 import synthetic, weights
+    from articulated_pose_b200.network import AncshNet
+    P, _ = synthetic.make_batch(range(5))
+    net = AncshNet(weights.synthetic_weights(3), 3, nsample=32)
+    a = net.forward(P)
+    b = net.forward(P)
+    c = net.forward(P[2:3])
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k])
+        np.testing.assert_array_equal(a[k][2:3], c[k])
+
+
+def test_rejects_unsupported_shapes():
+    from articulated_pose_b200 import _lib, weights
+    from articulated_pose_b200.network import AncshNet
+    net = AncshNet(weights.synthetic_weights(3), 3)
+    with pytest.raises(_lib.AncshError):
+        net.forward(np.zeros((1, 1000, 3), np.float32))       # N % 128 != 0
+    with pytest.raises(ValueError):
+        net.forward_device(torch.zeros((1, 1024, 4), device="cuda"))
