@@ -95,7 +95,7 @@ template <int NT, int PPT>
 static int fps_launch(int b, int n, int m, const float *xyz, int *idx, float *new_xyz, cudaStream_t st)
 {
     size_t smem = (size_t)n * 3 * sizeof(float);
-    if (smem > 48 * 1024) {
+    if (smem > 40 * 1024) {   // static shared memory counts against the 48 KB default limit too
         if (cudaFuncSetAttribute(fps_kernel<NT, PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
             cudaSuccess)
             return ANCSH_ERR_CUDA;
