@@ -86,6 +86,39 @@ ancsh_event_record = _sig("ancsh_event_record", [vp, vp])
 ancsh_event_elapsed_ms = _sig("ancsh_event_elapsed_ms", [vp, vp, ctypes.POINTER(ctypes.c_float)])
 ancsh_event_destroy = _sig("ancsh_event_destroy", [vp])
 
+
+
+class PoseCfg(ctypes.Structure):
+    _fields_ = [("n_parts", c_int), ("niter_single", c_int), ("niter_joint", c_int), ("inlier_th", ctypes.c_double),
+                ("seed", ctypes.c_ulonglong)]
+
+
+POSE_IN_FIELDS = ("P", "nocs", "mask", "joint_axis", "joint_cls", "idx_single", "idx_joint0", "idx_joint1")
+POSE_OUT_FIELDS = ("single_R", "single_s", "single_t", "single_score", "single_inliers", "joint_R0", "joint_s0",
+                   "joint_t0", "joint_R1", "joint_s1", "joint_t1", "joint_score", "joint_inliers0", "joint_inliers1",
+                   "part_count", "status")
+POSE_WS_FIELDS = ("part_idx", "part_src", "part_tgt", "axis_med", "single_scores", "joint_scores", "single_best",
+                  "joint_best", "total_bytes")
+
+
+class PoseIn(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_void_p) for k in POSE_IN_FIELDS]
+
+
+class PoseOut(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_void_p) for k in POSE_OUT_FIELDS]
+
+
+class PoseWs(ctypes.Structure):
+    _fields_ = [(k, c_size_t) for k in POSE_WS_FIELDS]
+
+
+ancsh_pose_plan = _sig("ancsh_pose_plan", [ctypes.POINTER(PoseCfg), c_int, c_int, ctypes.POINTER(PoseWs)])
+ancsh_pose_solve = _sig("ancsh_pose_solve", [ctypes.POINTER(PoseCfg), ctypes.POINTER(PoseIn), c_int, c_int, vp, c_size_t,
+                                             ctypes.POINTER(PoseOut), vp])
+ancsh_pose_sample_indices = _sig("ancsh_pose_sample_indices", [ctypes.c_ulonglong, c_int, c_int, c_int, vp, vp, vp])
+ancsh_umeyama = _sig("ancsh_umeyama", [c_int, c_int, vp, vp, vp, vp, vp, vp, vp])
+
 NET_STAGES = ("fps1", "fps2", "ball1", "sa1", "ball2", "sa2", "sa3", "fp1", "fp2", "fp3_heads")
 
 

@@ -1,0 +1,788 @@
+// pose.cu -- per-part RANSAC + joint-constrained nonlinear solve on the GPU (f64 on the FP64 pipe).
+//
+//   partition_kernel       argmax part labels, ordered per-part point lists, per-joint median axis
+//                          (evaluation/parallel_ancsh_pose.py:238-247, 259-260, 295)
+//   single_score_kernel    one thread per hypothesis: 3-point Kabsch/scale/translation + inlier count over the
+//                          part's points staged in shared memory as f64            (:35-54)
+//   single_refit_kernel    first-max hypothesis, its inlier mask, refit on the inliers incl. the O(n^2)
+//                          pairwise-distance scale                                   (:28-32, d3_utils.py:223-246)
+//   joint_score_kernel     one thread per hypothesis: 3+3 samples, MINPACK-lmder LM (pose_math.cuh), score (:106-194)
+//   joint_refit_kernel     first-max hypothesis, masks, block-cooperative LM refit on all inliers
+//   umeyama_kernel         lib/aligning.py:580-622 (GT poses, compute_gt_pose.py:87)
+#include "common.cuh"
+#include "pose_math.cuh"
+
+namespace {
+
+constexpr int RT = 256;   // threads of the cooperative kernels
+
+// ------------------------------------------------------------------------------------------------
+// block reduction of NV doubles per thread (fixed order -> deterministic); result broadcast to all threads
+// ------------------------------------------------------------------------------------------------
+template <int NV, int NTH>
+__device__ void block_sum(double *v, double *s_red)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 1
+    for (int k = 0; k < NV; ++k) {
+        double x = v[k];
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xFFFFFFFFu, x, off);
+        if (lane == 0) s_red[warp * NV + k] = x;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int k = 0; k < NV; ++k) {
+        double x = 0.0;
+        for (int w = 0; w < NTH / 32; ++w) x += s_red[w * NV + k];
+        v[k] = x;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ bool is_inlier(const double *R, double s, const double *t, const double *src, const double *tgt,
+                                          double th2)
+{
+    // res = target - scale * (R @ source) - translation ; sqrt(sum(res^2)) < th   (parallel_ancsh_pose.py:51-52)
+    double rs[3];
+    pm::matvec3(R, src, rs);
+    const double r0 = tgt[0] - s * rs[0] - t[0];
+    const double r1 = tgt[1] - s * rs[1] - t[1];
+    const double r2 = tgt[2] - s * rs[2] - t[2];
+    return (r0 * r0 + r1 * r1) + r2 * r2 < th2;
+}
+
+// ================================================================================================
+// partition
+// ================================================================================================
+struct PartitionArgs {
+    const float *P, *nocs, *mask, *joint_axis;
+    const int *joint_cls;
+    int N, K;
+    int *part_idx;
+    float *part_src, *part_tgt;
+    double *axis_med;
+    int *part_count;
+};
+
+__global__ void __launch_bounds__(RT) partition_kernel(const PartitionArgs a)
+{
+    extern __shared__ unsigned char s_raw[];
+    const int N = a.N, K = a.K, b = blockIdx.x, tid = threadIdx.x;
+    int npow2 = 1;
+    while (npow2 < N) npow2 <<= 1;
+    unsigned char *s_label = s_raw;                                      // N
+    int *s_cnt = reinterpret_cast<int *>(s_raw + ((N + 15) & ~15));      // RT * 8
+    float *s_val = reinterpret_cast<float *>(s_cnt + RT * 8);            // 3 * npow2
+    __shared__ int s_tot[8];
+    __shared__ int s_nj;
+
+    // labels = argmax(mask, axis=1), first maximum (np.argmax) -- parallel_ancsh_pose.py:238
+    for (int i = tid; i < N; i += RT) {
+        const float *m = a.mask + ((size_t)b * N + i) * K;
+        int best = 0;
+        float bv = m[0];
+        for (int k = 1; k < K; ++k)
+            if (m[k] > bv) { bv = m[k]; best = k; }
+        s_label[i] = (unsigned char)best;
+    }
+    __syncthreads();
+    // ordered compaction per part: each thread owns a contiguous chunk of points
+    const int chunk = (N + RT - 1) / RT;
+    const int i0 = tid * chunk, i1 = min(N, i0 + chunk);
+    int cnt[8];
+    for (int k = 0; k < 8; ++k) cnt[k] = 0;
+    for (int i = i0; i < i1; ++i) cnt[s_label[i]]++;
+    for (int k = 0; k < 8; ++k) s_cnt[k * RT + tid] = cnt[k];
+    __syncthreads();
+    if (tid < K) {                      // exclusive scan per part (RT entries, serial: tiny)
+        int run = 0;
+        for (int t = 0; t < RT; ++t) { int c = s_cnt[tid * RT + t]; s_cnt[tid * RT + t] = run; run += c; }
+        s_tot[tid] = run;
+        a.part_count[(size_t)b * K + tid] = run;
+    }
+    __syncthreads();
+    int pos[8];
+    for (int k = 0; k < 8; ++k) pos[k] = s_cnt[k * RT + tid];
+    for (int i = i0; i < i1; ++i) {
+        const int j = s_label[i];
+        const size_t o = ((size_t)b * K + j) * N + pos[j]++;
+        a.part_idx[o] = i;
+        const float *np_ = a.nocs + ((size_t)b * N + i) * 3 * K + 3 * j;      // nocs_pred[partidx[j], 3j:3j+3], :259
+        const float *pp = a.P + ((size_t)b * N + i) * 3;
+        a.part_src[o * 3 + 0] = np_[0]; a.part_src[o * 3 + 1] = np_[1]; a.part_src[o * 3 + 2] = np_[2];
+        a.part_tgt[o * 3 + 0] = pp[0]; a.part_tgt[o * 3 + 1] = pp[1]; a.part_tgt[o * 3 + 2] = pp[2];
+    }
+    // per-joint median of the predicted axis over the points with joint_cls == j (:295)
+    for (int j = 1; j < K; ++j) {
+        __syncthreads();
+        if (tid == 0) s_nj = 0;
+        for (int i = tid; i < 3 * npow2; i += RT) s_val[i] = __int_as_float(0x7f800000);   // +inf padding
+        __syncthreads();
+        for (int i = tid; i < N; i += RT) {
+            if (a.joint_cls[(size_t)b * N + i] == j) {
+                const int p = atomicAdd(&s_nj, 1);          // order is irrelevant: the values get sorted
+                const float *ax = a.joint_axis + ((size_t)b * N + i) * 3;
+                s_val[p] = ax[0]; s_val[npow2 + p] = ax[1]; s_val[2 * npow2 + p] = ax[2];
+            }
+        }
+        __syncthreads();
+        const int nj = s_nj;
+        for (int k = 2; k <= npow2; k <<= 1)
+            for (int jj = k >> 1; jj > 0; jj >>= 1) {
+                for (int t = tid; t < 3 * npow2; t += RT) {
+                    const int c = t / npow2, i = t - c * npow2, ixj = i ^ jj;
+                    if (ixj > i) {
+                        float *v = s_val + c * npow2;
+                        const bool up = (i & k) == 0;
+                        const float x = v[i], y = v[ixj];
+                        if ((x > y) == up) { v[i] = y; v[ixj] = x; }
+                    }
+                }
+                __syncthreads();
+            }
+        if (tid < 3) {
+            const float *v = s_val + tid * npow2;
+            double med;
+            if (nj == 0) med = nan("");
+            else if (nj & 1) med = (double)v[nj / 2];
+            else med = ((double)v[nj / 2 - 1] + (double)v[nj / 2]) / 2.0;
+            a.axis_med[((size_t)b * (K - 1) + (j - 1)) * 3 + tid] = med;
+        }
+    }
+}
+
+// ================================================================================================
+// single-part RANSAC
+// ================================================================================================
+struct SingleArgs {
+    const float *part_src, *part_tgt;   // (nprob, N, 3)
+    const int *part_count;              // (nprob)
+    const int *idx;                     // NULL or (nprob, niter, 3)
+    int *scores;                        // (nprob, niter)
+    int *best;                          // (nprob)
+    int N, niter;
+    double th2;
+    unsigned long long seed;
+    // refit outputs
+    double *R, *s, *t;
+    int *score_out;
+    unsigned char *inliers;
+    int *status;
+};
+
+__device__ __forceinline__ void load_part_f64(const float *src, const float *tgt, int n, double *s_src, double *s_tgt)
+{
+    for (int i = threadIdx.x; i < n * 3; i += blockDim.x) { s_src[i] = (double)src[i]; s_tgt[i] = (double)tgt[i]; }
+}
+
+__device__ __forceinline__ void fetch_sample(const int *idx, unsigned long long seed, unsigned prob, unsigned hyp,
+                                             unsigned stream, int niter, int n, int *out)
+{
+    if (idx) {
+        const int *p = idx + ((size_t)prob * niter + hyp) * 3;
+        for (int i = 0; i < 3; ++i) out[i] = min(max(p[i], 0), n - 1);
+    } else {
+        pm::sample3(seed, prob, hyp, stream, n, out);
+    }
+}
+
+__global__ void __launch_bounds__(RT, 2) single_score_kernel(const SingleArgs a)
+{
+    extern __shared__ double s_pts[];
+    const int prob = blockIdx.y;
+    const int n = a.part_count[prob];
+    double *s_src = s_pts, *s_tgt = s_pts + (size_t)a.N * 3;
+    const int h = blockIdx.x * RT + threadIdx.x;
+    if (n <= 0) {
+        if (h < a.niter) a.scores[(size_t)prob * a.niter + h] = 0;
+        return;
+    }
+    load_part_f64(a.part_src + (size_t)prob * a.N * 3, a.part_tgt + (size_t)prob * a.N * 3, n, s_src, s_tgt);
+    __syncthreads();
+    if (h >= a.niter) return;
+    int id[3];
+    fetch_sample(a.idx, a.seed, prob, h, 0u, a.niter, n, id);
+    double S[9], T[9], R[9], sc, t[3];
+    for (int i = 0; i < 3; ++i)
+        for (int c = 0; c < 3; ++c) { S[3 * i + c] = s_src[3 * id[i] + c]; T[3 * i + c] = s_tgt[3 * id[i] + c]; }
+    pm::transform3(S, T, R, &sc, t);
+    int cnt = 0;
+    for (int i = 0; i < n; ++i) cnt += is_inlier(R, sc, t, s_src + 3 * i, s_tgt + 3 * i, a.th2) ? 1 : 0;
+    a.scores[(size_t)prob * a.niter + h] = cnt;
+}
+
+// first maximum of an int score array (ransac keeps the FIRST best: strict '>' at parallel_ancsh_pose.py:28)
+__device__ int block_first_argmax_int(const int *scores, int n, unsigned long long *s_key)
+{
+    unsigned long long best = 0ull;
+    for (int h = threadIdx.x; h < n; h += RT) {
+        const unsigned long long key = ((unsigned long long)(unsigned)(scores[h] + 1) << 32) | (unsigned)(0xFFFFFFFFu - (unsigned)h);
+        best = key > best ? key : best;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long o = __shfl_down_sync(0xFFFFFFFFu, best, off);
+        best = o > best ? o : best;
+    }
+    if ((threadIdx.x & 31) == 0) s_key[threadIdx.x >> 5] = best;
+    __syncthreads();
+    best = 0ull;
+    for (int w = 0; w < RT / 32; ++w) best = s_key[w] > best ? s_key[w] : best;
+    __syncthreads();
+    return (int)(0xFFFFFFFFu - (unsigned)(best & 0xFFFFFFFFull));
+}
+
+__global__ void __launch_bounds__(RT) single_refit_kernel(const SingleArgs a)
+{
+    extern __shared__ double s_pts[];
+    __shared__ double s_red[(RT / 32) * 16];
+    __shared__ unsigned long long s_key[RT / 32];
+    __shared__ double s_model[13];
+    const int prob = blockIdx.x, tid = threadIdx.x;
+    const int n = a.part_count[prob];
+    double *s_src = s_pts, *s_tgt = s_pts + (size_t)a.N * 3;
+    unsigned char *s_inl = reinterpret_cast<unsigned char *>(s_pts + (size_t)a.N * 6);
+    unsigned char *g_inl = a.inliers + (size_t)prob * a.N;
+    double *oR = a.R + (size_t)prob * 9, *ot = a.t + (size_t)prob * 3;
+    if (n <= 0) {
+        for (int i = tid; i < a.N; i += RT) g_inl[i] = 0;
+        if (tid == 0) {
+            for (int i = 0; i < 9; ++i) oR[i] = nan("");
+            for (int i = 0; i < 3; ++i) ot[i] = nan("");
+            a.s[prob] = nan("");
+            a.score_out[prob] = 0;
+            a.best[prob] = -1;
+            a.status[prob] |= ANCSH_POSE_EMPTY_PART;
+        }
+        return;
+    }
+    load_part_f64(a.part_src + (size_t)prob * a.N * 3, a.part_tgt + (size_t)prob * a.N * 3, n, s_src, s_tgt);
+    const int hbest = block_first_argmax_int(a.scores + (size_t)prob * a.niter, a.niter, s_key);   // syncs inside
+    if (tid == 0) {
+        int id[3];
+        fetch_sample(a.idx, a.seed, prob, hbest, 0u, a.niter, n, id);
+        double S[9], T[9];
+        for (int i = 0; i < 3; ++i)
+            for (int c = 0; c < 3; ++c) { S[3 * i + c] = s_src[3 * id[i] + c]; T[3 * i + c] = s_tgt[3 * id[i] + c]; }
+        pm::transform3(S, T, s_model, s_model + 9, s_model + 10);
+        a.best[prob] = hbest;
+    }
+    __syncthreads();
+    // inlier mask of the best hypothesis + sums over the inliers
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int i = tid; i < a.N; i += RT) {
+        unsigned char in = 0;
+        if (i < n) {
+            in = is_inlier(s_model, s_model[9], s_model + 10, s_src + 3 * i, s_tgt + 3 * i, a.th2) ? 1 : 0;
+            s_inl[i] = in;
+            if (in) {
+                for (int c = 0; c < 3; ++c) { acc[c] += s_src[3 * i + c]; acc[3 + c] += s_tgt[3 * i + c]; }
+                acc[6] += 1.0;
+            }
+        }
+        g_inl[i] = in;
+    }
+    block_sum<7, RT>(acc, s_red);
+    const int nin = (int)acc[6];
+    if (nin == 0) {
+        if (tid == 0) {
+            for (int i = 0; i < 9; ++i) oR[i] = nan("");
+            for (int i = 0; i < 3; ++i) ot[i] = nan("");
+            a.s[prob] = nan("");
+            a.score_out[prob] = 0;
+            a.status[prob] |= ANCSH_POSE_NO_INLIERS;
+        }
+        return;
+    }
+    double ms[3], mt[3];
+    for (int c = 0; c < 3; ++c) { ms[c] = acc[c] / nin; mt[c] = acc[3 + c] / nin; }
+    // centre in place (transform_pts, d3_utils.py:226-227)
+    for (int i = tid; i < n; i += RT)
+        for (int c = 0; c < 3; ++c) { s_src[3 * i + c] -= ms[c]; s_tgt[3 * i + c] -= mt[c]; }
+    __syncthreads();
+    // M = target_c^T source_c (9) and the pairwise sums of scale_pts over unordered inlier pairs (2)
+    double v[11];
+    for (int k = 0; k < 11; ++k) v[k] = 0.0;
+    for (int i = tid; i < n; i += RT) {
+        if (!s_inl[i]) continue;
+        const double *si = s_src + 3 * i, *ti = s_tgt + 3 * i;
+        for (int p = 0; p < 3; ++p)
+            for (int q = 0; q < 3; ++q) v[3 * p + q] += ti[p] * si[q];
+        for (int j = i + 1; j < n; ++j) {
+            if (!s_inl[j]) continue;
+            const double *sj = s_src + 3 * j, *tj = s_tgt + 3 * j;
+            const double d0 = si[0] - sj[0], d1 = si[1] - sj[1], d2 = si[2] - sj[2];
+            const double e0 = ti[0] - tj[0], e1 = ti[1] - tj[1], e2 = ti[2] - tj[2];
+            const double A2 = d0 * d0 + d1 * d1 + d2 * d2, B2 = e0 * e0 + e1 * e1 + e2 * e2;
+            v[9] += sqrt(A2) * sqrt(B2);
+            v[10] += A2;
+        }
+    }
+    block_sum<11, RT>(v, s_red);
+    if (tid == 0) {
+        double R[9];
+        pm::kabsch_rotation(v, R);
+        const double scale = (2.0 * v[9]) / (2.0 * v[10] + 1e-6);           // all ordered pairs, d3_utils.py:241-245
+        double rs[3];
+        pm::matvec3(R, ms, rs);
+        for (int i = 0; i < 9; ++i) oR[i] = R[i];
+        a.s[prob] = scale;
+        for (int c = 0; c < 3; ++c) ot[c] = mt[c] - scale * rs[c];          // mean(target - s R source), :233
+        a.score_out[prob] = nin;
+    }
+}
+
+// ================================================================================================
+// joint RANSAC
+// ================================================================================================
+struct JointArgs {
+    const float *part_src, *part_tgt;   // (nparts_total, N, 3)
+    const int *part_count;              // (nparts_total)
+    const double *axis_med;             // (nprob, 3)
+    const int *idx0, *idx1;             // NULL or (nprob, niter, 3)
+    double *scores;                     // (nprob, niter)
+    int *best;                          // (nprob)
+    int N, K, niter;
+    double th2;
+    unsigned long long seed;
+    // refit outputs (nprob, ...)
+    double *R0, *s0, *t0, *R1, *s1, *t1, *score_out;
+    unsigned char *inl0, *inl1;
+    int *status;                        // (B,K)
+};
+
+// problem p = b*(K-1) + (j-1) couples part (b,0) with part (b,j)
+__device__ __forceinline__ void joint_parts(int prob, int K, int &pa, int &pb)
+{
+    const int b = prob / (K - 1), j = prob - b * (K - 1) + 1;
+    pa = b * K;
+    pb = b * K + j;
+}
+
+constexpr int JT = 64;   // threads per block of the joint scoring kernel (one LM solve per thread)
+
+__global__ void __launch_bounds__(JT) joint_score_kernel(const JointArgs a)
+{
+    extern __shared__ double s_pts[];
+    const int prob = blockIdx.y;
+    int pa, pb;
+    joint_parts(prob, a.K, pa, pb);
+    const int n0 = a.part_count[pa], n1 = a.part_count[pb];
+    const int h = blockIdx.x * JT + threadIdx.x;
+    if (n0 <= 0 || n1 <= 0) {
+        if (h < a.niter) a.scores[(size_t)prob * a.niter + h] = 0.0;
+        return;
+    }
+    double *s_src0 = s_pts, *s_tgt0 = s_src0 + 3 * n0, *s_src1 = s_tgt0 + 3 * n0, *s_tgt1 = s_src1 + 3 * n1;
+    load_part_f64(a.part_src + (size_t)pa * a.N * 3, a.part_tgt + (size_t)pa * a.N * 3, n0, s_src0, s_tgt0);
+    load_part_f64(a.part_src + (size_t)pb * a.N * 3, a.part_tgt + (size_t)pb * a.N * 3, n1, s_src1, s_tgt1);
+    __syncthreads();
+    if (h >= a.niter) return;
+    int i0[3], i1[3];
+    fetch_sample(a.idx0, a.seed, prob, h, 1u, a.niter, n0, i0);
+    fetch_sample(a.idx1, a.seed, prob, h, 2u, a.niter, n1, i1);
+    double S0[9], T0[9], S1[9], T1[9];
+    for (int i = 0; i < 3; ++i)
+        for (int c = 0; c < 3; ++c) {
+            S0[3 * i + c] = s_src0[3 * i0[i] + c]; T0[3 * i + c] = s_tgt0[3 * i0[i] + c];
+            S1[3 * i + c] = s_src1[3 * i1[i] + c]; T1[3 * i + c] = s_tgt1[3 * i1[i] + c];
+        }
+    pm::JointModel m;
+    pm::joint_estimate3(S0, T0, S1, T1, a.axis_med + (size_t)prob * 3, m);
+    int c0 = 0, c1 = 0;
+    for (int i = 0; i < n0; ++i) c0 += is_inlier(m.R0, m.s0, m.t0, s_src0 + 3 * i, s_tgt0 + 3 * i, a.th2) ? 1 : 0;
+    for (int i = 0; i < n1; ++i) c1 += is_inlier(m.R1, m.s1, m.t1, s_src1 + 3 * i, s_tgt1 + 3 * i, a.th2) ? 1 : 0;
+    // score = (sum(inl0)/res0.shape[0] + sum(inl1)/res1.shape[0]) / 2 with shape[0] == 3   (:193)
+    a.scores[(size_t)prob * a.niter + h] = ((double)c0 / 3.0 + (double)c1 / 3.0) / 2.0;
+}
+
+// block-cooperative evaluator of objective_eval over the masked (inlier) points in shared memory
+struct BlockProb {
+    const double *x0, *y0, *x1, *y1;
+    const unsigned char *m0, *m1;
+    int n0, n1;
+    double u[3];
+    double nj;
+    double *s_red;
+    __host__ __device__ double cost(const double *p) const
+    {
+#ifdef __CUDA_ARCH__
+        pm::RotVec r0, r1;
+        r0.set(p);
+        r1.set(p + 3);
+        double fsq[1] = {0.0};
+        for (int i = threadIdx.x; i < n0; i += RT)
+            if (m0[i]) pm::accum_part(r0, 0, x0 + 3 * i, y0 + 3 * i, nullptr, fsq[0]);
+        for (int i = threadIdx.x; i < n1; i += RT)
+            if (m1[i]) pm::accum_part(r1, 1, x1 + 3 * i, y1 + 3 * i, nullptr, fsq[0]);
+        if (threadIdx.x == 0) pm::accum_joint(r0, r1, u, nj, nullptr, fsq[0]);
+        block_sum<1, RT>(fsq, s_red);
+        return fsq[0];
+#else
+        return 0.0;
+#endif
+    }
+    __host__ __device__ void normal(const double *p, pm::Normal6 &N) const
+    {
+#ifdef __CUDA_ARCH__
+        pm::RotVec r0, r1;
+        r0.set(p);
+        r1.set(p + 3);
+        N.zero();
+        double fsq = 0.0;
+        for (int i = threadIdx.x; i < n0; i += RT)
+            if (m0[i]) pm::accum_part(r0, 0, x0 + 3 * i, y0 + 3 * i, &N, fsq);
+        for (int i = threadIdx.x; i < n1; i += RT)
+            if (m1[i]) pm::accum_part(r1, 1, x1 + 3 * i, y1 + 3 * i, &N, fsq);
+        if (threadIdx.x == 0) pm::accum_joint(r0, r1, u, nj, &N, fsq);
+        N.fsq = fsq;
+        block_sum<43, RT>(N.JtJ, s_red);     // JtJ[36], Jtf[6], fsq are contiguous in Normal6
+#endif
+    }
+};
+static_assert(sizeof(pm::Normal6) == 43 * sizeof(double), "Normal6 must be 43 contiguous doubles");
+
+__device__ int block_first_argmax_f64(const double *scores, int n, double *s_val, int *s_idx)
+{
+    double bv = -1.0;
+    int bi = 0x7FFFFFFF;
+    for (int h = threadIdx.x; h < n; h += RT) {
+        const double v = scores[h];
+        if (v > bv) { bv = v; bi = h; }       // ascending h per thread: strict '>' keeps the first
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_down_sync(0xFFFFFFFFu, bv, off);
+        const int oi = __shfl_down_sync(0xFFFFFFFFu, bi, off);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_val[threadIdx.x >> 5] = bv; s_idx[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    bv = -1.0; bi = 0x7FFFFFFF;
+    for (int w = 0; w < RT / 32; ++w)
+        if (s_val[w] > bv || (s_val[w] == bv && s_idx[w] < bi)) { bv = s_val[w]; bi = s_idx[w]; }
+    __syncthreads();
+    return bi;
+}
+
+__global__ void __launch_bounds__(RT) joint_refit_kernel(const JointArgs a)
+{
+    extern __shared__ double s_pts[];
+    __shared__ double s_red[(RT / 32) * 43];
+    __shared__ double s_val[RT / 32];
+    __shared__ int s_idx[RT / 32];
+    __shared__ pm::JointModel s_model;
+    const int prob = blockIdx.x, tid = threadIdx.x;
+    int pa, pb;
+    joint_parts(prob, a.K, pa, pb);
+    const int n0 = a.part_count[pa], n1 = a.part_count[pb];
+    const int jpart = pb - pa;
+    unsigned char *g0 = a.inl0 + (size_t)prob * a.N, *g1 = a.inl1 + (size_t)prob * a.N;
+    auto write_nan = [&](int flag) {
+        if (tid == 0) {
+            for (int i = 0; i < 9; ++i) { a.R0[(size_t)prob * 9 + i] = nan(""); a.R1[(size_t)prob * 9 + i] = nan(""); }
+            for (int i = 0; i < 3; ++i) { a.t0[(size_t)prob * 3 + i] = nan(""); a.t1[(size_t)prob * 3 + i] = nan(""); }
+            a.s0[prob] = nan(""); a.s1[prob] = nan("");
+            a.status[pa + jpart] |= flag;
+        }
+    };
+    if (n0 <= 0 || n1 <= 0) {
+        for (int i = tid; i < a.N; i += RT) { g0[i] = 0; g1[i] = 0; }
+        if (tid == 0) { a.best[prob] = -1; a.score_out[prob] = 0.0; }
+        write_nan(ANCSH_POSE_EMPTY_PART);
+        return;
+    }
+    double *s_src0 = s_pts, *s_tgt0 = s_src0 + 3 * n0, *s_src1 = s_tgt0 + 3 * n0, *s_tgt1 = s_src1 + 3 * n1;
+    unsigned char *s_m0 = reinterpret_cast<unsigned char *>(s_tgt1 + 3 * n1), *s_m1 = s_m0 + n0;
+    load_part_f64(a.part_src + (size_t)pa * a.N * 3, a.part_tgt + (size_t)pa * a.N * 3, n0, s_src0, s_tgt0);
+    load_part_f64(a.part_src + (size_t)pb * a.N * 3, a.part_tgt + (size_t)pb * a.N * 3, n1, s_src1, s_tgt1);
+    const double *axis = a.axis_med + (size_t)prob * 3;
+    const int hbest = block_first_argmax_f64(a.scores + (size_t)prob * a.niter, a.niter, s_val, s_idx);   // syncs
+    if (tid == 0) {
+        int i0[3], i1[3];
+        fetch_sample(a.idx0, a.seed, prob, hbest, 1u, a.niter, n0, i0);
+        fetch_sample(a.idx1, a.seed, prob, hbest, 2u, a.niter, n1, i1);
+        double S0[9], T0[9], S1[9], T1[9];
+        for (int i = 0; i < 3; ++i)
+            for (int c = 0; c < 3; ++c) {
+                S0[3 * i + c] = s_src0[3 * i0[i] + c]; T0[3 * i + c] = s_tgt0[3 * i0[i] + c];
+                S1[3 * i + c] = s_src1[3 * i1[i] + c]; T1[3 * i + c] = s_tgt1[3 * i1[i] + c];
+            }
+        pm::joint_estimate3(S0, T0, S1, T1, axis, s_model);
+        a.best[prob] = hbest;
+        a.score_out[prob] = a.scores[(size_t)prob * a.niter + hbest];
+    }
+    __syncthreads();
+    // masks of the best hypothesis and the sums needed for centring: sum S, sum T, count per part
+    double acc[14];
+    for (int k = 0; k < 14; ++k) acc[k] = 0.0;
+    for (int i = tid; i < a.N; i += RT) {
+        unsigned char in = 0;
+        if (i < n0) {
+            in = is_inlier(s_model.R0, s_model.s0, s_model.t0, s_src0 + 3 * i, s_tgt0 + 3 * i, a.th2) ? 1 : 0;
+            s_m0[i] = in;
+            if (in) { for (int c = 0; c < 3; ++c) { acc[c] += s_src0[3 * i + c]; acc[3 + c] += s_tgt0[3 * i + c]; } acc[6] += 1.0; }
+        }
+        g0[i] = in;
+        in = 0;
+        if (i < n1) {
+            in = is_inlier(s_model.R1, s_model.s1, s_model.t1, s_src1 + 3 * i, s_tgt1 + 3 * i, a.th2) ? 1 : 0;
+            s_m1[i] = in;
+            if (in) { for (int c = 0; c < 3; ++c) { acc[7 + c] += s_src1[3 * i + c]; acc[10 + c] += s_tgt1[3 * i + c]; } acc[13] += 1.0; }
+        }
+        g1[i] = in;
+    }
+    block_sum<14, RT>(acc, s_red);
+    const int nin0 = (int)acc[6], nin1 = (int)acc[13];
+    if (nin0 == 0 || nin1 == 0) { write_nan(ANCSH_POSE_NO_INLIERS); return; }
+    double mS0[3], mT0[3], mS1[3], mT1[3];
+    for (int c = 0; c < 3; ++c) {
+        mS0[c] = acc[c] / nin0; mT0[c] = acc[3 + c] / nin0;
+        mS1[c] = acc[7 + c] / nin1; mT1[c] = acc[10 + c] / nin1;
+    }
+    // scale_pts(S,T) and scale_pts(T,S) over the inliers of each part (:121-124): pairwise sums
+    double pw[6];
+    for (int k = 0; k < 6; ++k) pw[k] = 0.0;
+    for (int part = 0; part < 2; ++part) {
+        const double *S = part ? s_src1 : s_src0, *T = part ? s_tgt1 : s_tgt0;
+        const unsigned char *mk = part ? s_m1 : s_m0;
+        const int n = part ? n1 : n0;
+        double ab = 0.0, aa = 0.0, bb = 0.0;
+        for (int i = tid; i < n; i += RT) {
+            if (!mk[i]) continue;
+            const double *si = S + 3 * i, *ti = T + 3 * i;
+            for (int j = i + 1; j < n; ++j) {
+                if (!mk[j]) continue;
+                const double *sj = S + 3 * j, *tj = T + 3 * j;
+                const double d0 = si[0] - sj[0], d1 = si[1] - sj[1], d2 = si[2] - sj[2];
+                const double e0 = ti[0] - tj[0], e1 = ti[1] - tj[1], e2 = ti[2] - tj[2];
+                const double A2 = d0 * d0 + d1 * d1 + d2 * d2, B2 = e0 * e0 + e1 * e1 + e2 * e2;
+                ab += sqrt(A2) * sqrt(B2); aa += A2; bb += B2;
+            }
+        }
+        pw[3 * part] = ab; pw[3 * part + 1] = aa; pw[3 * part + 2] = bb;
+    }
+    block_sum<6, RT>(pw, s_red);
+    const double sc0 = 2.0 * pw[0] / (2.0 * pw[1] + 1e-6), sinv0 = 2.0 * pw[0] / (2.0 * pw[2] + 1e-6);
+    const double sc1 = 2.0 * pw[3] / (2.0 * pw[4] + 1e-6), sinv1 = 2.0 * pw[3] / (2.0 * pw[5] + 1e-6);
+    // centre / pre-scale in place (:126-132): x = S - mean(S); y = sinv*T - mean(sinv*T)
+    for (int i = tid; i < n0; i += RT)
+        for (int c = 0; c < 3; ++c) { s_src0[3 * i + c] -= mS0[c]; s_tgt0[3 * i + c] = sinv0 * s_tgt0[3 * i + c] - sinv0 * mT0[c]; }
+    for (int i = tid; i < n1; i += RT)
+        for (int c = 0; c < 3; ++c) { s_src1[3 * i + c] -= mS1[c]; s_tgt1[3 * i + c] = sinv1 * s_tgt1[3 * i + c] - sinv1 * mT1[c]; }
+    __syncthreads();
+    // Kabsch initialisation (:138-139)
+    double M[18];
+    for (int k = 0; k < 18; ++k) M[k] = 0.0;
+    for (int i = tid; i < n0; i += RT)
+        if (s_m0[i])
+            for (int p = 0; p < 3; ++p)
+                for (int q = 0; q < 3; ++q) M[3 * p + q] += s_tgt0[3 * i + p] * s_src0[3 * i + q];
+    for (int i = tid; i < n1; i += RT)
+        if (s_m1[i])
+            for (int p = 0; p < 3; ++p)
+                for (int q = 0; q < 3; ++q) M[9 + 3 * p + q] += s_tgt1[3 * i + p] * s_src1[3 * i + q];
+    block_sum<18, RT>(M, s_red);
+    double R0[9], R1[9], x[6];
+    pm::kabsch_rotation(M, R0);
+    pm::kabsch_rotation(M + 9, R1);
+    pm::matrix_to_rotvec(R0, x);
+    pm::matrix_to_rotvec(R1, x + 3);
+    BlockProb P;
+    P.x0 = s_src0; P.y0 = s_tgt0; P.x1 = s_src1; P.y1 = s_tgt1; P.m0 = s_m0; P.m1 = s_m1; P.n0 = n0; P.n1 = n1;
+    P.u[0] = axis[0]; P.u[1] = axis[1]; P.u[2] = axis[2];
+    P.nj = (double)min(nin0, nin1);
+    P.s_red = s_red;
+    pm::lm_solve(P, x, 1e-4, 1e-8, 1e-8, 600, 100.0);            // uniform control flow: every thread sees the same sums
+    if (tid == 0) {
+        pm::rotvec_to_matrix(x, R0);
+        pm::rotvec_to_matrix(x + 3, R1);
+        double rs[3];
+        for (int i = 0; i < 9; ++i) { a.R0[(size_t)prob * 9 + i] = R0[i]; a.R1[(size_t)prob * 9 + i] = R1[i]; }
+        a.s0[prob] = sc0; a.s1[prob] = sc1;
+        pm::matvec3(R0, mS0, rs);
+        for (int c = 0; c < 3; ++c) a.t0[(size_t)prob * 3 + c] = mT0[c] - sc0 * rs[c];     // :174
+        pm::matvec3(R1, mS1, rs);
+        for (int c = 0; c < 3; ++c) a.t1[(size_t)prob * 3 + c] = mT1[c] - sc1 * rs[c];     // :175
+    }
+}
+
+// ================================================================================================
+// Umeyama (lib/aligning.py:580-622)
+// ================================================================================================
+__global__ void __launch_bounds__(RT) umeyama_kernel(int nmax, const float *__restrict__ src, const float *__restrict__ tgt,
+                                                     const int *__restrict__ cnt, double *scale, double *Rout, double *tout)
+{
+    __shared__ double s_red[(RT / 32) * 16];
+    const int prob = blockIdx.x, tid = threadIdx.x;
+    const int n = cnt[prob];
+    const float *S = src + (size_t)prob * nmax * 3, *T = tgt + (size_t)prob * nmax * 3;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = tid; i < n; i += RT)
+        for (int c = 0; c < 3; ++c) { acc[c] += (double)S[3 * i + c]; acc[3 + c] += (double)T[3 * i + c]; }
+    block_sum<6, RT>(acc, s_red);
+    if (n <= 0) {
+        if (tid == 0) {
+            scale[prob] = nan("");
+            for (int i = 0; i < 9; ++i) Rout[(size_t)prob * 9 + i] = nan("");
+            for (int i = 0; i < 3; ++i) tout[(size_t)prob * 3 + i] = nan("");
+        }
+        return;
+    }
+    double ms[3], mt[3];
+    for (int c = 0; c < 3; ++c) { ms[c] = acc[c] / n; mt[c] = acc[3 + c] / n; }
+    double v[12];
+    for (int k = 0; k < 12; ++k) v[k] = 0.0;
+    for (int i = tid; i < n; i += RT) {
+        double sc[3], tc[3];
+        for (int c = 0; c < 3; ++c) { sc[c] = (double)S[3 * i + c] - ms[c]; tc[c] = (double)T[3 * i + c] - mt[c]; }
+        for (int p = 0; p < 3; ++p)
+            for (int q = 0; q < 3; ++q) v[3 * p + q] += tc[p] * sc[q];        // CovMatrix = T_c S_c^T / n
+        for (int c = 0; c < 3; ++c) v[9 + c] += sc[c] * sc[c];               // np.var(Source, axis=1) * n
+    }
+    block_sum<12, RT>(v, s_red);
+    if (tid == 0) {
+        double C[9], R[9], sv[3];
+        for (int i = 0; i < 9; ++i) C[i] = v[i] / n;
+        pm::kabsch_rotation(C, R);                 // U Vh with the reflection fix
+        pm::singular_values3(C, sv);
+        double dsum = sv[0] + sv[1] + sv[2];
+        if (pm::det3(C) < 0.0) dsum -= 2.0 * sv[2];     // D[-1] = -D[-1] when det(U)det(Vh) < 0  (:599-601)
+        const double varP = (v[9] + v[10] + v[11]) / n;
+        const double sf = 1.0 / varP * dsum;
+        scale[prob] = sf;
+        // Rotation = (U Vh)^T (:606); Translation = T_mean - S_mean . (sf * Rotation)  (:613)
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) Rout[(size_t)prob * 9 + 3 * i + j] = R[3 * j + i];
+        for (int j = 0; j < 3; ++j) {
+            double d = 0.0;
+            for (int i = 0; i < 3; ++i) d += ms[i] * sf * R[3 * j + i];      // (S_mean . Rot)[j] = sum_i S_mean[i] Rot[i][j]
+            tout[(size_t)prob * 3 + j] = mt[j] - d;
+        }
+    }
+}
+
+__global__ void sample_indices_kernel(unsigned long long seed, int stream_id, int nprob, int niter, const int *n_per,
+                                      int *idx)
+{
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long)nprob * niter) return;
+    const int prob = (int)(t / niter), h = (int)(t - (long)prob * niter);
+    int out[3] = {0, 0, 0};
+    if (n_per[prob] > 0) pm::sample3(seed, (unsigned)prob, (unsigned)h, (unsigned)stream_id, n_per[prob], out);
+    idx[t * 3 + 0] = out[0]; idx[t * 3 + 1] = out[1]; idx[t * 3 + 2] = out[2];
+}
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+extern "C" int ancsh_pose_plan(const ancsh_pose_cfg_t *cfg, int B, int N, ancsh_pose_ws_t *L)
+{
+    if (!cfg || !L || B <= 0 || N <= 0) return ANCSH_ERR_INVALID_ARG;
+    const size_t K = cfg->n_parts, b = B, n = N;
+    if (K < 1 || K > 8 || N > 4096 || cfg->niter_single < 1 || cfg->niter_joint < 1) return ANCSH_ERR_UNSUPPORTED;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align256(off + bytes); return o; };
+    L->part_idx = take(b * K * n * 4);
+    L->part_src = take(b * K * n * 3 * 4);
+    L->part_tgt = take(b * K * n * 3 * 4);
+    L->axis_med = take(b * (K > 1 ? K - 1 : 1) * 3 * 8);
+    L->single_scores = take(b * K * (size_t)cfg->niter_single * 4);
+    L->joint_scores = take(b * (K > 1 ? K - 1 : 1) * (size_t)cfg->niter_joint * 8);
+    L->single_best = take(b * K * 4);
+    L->joint_best = take(b * (K > 1 ? K - 1 : 1) * 4);
+    L->total_bytes = off;
+    return ANCSH_OK;
+}
+
+extern "C" int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in_t *in, int B, int N, void *workspace,
+                                size_t workspace_bytes, const ancsh_pose_out_t *out, void *stream)
+{
+    if (!cfg || !in || !out || !workspace) return ANCSH_ERR_INVALID_ARG;
+    if (!in->P || !in->nocs || !in->mask) return ANCSH_ERR_INVALID_ARG;
+    ancsh_pose_ws_t L;
+    int rc = ancsh_pose_plan(cfg, B, N, &L);
+    if (rc) return rc;
+    if (workspace_bytes < L.total_bytes) return ANCSH_ERR_WORKSPACE;
+    const int K = cfg->n_parts;
+    if (K > 1 && (!in->joint_axis || !in->joint_cls)) return ANCSH_ERR_INVALID_ARG;
+    if ((long)B * K > 65535) return ANCSH_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)workspace;
+    int *part_idx = (int *)(ws + L.part_idx);
+    float *part_src = (float *)(ws + L.part_src), *part_tgt = (float *)(ws + L.part_tgt);
+    double *axis_med = (double *)(ws + L.axis_med);
+    int *single_scores = (int *)(ws + L.single_scores);
+    double *joint_scores = (double *)(ws + L.joint_scores);
+    int *single_best = (int *)(ws + L.single_best), *joint_best = (int *)(ws + L.joint_best);
+
+    ANCSH_CUDA(cudaMemsetAsync(out->status, 0, (size_t)B * K * sizeof(int), st));
+    {
+        PartitionArgs a{in->P, in->nocs, in->mask, in->joint_axis, in->joint_cls, N, K, part_idx, part_src, part_tgt,
+                        axis_med, out->part_count};
+        int npow2 = 1;
+        while (npow2 < N) npow2 <<= 1;
+        size_t smem = ((N + 15) & ~15) + (size_t)RT * 8 * 4 + (size_t)3 * npow2 * 4;
+        ANCSH_CUDA(cudaFuncSetAttribute(partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        partition_kernel<<<B, RT, smem, st>>>(a);
+        ANCSH_CHECK_LAUNCH();
+    }
+    const double th2 = cfg->inlier_th * cfg->inlier_th;
+    {
+        SingleArgs a{};
+        a.part_src = part_src; a.part_tgt = part_tgt; a.part_count = out->part_count; a.idx = in->idx_single;
+        a.scores = single_scores; a.best = single_best; a.N = N; a.niter = cfg->niter_single; a.th2 = th2;
+        a.seed = cfg->seed;
+        a.R = out->single_R; a.s = out->single_s; a.t = out->single_t; a.score_out = out->single_score;
+        a.inliers = out->single_inliers; a.status = out->status;
+        size_t smem = (size_t)N * 6 * sizeof(double);
+        ANCSH_CUDA(cudaFuncSetAttribute(single_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid(ancsh_cdiv(cfg->niter_single, RT), B * K);
+        single_score_kernel<<<grid, RT, smem, st>>>(a);
+        ANCSH_CHECK_LAUNCH();
+        size_t smem2 = smem + N;
+        ANCSH_CUDA(cudaFuncSetAttribute(single_refit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        single_refit_kernel<<<B * K, RT, smem2, st>>>(a);
+        ANCSH_CHECK_LAUNCH();
+    }
+    if (K > 1) {
+        JointArgs a{};
+        a.part_src = part_src; a.part_tgt = part_tgt; a.part_count = out->part_count; a.axis_med = axis_med;
+        a.idx0 = in->idx_joint0; a.idx1 = in->idx_joint1; a.scores = joint_scores; a.best = joint_best;
+        a.N = N; a.K = K; a.niter = cfg->niter_joint; a.th2 = th2; a.seed = cfg->seed;
+        a.R0 = out->joint_R0; a.s0 = out->joint_s0; a.t0 = out->joint_t0;
+        a.R1 = out->joint_R1; a.s1 = out->joint_s1; a.t1 = out->joint_t1; a.score_out = out->joint_score;
+        a.inl0 = out->joint_inliers0; a.inl1 = out->joint_inliers1; a.status = out->status;
+        size_t smem = (size_t)N * 6 * sizeof(double);          // n0 + n1 <= N
+        ANCSH_CUDA(cudaFuncSetAttribute(joint_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid(ancsh_cdiv(cfg->niter_joint, JT), B * (K - 1));
+        joint_score_kernel<<<grid, JT, smem, st>>>(a);
+        ANCSH_CHECK_LAUNCH();
+        size_t smem2 = smem + N + 16;
+        ANCSH_CUDA(cudaFuncSetAttribute(joint_refit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        joint_refit_kernel<<<B * (K - 1), RT, smem2, st>>>(a);
+        ANCSH_CHECK_LAUNCH();
+    }
+    return ANCSH_OK;
+}
+
+extern "C" int ancsh_pose_sample_indices(unsigned long long seed, int stream_id, int nprob, int niter,
+                                         const int *n_per_problem, int *idx, void *stream)
+{
+    if (nprob < 0 || niter < 0 || !n_per_problem || !idx) return ANCSH_ERR_INVALID_ARG;
+    const long total = (long)nprob * niter;
+    if (total == 0) return ANCSH_OK;
+    sample_indices_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(seed, stream_id, nprob, niter,
+                                                                                             n_per_problem, idx);
+    ANCSH_CHECK_LAUNCH();
+    return ANCSH_OK;
+}
+
+extern "C" int ancsh_umeyama(int nprob, int nmax, const float *src, const float *tgt, const int *cnt, double *scale,
+                             double *R, double *t, void *stream)
+{
+    if (nprob < 0 || nmax <= 0 || !src || !tgt || !cnt || !scale || !R || !t) return ANCSH_ERR_INVALID_ARG;
+    if (nprob == 0) return ANCSH_OK;
+    umeyama_kernel<<<nprob, RT, 0, (cudaStream_t)stream>>>(nmax, src, tgt, cnt, scale, R, t);
+    ANCSH_CHECK_LAUNCH();
+    return ANCSH_OK;
+}

@@ -701,4 +701,98 @@ PM_HDN inline void transform3(const double *src, const double *tgt, double *R, d
     for (int c = 0; c < 3; ++c) t[c] = acc[c] / 3.0;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// joint_transformation_estimator (evaluation/parallel_ancsh_pose.py:106-184) for one RANSAC hypothesis:
+// 3 sampled correspondences per part.  model = {R0[9], s0, t0[3], R1[9], s1, t1[3]} (26 doubles).
+// LM settings of the reference call: ftol=1e-4, xtol=gtol=1e-8 (scipy defaults), max_nfev=100*n, factor=100.
+// ---------------------------------------------------------------------------------------------------
+struct JointModel {
+    double R0[9], s0, t0[3], R1[9], s1, t1[3];
+};
+
+PM_HDN inline void centre_scale3(const double *S, const double *T, double *Sc, double *Tsc, double *scale)
+{
+    *scale = pair_scale_small(S, T, 3);                        // :121
+    const double sinv = pair_scale_small(T, S, 3);             // :123 scale_pts(target, source)
+    double ms[3] = {0, 0, 0}, mt[3] = {0, 0, 0};
+    for (int i = 0; i < 3; ++i)
+        for (int c = 0; c < 3; ++c) { ms[c] += S[3 * i + c]; mt[c] += sinv * T[3 * i + c]; }
+    for (int c = 0; c < 3; ++c) { ms[c] /= 3.0; mt[c] /= 3.0; }
+    for (int i = 0; i < 3; ++i)
+        for (int c = 0; c < 3; ++c) { Sc[3 * i + c] = S[3 * i + c] - ms[c]; Tsc[3 * i + c] = sinv * T[3 * i + c] - mt[c]; }
+}
+
+PM_HDN inline void kabsch_points(const double *Sc, const double *Tc, int n, double *R)
+{
+    // rotate_pts re-centres its (already centred) inputs, d3_utils.py:211-212
+    double ms[3] = {0, 0, 0}, mt[3] = {0, 0, 0};
+    for (int i = 0; i < n; ++i)
+        for (int c = 0; c < 3; ++c) { ms[c] += Sc[3 * i + c]; mt[c] += Tc[3 * i + c]; }
+    for (int c = 0; c < 3; ++c) { ms[c] /= n; mt[c] /= n; }
+    double M[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < n; ++i)
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) M[3 * a + b] += (Tc[3 * i + a] - mt[a]) * (Sc[3 * i + b] - ms[b]);
+    kabsch_rotation(M, R);
+}
+
+PM_HDN inline void mean_translation(const double *S, const double *T, int n, const double *R, double scale, double *t)
+{
+    double acc[3] = {0, 0, 0};
+    for (int i = 0; i < n; ++i) {
+        double rs[3];
+        matvec3(R, S + 3 * i, rs);
+        for (int c = 0; c < 3; ++c) acc[c] += T[3 * i + c] - scale * rs[c];
+    }
+    for (int c = 0; c < 3; ++c) t[c] = acc[c] / n;
+}
+
+PM_HDN inline LmResult joint_estimate3(const double *S0, const double *T0, const double *S1, const double *T1,
+                                       const double *u, JointModel &m)
+{
+    double S0c[9], T0c[9], S1c[9], T1c[9];
+    centre_scale3(S0, T0, S0c, T0c, &m.s0);
+    centre_scale3(S1, T1, S1c, T1c, &m.s1);
+    kabsch_points(S0c, T0c, 3, m.R0);                          // :138-139
+    kabsch_points(S1c, T1c, 3, m.R1);
+    double x[6];
+    matrix_to_rotvec(m.R0, x);                                 // :147-148
+    matrix_to_rotvec(m.R1, x + 3);
+    SerialProb P;
+    P.x0 = S0c; P.y0 = T0c; P.n0 = 3; P.x1 = S1c; P.y1 = T1c; P.n1 = 3;
+    P.u[0] = u[0]; P.u[1] = u[1]; P.u[2] = u[2];
+    P.nj = 3.0;                                                // min(n0,n1) copies of the joint direction, :134
+    LmResult r = lm_solve(P, x, 1e-4, 1e-8, 1e-8, 600, 100.0); // :154-155
+    rotvec_to_matrix(x, m.R0);                                 // :156-157
+    rotvec_to_matrix(x + 3, m.R1);
+    mean_translation(S0, T0, 3, m.R0, m.s0, m.t0);             // :174-175 (un-refined scale)
+    mean_translation(S1, T1, 3, m.R1, m.s1, m.t1);
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based generator for hypothesis sampling (hard part 4).
+// ---------------------------------------------------------------------------------------------------
+PM_HD void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned *out)
+{
+    for (int r = 0; r < 10; ++r) {
+        const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
+        const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+        const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0;
+        const unsigned n1 = (unsigned)p1;
+        const unsigned n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1;
+        const unsigned n3 = (unsigned)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// three sample positions in [0,n) for hypothesis `hyp` of problem `prob`, stream 0 (single) / 1,2 (joint parts)
+PM_HD void sample3(unsigned long long seed, unsigned prob, unsigned hyp, unsigned stream, int n, int *idx)
+{
+    unsigned r[4];
+    philox4x32_10(hyp, prob, stream, 0u, (unsigned)seed, (unsigned)(seed >> 32), r);
+    for (int i = 0; i < 3; ++i) idx[i] = (int)(((unsigned long long)r[i] * (unsigned long long)n) >> 32);
+}
+
 }  // namespace pm

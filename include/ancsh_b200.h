@@ -159,6 +159,83 @@ int ancsh_event_record(void *event, void *stream);
 int ancsh_event_elapsed_ms(void *start, void *stop, float *ms_out); /* both events must have completed */
 int ancsh_event_destroy(void *event);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Pose level -- replaces the per-cloud body of solver_ransac_nonlinear
+ * (evaluation/parallel_ancsh_pose.py:214-352): K single-part RANSACs (ransac() :20-33 with
+ * single_transformation_estimator/_verifier :35-54) and K-1 joint RANSACs part 0 <-> part j
+ * (joint_transformation_estimator/_verifier :106-194, LM of :154-155), each followed by the refit on the
+ * best hypothesis' inliers.  All arithmetic in f64 on f32 inputs.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int n_parts;             /* K */
+    int niter_single;        /* reference: 10000 (parallel_ancsh_pose.py:262) */
+    int niter_joint;         /* reference: 200   (parallel_ancsh_pose.py:288) */
+    double inlier_th;        /* reference: 0.1   (pose_multi_process.py:32) */
+    unsigned long long seed; /* Philox4x32-10 key, used when the idx_* tensors are NULL */
+} ancsh_pose_cfg_t;
+
+typedef struct {
+    const float *P;          /* (B,N,3)  input cloud                       (h5 'P') */
+    const float *nocs;       /* (B,N,3K) nocs_per_point                    (h5 'nocs_per_point') */
+    const float *mask;       /* (B,N,K)  instance_per_point (W); argmax = part label, :238 */
+    const float *joint_axis; /* (B,N,3)  joint_axis_per_point; median over the joint's points, :295 */
+    const int *joint_cls;    /* (B,N)    joint_cls_gt: j in 1..K-1 marks points of joint j, :244-247 */
+    const int *idx_single;   /* NULL or (B,K,niter_single,3): sample POSITIONS inside the part's point list */
+    const int *idx_joint0;   /* NULL or (B,K-1,niter_joint,3): samples of part 0 */
+    const int *idx_joint1;   /* NULL or (B,K-1,niter_joint,3): samples of part j */
+} ancsh_pose_in_t;
+
+#define ANCSH_POSE_EMPTY_PART 1   /* status bit: the part has no points (the reference raises ValueError) */
+#define ANCSH_POSE_NO_INLIERS 2   /* status bit: best hypothesis has no inliers -> NaN model */
+
+typedef struct {
+    /* single-part RANSAC ('baseline' entries of the reference's result dict, :281-285) */
+    double *single_R;               /* (B,K,9) row-major rotation */
+    double *single_s;               /* (B,K) */
+    double *single_t;               /* (B,K,3) */
+    int *single_score;              /* (B,K) inlier count of the best hypothesis */
+    unsigned char *single_inliers;  /* (B,K,N) best_inliers mask over the part's point list (first part_count entries) */
+    /* joint RANSAC ('nonlinear' entries, :325-343); entry j-1 couples part 0 with part j */
+    double *joint_R0, *joint_s0, *joint_t0; /* (B,K-1,9) (B,K-1) (B,K-1,3) */
+    double *joint_R1, *joint_s1, *joint_t1;
+    double *joint_score;            /* (B,K-1) score of the best hypothesis, (n0/3+n1/3)/2 as in :193 */
+    unsigned char *joint_inliers0;  /* (B,K-1,N) */
+    unsigned char *joint_inliers1;  /* (B,K-1,N) */
+    int *part_count;                /* (B,K) */
+    int *status;                    /* (B,K) ANCSH_POSE_* bits (joint j reports in entry j) */
+} ancsh_pose_out_t;
+
+typedef struct {
+    size_t part_idx;       /* int32 (B,K,N) point indices of each part, ascending (np.where, :241) */
+    size_t part_src;       /* f32 (B,K,N,3) nocs of the part's points, channels 3j..3j+2 */
+    size_t part_tgt;       /* f32 (B,K,N,3) P of the part's points */
+    size_t axis_med;       /* f64 (B,K-1,3) per-joint median axis */
+    size_t single_scores;  /* int32 (B,K,niter_single) per-hypothesis inlier counts */
+    size_t joint_scores;   /* f64 (B,K-1,niter_joint) per-hypothesis scores */
+    size_t single_best;    /* int32 (B,K) index of the winning hypothesis */
+    size_t joint_best;     /* int32 (B,K-1) */
+    size_t total_bytes;
+} ancsh_pose_ws_t;
+
+int ancsh_pose_plan(const ancsh_pose_cfg_t *cfg, int B, int N, ancsh_pose_ws_t *layout);
+
+/* Solves B clouds.  N <= 4096, K <= 8. */
+int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in_t *in, int B, int N, void *workspace,
+                     size_t workspace_bytes, const ancsh_pose_out_t *out, void *stream);
+
+/* Writes the sample positions the Philox generator produces for (seed, problem, hypothesis) so that a CPU
+ * checker can replay them: idx (nprob,niter,3); n_per_problem (nprob) is the part size each problem samples
+ * from; stream_id 0 = single RANSAC, 1 / 2 = part 0 / part j of the joint RANSAC. */
+int ancsh_pose_sample_indices(unsigned long long seed, int stream_id, int nprob, int niter, const int *n_per_problem,
+                              int *idx, void *stream);
+
+/* Batched Umeyama similarity (lib/aligning.py:580-622 estimateSimilarityUmeyama, as called by
+ * evaluation/compute_gt_pose.py:87 for the GT part poses): src/tgt (nprob,nmax,3) f32, cnt (nprob) ->
+ * scale (nprob), R (nprob,9) row-major in the REFERENCE's convention (Rotation = (U Vh)^T), t (nprob,3). */
+int ancsh_umeyama(int nprob, int nmax, const float *src, const float *tgt, const int *cnt, double *scale, double *R,
+                  double *t, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

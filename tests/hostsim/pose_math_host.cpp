@@ -29,6 +29,20 @@ int hs_lm(const double *x0, const double *y0, int n0, const double *x1, const do
     out[0] = r.nfev; out[1] = r.njev; out[2] = r.fnorm;
     return r.info;
 }
+int hs_joint_estimate3(const double *S0, const double *T0, const double *S1, const double *T1, const double *u,
+                       double *model26, double *out)
+{
+    pm::JointModel m;
+    pm::LmResult r = pm::joint_estimate3(S0, T0, S1, T1, u, m);
+    const double *src = reinterpret_cast<const double *>(&m);
+    for (int i = 0; i < 26; ++i) model26[i] = src[i];
+    out[0] = r.nfev; out[1] = r.njev; out[2] = r.fnorm;
+    return r.info;
+}
+void hs_sample3(unsigned long long seed, unsigned prob, unsigned hyp, unsigned stream, int n, int *idx)
+{
+    pm::sample3(seed, prob, hyp, stream, n, idx);
+}
 void hs_normal(const double *x0, const double *y0, int n0, const double *x1, const double *y1, int n1, const double *u,
                double nj, const double *x, double *JtJ, double *Jtf, double *fsq)
 {

@@ -176,3 +176,45 @@ def test_lm_on_garbage_correspondences_is_finite(lib):
         ref = _run_scipy(*prob)
         close += int(np.abs(x - ref.x).max() < 1e-4)
     assert close >= 80, close          # same basin / same early stop in the vast majority of ill-posed cases too
+
+
+def test_joint_estimate3_matches_oracle_estimator(lib):
+    """One RANSAC hypothesis of the joint estimator (3+3 samples) vs oracle/pose_np.joint_estimator."""
+    from articulated_pose_b200 import synthetic
+    cloud = synthetic.make_cloud(7)
+    pred = synthetic.teacher_predictions(cloud)
+    cls = np.argmax(pred["W"], 1)
+    p0, p1 = np.where(cls == 0)[0], np.where(cls == 1)[0]
+    ds = {"source0": pred["nocs_per_point"][p0, 0:3].astype(np.float64), "target0": cloud["P"][p0].astype(np.float64),
+          "source1": pred["nocs_per_point"][p1, 3:6].astype(np.float64), "target1": cloud["P"][p1].astype(np.float64),
+          "joint_direction": np.median(pred["joint_axis_per_point"][cloud["joint_cls_gt"] == 1].astype(np.float64), 0)}
+    rng = np.random.default_rng(9)
+    diffs = []
+    c = np.ascontiguousarray
+    for _ in range(300):
+        i0, i1 = rng.integers(0, len(p0), 3), rng.integers(0, len(p1), 3)
+        if len(set(i0)) < 3 or len(set(i1)) < 3:
+            continue                                   # repeated indices: rank-deficient, LAPACK-arbitrary
+        ref = pose_np.joint_estimator(ds, i0, i1)
+        model = np.zeros(26); out = np.zeros(3)
+        info = lib.hs_joint_estimate3(dp(c(ds["source0"][i0])), dp(c(ds["target0"][i0])), dp(c(ds["source1"][i1])),
+                                      dp(c(ds["target1"][i1])), dp(c(ds["joint_direction"])), dp(model), dp(out))
+        assert info != 0
+        got = {"rotation0": model[0:9].reshape(3, 3), "scale0": model[9], "translation0": model[10:13],
+               "rotation1": model[13:22].reshape(3, 3), "scale1": model[22], "translation1": model[23:26]}
+        d = max(np.abs(np.asarray(got[k]) - np.asarray(ref[k])).max() for k in got)
+        diffs.append(d)
+    diffs = np.array(diffs)
+    assert np.median(diffs) < 1e-7 and np.mean(diffs < 1e-4) > 0.97, (np.median(diffs), np.mean(diffs < 1e-4), diffs.max())
+
+
+def test_sample3_range_and_determinism(lib):
+    I = ctypes.POINTER(ctypes.c_int)
+    a = np.zeros(3, np.int32); b = np.zeros(3, np.int32)
+    seen = set()
+    for h in range(200):
+        lib.hs_sample3(ctypes.c_ulonglong(1234), 5, h, 0, 341, a.ctypes.data_as(I))
+        lib.hs_sample3(ctypes.c_ulonglong(1234), 5, h, 0, 341, b.ctypes.data_as(I))
+        assert (a == b).all() and (a >= 0).all() and (a < 341).all()
+        seen.add(tuple(a))
+    assert len(seen) > 190
