@@ -52,7 +52,7 @@ PRED_FIELDS = ("W", "nocs_per_point", "confi_per_point", "heatmap_per_point", "u
 
 
 class Pred(ctypes.Structure):
-    _fields_ = [(k, ctypes.c_void_p) for k in PRED_FIELDS]
+    _fields_ = [(k, ctypes.c_void_p) for k in PRED_FIELDS + ("net",)]
 
 
 WS_FIELDS = ("fps_idx1", "l1_xyz", "fps_idx2", "l2_xyz", "ball_idx1", "ball_cnt1", "ball_idx2", "ball_cnt2",
@@ -115,7 +115,8 @@ class PoseWs(ctypes.Structure):
 
 ancsh_pose_plan = _sig("ancsh_pose_plan", [ctypes.POINTER(PoseCfg), c_int, c_int, ctypes.POINTER(PoseWs)])
 ancsh_pose_solve = _sig("ancsh_pose_solve", [ctypes.POINTER(PoseCfg), ctypes.POINTER(PoseIn), c_int, c_int, vp, c_size_t,
-                                             ctypes.POINTER(PoseOut), vp])
+                                             ctypes.POINTER(PoseOut), ctypes.POINTER(vp), vp])
+POSE_STAGES = ("partition", "single_score", "single_refit", "joint_score", "joint_refit")
 ancsh_pose_sample_indices = _sig("ancsh_pose_sample_indices", [ctypes.c_ulonglong, c_int, c_int, c_int, vp, vp, vp])
 ancsh_umeyama = _sig("ancsh_umeyama", [c_int, c_int, vp, vp, vp, vp, vp, vp, vp])
 

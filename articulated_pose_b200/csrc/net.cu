@@ -257,6 +257,10 @@ __global__ void __launch_bounds__(NT) fp_kernel(const FpArgs a)
         layer_to_smem<TM>(bufB, a.ldB, a.L[1], a.L[1].b, bufA, a.ldA, Wsm);
         layer_to_smem<TM>(bufA, a.ldA, a.L[2], a.L[2].b, bufB, a.ldB, Wsm);
         layer_to_smem<TM>(bufB, a.ldB, a.fc1, a.fc1.b, bufA, a.ldA, Wsm);                    // net
+        if (a.pred.net) {
+            __syncthreads();
+            copy_tile_out(a.pred.net + ((size_t)b * a.n1 + row0) * a.fc1.cout, a.fc1.cout, bufA, a.ldA, 0, TM);
+        }
         layer_to_smem<TM>(bufA, a.ldA, a.nocs_heads, a.nocs_heads.b, bufC, a.ldC, Wsm);      // raw nocs_net outputs
         layer_to_smem<TM>(bufA, a.ldA, a.fc3[0], a.fc3[0].b, bufB, a.ldB, Wsm);
         layer_to_smem<TM>(bufB, a.ldB, a.fc3[1], a.fc3[1].b, bufA, a.ldA, Wsm);

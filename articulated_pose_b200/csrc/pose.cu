@@ -695,7 +695,8 @@ extern "C" int ancsh_pose_plan(const ancsh_pose_cfg_t *cfg, int B, int N, ancsh_
 }
 
 extern "C" int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in_t *in, int B, int N, void *workspace,
-                                size_t workspace_bytes, const ancsh_pose_out_t *out, void *stream)
+                                size_t workspace_bytes, const ancsh_pose_out_t *out, void *const *stage_events,
+                                void *stream)
 {
     if (!cfg || !in || !out || !workspace) return ANCSH_ERR_INVALID_ARG;
     if (!in->P || !in->nocs || !in->mask) return ANCSH_ERR_INVALID_ARG;
@@ -715,6 +716,13 @@ extern "C" int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in
     double *joint_scores = (double *)(ws + L.joint_scores);
     int *single_best = (int *)(ws + L.single_best), *joint_best = (int *)(ws + L.joint_best);
 
+    int stage = 0;
+#define STAGE_MARK()                                                                        \
+    do {                                                                                    \
+        if (stage_events) ANCSH_CUDA(cudaEventRecord((cudaEvent_t)stage_events[stage], st)); \
+        ++stage;                                                                            \
+    } while (0)
+    STAGE_MARK();
     ANCSH_CUDA(cudaMemsetAsync(out->status, 0, (size_t)B * K * sizeof(int), st));
     {
         PartitionArgs a{in->P, in->nocs, in->mask, in->joint_axis, in->joint_cls, N, K, part_idx, part_src, part_tgt,
@@ -727,6 +735,7 @@ extern "C" int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in
         ANCSH_CHECK_LAUNCH();
     }
     const double th2 = cfg->inlier_th * cfg->inlier_th;
+    STAGE_MARK();
     {
         SingleArgs a{};
         a.part_src = part_src; a.part_tgt = part_tgt; a.part_count = out->part_count; a.idx = in->idx_single;
@@ -739,11 +748,13 @@ extern "C" int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in
         dim3 grid(ancsh_cdiv(cfg->niter_single, RT), B * K);
         single_score_kernel<<<grid, RT, smem, st>>>(a);
         ANCSH_CHECK_LAUNCH();
+        STAGE_MARK();
         size_t smem2 = smem + N;
         ANCSH_CUDA(cudaFuncSetAttribute(single_refit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         single_refit_kernel<<<B * K, RT, smem2, st>>>(a);
         ANCSH_CHECK_LAUNCH();
     }
+    STAGE_MARK();
     if (K > 1) {
         JointArgs a{};
         a.part_src = part_src; a.part_tgt = part_tgt; a.part_count = out->part_count; a.axis_med = axis_med;
@@ -757,11 +768,16 @@ extern "C" int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in
         dim3 grid(ancsh_cdiv(cfg->niter_joint, JT), B * (K - 1));
         joint_score_kernel<<<grid, JT, smem, st>>>(a);
         ANCSH_CHECK_LAUNCH();
+        STAGE_MARK();
         size_t smem2 = smem + N + 16;
         ANCSH_CUDA(cudaFuncSetAttribute(joint_refit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         joint_refit_kernel<<<B * (K - 1), RT, smem2, st>>>(a);
         ANCSH_CHECK_LAUNCH();
+    } else {
+        STAGE_MARK();
     }
+    STAGE_MARK();
+#undef STAGE_MARK
     return ANCSH_OK;
 }
 

@@ -99,7 +99,7 @@ class AncshNet:
             out[k] = torch.empty((B, N, _PRED_WIDTH[k](K)), dtype=torch.float32, device=self.device)
         return out
 
-    def forward_device(self, P, out=None, stage_events=None):
+    def forward_device(self, P, out=None, stage_events=None, net_out=None):
         """P: CUDA f32 (B,N,3).  Launches on torch's current stream; returns dict of CUDA tensors.
         stage_events: optional _lib.EventList(len(_lib.NET_STAGES)+1) recorded around each stage."""
         if P.dtype != torch.float32 or P.dim() != 3 or P.shape[2] != 3 or not P.is_cuda:
@@ -112,6 +112,7 @@ class AncshNet:
         pred = _lib.Pred()
         for k in _lib.PRED_FIELDS:
             setattr(pred, k, out[k].data_ptr() if k in out else None)
+        pred.net = net_out.data_ptr() if net_out is not None else None     # optional (B,N,128) trunk feature
         rc = _lib.ancsh_net_forward(ctypes.byref(self._net), B, N, P.data_ptr(), ws.data_ptr(), lay.total_bytes,
                                     ctypes.byref(pred), stage_events.arr if stage_events is not None else None,
                                     torch.cuda.current_stream().cuda_stream)
@@ -140,6 +141,16 @@ class AncshNet:
                 hout[k].copy_(v, non_blocking=True)
             torch.cuda.current_stream().synchronize()
         return {k: (v.numpy().copy() if copy else v.numpy()) for k, v in hout.items()}
+
+    def features(self, P):
+        """Host (B,N,3) -> host (B,N,128) trunk feature `net` (input of all heads); used to fit synthetic heads."""
+        Pd = torch.from_numpy(np.ascontiguousarray(P, dtype=np.float32)).to(self.device)
+        B, N, _ = Pd.shape
+        net = torch.empty((B, N, 128), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self.forward_device(Pd, net_out=net)
+            torch.cuda.current_stream().synchronize()
+        return net.cpu().numpy()
 
     def intermediates(self):
         """Views of the last forward's workspace (indices and per-level features), for parity tests."""

@@ -1,0 +1,73 @@
+"""End-to-end hot path: PointNet++ forward(s) -> per-part RANSAC -> joint-constrained solve, all on the device.
+
+Mirrors what the reference does across two programs and a directory of h5 files:
+  main.py --test  (Network.predict_and_save, lib/network.py:257-305)  ->  results/test_pred/<exp>/<basename>.h5
+  pose_multi_process.py -> solver_ransac_nonlinear (evaluation/parallel_ancsh_pose.py:196-352)
+The reference's solver reads NOCS + segmentation from the NPCS *baseline* experiment (USE_BASELINE = True,
+parallel_ancsh_pose.py:197,232-236) and the joint axis from the ANCSH experiment, i.e. two network forwards per
+cloud; `use_baseline` keeps that default.  Here the predictions never leave HBM between the stages.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .network import AncshNet
+from .pose import PoseSolver, unpack_results
+
+
+class AncshPipeline:
+    def __init__(self, weights_ancsh, n_parts, weights_npcs=None, use_baseline=True, nsample=64, niter_single=10000,
+                 niter_joint=200, inlier_th=0.1, seed=0, device="cuda:0"):
+        self.device = torch.device(device)
+        self.K = int(n_parts)
+        self.use_baseline = bool(use_baseline and weights_npcs is not None)
+        self.net = AncshNet(weights_ancsh, n_parts, mixed_pred=True, early_split_nocs=True, nsample=nsample, device=device)
+        self.net_npcs = None
+        if self.use_baseline:
+            self.net_npcs = AncshNet(weights_npcs, n_parts, mixed_pred=False, early_split_nocs=False, nsample=nsample,
+                                     device=device)
+        self.pose = PoseSolver(n_parts, niter_single, niter_joint, inlier_th, seed, device)
+        self._buf = {}
+
+    def _buffers(self, B, N):
+        key = (B, N)
+        if key not in self._buf:
+            d = {"pred": self.net.alloc_outputs(B, N), "pose": self.pose.alloc_outputs(B, N),
+                 "P": torch.empty((B, N, 3), dtype=torch.float32, device=self.device),
+                 "jc": torch.empty((B, N), dtype=torch.int32, device=self.device),
+                 "hP": torch.empty((B, N, 3), dtype=torch.float32).pin_memory(),
+                 "hjc": torch.empty((B, N), dtype=torch.int32).pin_memory()}
+            if self.net_npcs is not None:
+                d["pred_b"] = self.net_npcs.alloc_outputs(B, N)
+            d["hpose"] = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in d["pose"].items()}
+            self._buf[key] = d
+        return self._buf[key]
+
+    def run_device(self, P, joint_cls, net_events=None, net_b_events=None, pose_events=None):
+        """P (B,N,3) f32 CUDA, joint_cls (B,N) int32 CUDA -> dict of CUDA pose tensors (ancsh_pose_out_t)."""
+        B, N, _ = P.shape
+        buf = self._buffers(B, N)
+        pred = self.net.forward_device(P, buf["pred"], stage_events=net_events)
+        src = pred
+        if self.net_npcs is not None:
+            src = self.net_npcs.forward_device(P, buf["pred_b"], stage_events=net_b_events)
+        return self.pose.solve_device(P, src["nocs_per_point"], src["W"], pred["joint_axis_per_point"], joint_cls,
+                                      out=buf["pose"], stage_events=pose_events)
+
+    def run(self, P, joint_cls, unpack=True):
+        """Host arrays in, host results out: pinned H2D of the clouds, all stages on the device, D2H of the poses
+        (rotations, scales, translations, scores, inlier masks)."""
+        P = np.ascontiguousarray(P, np.float32)
+        B, N, _ = P.shape
+        buf = self._buffers(B, N)
+        buf["hP"].numpy()[...] = P
+        buf["hjc"].numpy()[...] = joint_cls
+        with torch.cuda.device(self.device):
+            buf["P"].copy_(buf["hP"], non_blocking=True)
+            buf["jc"].copy_(buf["hjc"], non_blocking=True)
+            out = self.run_device(buf["P"], buf["jc"])
+            for k, v in out.items():
+                buf["hpose"][k].copy_(v, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        h = {k: v.numpy() for k, v in buf["hpose"].items()}
+        return unpack_results(h, self.K) if unpack else h

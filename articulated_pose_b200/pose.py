@@ -75,7 +75,7 @@ class PoseSolver:
         return {k: torch.empty(shp(B, self.K, N, J), dtype=dt, device=self.device) for k, (dt, shp) in _OUT_SPEC.items()}
 
     def solve_device(self, P, nocs, mask, joint_axis=None, joint_cls=None, idx_single=None, idx_joint0=None,
-                     idx_joint1=None, out=None):
+                     idx_joint1=None, out=None, stage_events=None):
         """P (B,N,3) f32, nocs (B,N,3K) f32, mask (B,N,K) f32, joint_axis (B,N,3) f32, joint_cls (B,N) int32;
         optional idx_single (B,K,niter_single,3), idx_joint0/1 (B,K-1,niter_joint,3) int32.  Launches on torch's
         current stream and returns a dict of CUDA tensors (see include/ancsh_b200.h: ancsh_pose_out_t)."""
@@ -109,7 +109,8 @@ class PoseSolver:
         for k in _lib.POSE_OUT_FIELDS:
             setattr(pout, k, out[k].data_ptr())
         rc = _lib.ancsh_pose_solve(ctypes.byref(self.cfg), ctypes.byref(pin), B, N, ws.data_ptr(), lay.total_bytes,
-                                   ctypes.byref(pout), torch.cuda.current_stream().cuda_stream)
+                                   ctypes.byref(pout), stage_events.arr if stage_events is not None else None,
+                                   torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "ancsh_pose_solve")
         self.last = (ws, lay, B, N)
         return out

@@ -4,7 +4,7 @@ there is no network): SURVEY.md section 8(d).
 `make_cloud(cloud_id, category)` mimics what lib/dataset.py:251-432 (create_unit_data_from_hdf5) hands to the
 network and what the pose stage later reads back from the per-cloud h5 (lib/prediction_io.py:73-92):
   P (N,3) camera-space points, cls_gt (N,), nocs_gt (N,3) part-normalised coordinates, joint_cls_gt (N,),
-  joint axis per joint, and the ground-truth per-part similarity (scale, R, t) with
+  joint axis per joint (canonical frame), and the ground-truth per-part similarity (scale, R, t) with
   P = scale * R @ nocs + t  -- exactly the model solver_ransac_nonlinear fits
   (evaluation/parallel_ancsh_pose.py:258-269).
 
@@ -93,7 +93,9 @@ def make_cloud(cloud_id, category="eyeglasses", n_points=None, noise=0.002, seed
             pj[child] = np.asarray(pivot, np.float64)
         else:
             dj[child] = ax * q
-        joint_axis_cam.append(R_obj @ ax)
+        # The reference's joint residual is Rod(r0) u - Rod(r1) u (parallel_ancsh_pose.py:63): it is consistent with
+        # the part poses only for u expressed in the canonical (rest / NOCS) frame, where R_gt[0] u == R_gt[j] u.
+        joint_axis_cam.append(ax.copy())
 
     n_draw = 4 * N
     counts = np.maximum(1, (np.asarray(cat["split"]) * n_draw).astype(int))

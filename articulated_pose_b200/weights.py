@@ -187,3 +187,46 @@ def flatten_packed(layers):
         flat[wo:wo + pl.W.size] = pl.W.ravel()
         flat[bo:bo + pl.b.size] = pl.b
     return flat, offs
+
+
+def fit_heads(weights, features, cls_gt, nocs_gt, n_parts, early_split_nocs=True, prefix="SPFN", ridge=1e-2):
+    """Synthetic-but-meaningful heads: keep the random trunk, fit the linear segmentation and NOCS heads by ridge
+    regression of the trunk feature `net` (AncshNet.features) onto ground truth of a few synthetic clouds.
+
+    No checkpoint ships with the reference (README.md:95-105) and purely random heads put every point into one
+    part, which would leave the pose stage without its real workload; a random-feature trunk with fitted linear
+    read-outs gives network outputs with realistic part partitions.  Returns a new weights dict.
+
+    features (M,128), cls_gt (M,), nocs_gt (M,3) part-normalised coordinates of each point's own part.
+    """
+    F = np.asarray(features, np.float64).reshape(-1, 128)
+    cls_gt = np.asarray(cls_gt).reshape(-1).astype(int)
+    nocs_gt = np.asarray(nocs_gt, np.float64).reshape(-1, 3)
+    A = np.hstack([F, np.ones((F.shape[0], 1))])
+
+    def solve(Asub, T):
+        G = Asub.T @ Asub + ridge * Asub.shape[0] * np.eye(Asub.shape[1])
+        X = np.linalg.solve(G, Asub.T @ T)
+        return X[:-1], X[-1]
+
+    out = OrderedDict((k, np.array(v, copy=True)) for k, v in weights.items())
+    n = prefix + "/nocs_net/"
+    T = np.full((F.shape[0], n_parts), -3.0)
+    T[np.arange(F.shape[0]), cls_gt] = 3.0
+    W, b = solve(A, T)
+    out[n + "fc2_0/weights"] = W.reshape(1, 128, n_parts).astype(np.float32)
+    out[n + "fc2_0/biases"] = b.astype(np.float32)
+    Wn = np.zeros((128, 3 * n_parts))
+    bn = np.zeros(3 * n_parts)
+    y = np.clip(nocs_gt, 0.02, 0.98)
+    logit = np.log(y / (1.0 - y))
+    for j in range(n_parts):
+        m = cls_gt == j
+        if m.sum() > 130:
+            Wn[:, 3 * j:3 * j + 3], bn[3 * j:3 * j + 3] = solve(A[m], logit[m])
+    out[n + "fc2_1/weights"] = Wn.reshape(1, 128, 3 * n_parts).astype(np.float32)
+    out[n + "fc2_1/biases"] = bn.astype(np.float32)
+    if early_split_nocs and (n + "fc11_1/weights") in out:
+        out[n + "fc11_1/weights"] = np.eye(128, dtype=np.float32).reshape(1, 128, 128)
+        out[n + "fc11_1/biases"] = np.zeros(128, np.float32)
+    return out

@@ -5,16 +5,21 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one pass of the hot path over one batch of synthetic clouds per rank (weak scaling: every rank
-owns its own batch; clouds are independent).  Prints ONE JSON line on rank 0.
+owns its own batch; clouds are independent; one all-gather of the pose records at the end).
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): eyeglasses, N=1024, nsample=32,
+full pipeline = ANCSH forward + NPCS-baseline forward (the reference's solver reads NOCS/mask from the baseline
+experiment, parallel_ancsh_pose.py:197,232-236) + 3 single RANSACs (500 hyp) + 2 joint RANSACs (200 hyp, LM).
+Prints ONE JSON line on rank 0.
 
   value     device-timed clouds/s, inputs resident in HBM (CUDA events per step on the launch stream, L2 flushed
             between steps, summed over the K steps, max over ranks)
-  e2e       the same pass through the public host API (AncshNet.forward / solve) with HOST buffers: pinned H2D of
-            the clouds and D2H of the results inside the timed region
+  e2e       the same pass through the public host API (AncshPipeline.run) with HOST buffers: pinned H2D of the
+            clouds and D2H of the pose results inside the timed region
   roofline  the dominant kernel (grouped-MLP set-abstraction stage) from per-stage CUDA events recorded during
             the timed steps, against the measured bf16 tensor peak (MEASURED_PEAKS.json)
-  cpu_baseline / --impl reference   the CPU oracle (oracle/, a line-for-line restatement of the reference; TF1
-            cannot be installed and the reference has no CPU kernels for FPS / ball query) on this box's host cores
+  cpu_baseline / --impl reference   the CPU oracle (oracle/: line-for-line restatement of the reference's network
+            ops -- TF1 cannot be installed and the reference has no CPU kernels for FPS / ball query -- and of its
+            numpy/scipy pose code) on this box's host cores
 """
 import argparse
 import json
@@ -32,20 +37,22 @@ sys.path.insert(0, ROOT)
 
 METRIC = "clouds/sec end-to-end (PN++ fwd + RANSAC + joint solve)"
 UNIT = "clouds/s"
+CALIB_CLOUDS = 16
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="clouds per rank per step")
     ap.add_argument("--category", default="eyeglasses")
     ap.add_argument("--nsample", type=int, default=32, help="BASELINE config K=32 (reference default: 64)")
-    ap.add_argument("--hyp", type=int, default=500, help="RANSAC hypotheses per part (BASELINE config: 500)")
+    ap.add_argument("--hyp", type=int, default=500, help="RANSAC hypotheses per part (BASELINE config: 500; reference 10000)")
     ap.add_argument("--joint-hyp", type=int, default=200)
-    ap.add_argument("--stages", default="auto", help="forward | full | auto")
+    ap.add_argument("--stages", default="full", choices=["forward", "full"])
+    ap.add_argument("--no-baseline-net", action="store_true", help="USE_BASELINE=False: one forward per cloud")
     ap.add_argument("--cpu-sample", type=int, default=0, help="clouds in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -122,43 +129,80 @@ def stage_flops(net, B, N):
     return {k: v * B for k, v in f.items()}
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path = the oracle port (oracle/), all host
-    threads.  Rank 0 only."""
-    if rank != 0:
-        return
-    from articulated_pose_b200 import synthetic, weights
-    from oracle import pnpp
-    K = synthetic.CATEGORIES[args.category]["boxes"].__len__()
-    w = weights.synthetic_weights(K)
-    cores = os.cpu_count() or 1
-    pnpp.set_threads(cores)
-    n_s = args.cpu_sample or 4
-    P, _ = synthetic.make_batch(range(n_s), args.category)
-    for _ in range(max(1, min(args.warmup, 1))):
-        pnpp.forward(P[:1], w, K, nsample=args.nsample)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        pnpp.forward(P, w, K, nsample=args.nsample)
-    dt = time.perf_counter() - t0
-    val = n_s * args.steps / dt
-    sample = "%d clouds/step x %d steps, network forward only (pose stage port pending)" % (n_s, args.steps)
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args, "forward"), "sample": sample},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
-
-
-def workload_name(args, stages):
+def workload_name(args):
     cat = args.category
     n = 1024 if cat == "eyeglasses" else 2048
-    if stages == "forward":
+    if args.stages == "forward":
         return "%s ANCSH, N=%d nsample=%d, batch=%d clouds/GPU, PN++ forward + heads" % (cat, n, args.nsample, args.batch)
-    return "%s ANCSH, N=%d nsample=%d, batch=%d clouds/GPU, full pipeline: PN++ forward + RANSAC(%d hyp/part) + joint solve(%d hyp/joint)" % (
-        cat, n, args.nsample, args.batch, args.hyp, args.joint_hyp)
+    return ("%s ANCSH, N=%d nsample=%d, batch=%d clouds/GPU, full pipeline: %s + RANSAC(%d hyp/part) + "
+            "joint solve(%d hyp/joint, LM)") % (cat, n, args.nsample, args.batch,
+                                                "ANCSH forward" if args.no_baseline_net else "ANCSH + NPCS-baseline forwards",
+                                                args.hyp, args.joint_hyp)
+
+
+def synthetic_weight_sets(K, args, feature_fn=None):
+    """Seeded random trunks; when feature_fn(net_kind, weights, P) -> (M,128) is given, the linear segmentation /
+    NOCS heads are fitted on CALIB_CLOUDS synthetic clouds (weights.fit_heads) so that the part partition -- and
+    with it the pose-stage workload -- is realistic."""
+    from articulated_pose_b200 import synthetic, weights
+    w_a = weights.synthetic_weights(K, True, True, seed=7)
+    w_n = None if args.no_baseline_net else weights.synthetic_weights(K, False, False, seed=8)
+    if feature_fn is not None:
+        Pc, cc = synthetic.make_batch(range(900000, 900000 + CALIB_CLOUDS), args.category)
+        cls = np.stack([c["cls_gt"] for c in cc])
+        nocs = np.stack([c["nocs_gt"] for c in cc])
+        w_a = weights.fit_heads(w_a, feature_fn("ancsh", w_a, Pc), cls, nocs, K, early_split_nocs=True)
+        if w_n is not None:
+            w_n = weights.fit_heads(w_n, feature_fn("npcs", w_n, Pc), cls, nocs, K, early_split_nocs=False)
+    return w_a, w_n
+
+
+def cpu_reference_run(args, K, P, jc, w_a, w_n, n_clouds, steps):
+    """Times the CPU oracle on `n_clouds` clouds per step.  Returns (clouds/s, seconds, cores, description)."""
+    from oracle import pipeline_cpu
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    done = 0
+    for s in range(steps):
+        lo = (s * n_clouds) % max(1, P.shape[0] - n_clouds + 1)
+        done += pipeline_cpu.run_clouds(P[lo:lo + n_clouds], jc[lo:lo + n_clouds], w_a, w_n, K, args.nsample, 0.1, args.hyp,
+                                        args.joint_hyp, stages=args.stages, seed=s)
+    dt = time.perf_counter() - t0
+    desc = ("%d cloud(s)/step x %d step(s) of the same workload; network ops OpenMP over %d threads, RANSAC hypotheses "
+            "over %d forked workers (pose_multi_process.py uses cpu_count-2)") % (n_clouds, steps, cores,
+                                                                                 pipeline_cpu.workers())
+    return done / dt, dt, cores, desc
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; see module docstring)
+    with all host threads, bounded sample per step.  Rank 0 only."""
+    if rank != 0:
+        return
+    from articulated_pose_b200 import synthetic
+    from oracle import pipeline_cpu, pnpp
+    K = len(synthetic.CATEGORIES[args.category]["boxes"])
+
+    def feats(kind, w, Pc):      # trunk feature through the oracle (this arm never touches the GPU)
+        tr = {}
+        pnpp.set_threads(os.cpu_count() or 1)
+        pnpp.forward(Pc, w, K, nsample=args.nsample, mixed_pred=(kind == "ancsh"), early_split_nocs=(kind == "ancsh"), trace=tr)
+        return tr["net"]
+    w_a, w_n = synthetic_weight_sets(K, args, feats if args.stages == "full" else None)
+    n_s = args.cpu_sample or 1
+    P, clouds = synthetic.make_batch(range(max(n_s, 4)), args.category)
+    jc = np.stack([c["joint_cls_gt"] for c in clouds])
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_run(args, K, P, jc, w_a, w_n, 1, 1)
+    val, dt, cores, desc = cpu_reference_run(args, K, P, jc, w_a, w_n, n_s, args.steps)
+    pipeline_cpu.close_pool()
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 network / f64 pose", "data": "synthetic",
+            "config": {"workload": workload_name(args), "stages": args.stages, "sample": desc},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
 
 
 def main():
@@ -167,13 +211,14 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank)
         return
 
     import torch
     import torch.distributed as dist
-    from articulated_pose_b200 import _lib, synthetic, weights
+    from articulated_pose_b200 import _lib, synthetic
     from articulated_pose_b200.network import AncshNet
+    from articulated_pose_b200.pipeline import AncshPipeline
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -182,24 +227,38 @@ def main():
 
     K = len(synthetic.CATEGORIES[args.category]["boxes"])
     B = args.batch
-    w = weights.synthetic_weights(K)
-    net = AncshNet(w, K, nsample=args.nsample, device=dev)
+    full = args.stages == "full"
+
+    def feats(kind, w, Pc):
+        n = AncshNet(w, K, mixed_pred=(kind == "ancsh"), early_split_nocs=(kind == "ancsh"), nsample=args.nsample, device=dev)
+        return n.features(Pc)
+    w_a, w_n = synthetic_weight_sets(K, args, feats if full else None)
+    pipe = AncshPipeline(w_a, K, weights_npcs=w_n if full else None, use_baseline=full and not args.no_baseline_net,
+                         nsample=args.nsample, niter_single=args.hyp, niter_joint=args.joint_hyp, seed=1234 + rank,
+                         device=dev)
     P_host, clouds = synthetic.make_batch(range(rank * B, rank * B + B), args.category)
+    jc_host = np.stack([c["joint_cls_gt"] for c in clouds]).astype(np.int32)
     N = P_host.shape[1]
     P_dev = torch.from_numpy(P_host).to(dev)
-    out = net.alloc_outputs(B, N)
+    jc_dev = torch.from_numpy(jc_host).to(dev)
+    out_fwd = pipe.net.alloc_outputs(B, N)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    stages = "forward"
+    two_nets = pipe.net_npcs is not None
+
+    nst, npst = len(_lib.NET_STAGES), len(_lib.POSE_STAGES)
 
     def step(ev=None):
-        net.forward_device(P_dev, out, stage_events=ev)
+        if full:
+            return pipe.run_device(P_dev, jc_dev, net_events=ev[0] if ev else None, net_b_events=ev[1] if ev else None,
+                                   pose_events=ev[2] if ev else None)
+        return pipe.net.forward_device(P_dev, out_fwd, stage_events=ev[0] if ev else None)
 
     for _ in range(max(args.warmup, 3)):
-        step()
+        res = step()
     torch.cuda.synchronize()
+    part_hist = res["part_count"].float().mean(0).tolist() if full else None
 
-    nst = len(_lib.NET_STAGES)
-    evs = [_lib.EventList(nst + 1) for _ in range(args.steps)]
+    evs = [(_lib.EventList(nst + 1), _lib.EventList(nst + 1), _lib.EventList(npst + 1)) for _ in range(args.steps)]
     sampler = ClockSampler(local_rank)
     if world > 1:
         dist.barrier()
@@ -207,33 +266,62 @@ def main():
     sampler.start()
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
-        flush.zero_()                       # L2 flush between timed iterations (not inside the event pair)
+        flush.zero_()                       # L2 flush between timed iterations (outside the event pair)
         step(evs[i])
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
-    step_ms = [e.elapsed_ms(0, nst) for e in evs]
+
+    def span(e):       # first event of the step .. last event of the step, same stream
+        if not full:
+            return e[0].elapsed_ms(0, nst)
+        ms = ctypes_elapsed(e[0], 0, e[2], npst)
+        return ms
+
+    def ctypes_elapsed(ea, i, eb, j):
+        import ctypes
+        ms = ctypes.c_float()
+        _lib.check(_lib.ancsh_event_elapsed_ms(ea.arr[i], eb.arr[j], ctypes.byref(ms)), "elapsed")
+        return float(ms.value)
+
+    step_ms = [span(e) for e in evs]
     total_ms = sum(step_ms)
-    stage_ms = {nm: sum(e.elapsed_ms(i, i + 1) for e in evs) / args.steps for i, nm in enumerate(_lib.NET_STAGES)}
+    stage_ms = {nm: sum(e[0].elapsed_ms(i, i + 1) for e in evs) / args.steps for i, nm in enumerate(_lib.NET_STAGES)}
+    extra_ms = {}
+    if full:
+        if two_nets:
+            extra_ms["npcs_forward"] = sum(e[1].elapsed_ms(0, nst) for e in evs) / args.steps
+        for i, nm in enumerate(_lib.POSE_STAGES):
+            extra_ms["pose_" + nm] = sum(e[2].elapsed_ms(i, i + 1) for e in evs) / args.steps
 
     # ---- end to end through the public host API (host buffers, H2D + D2H inside the timed region) ----
+    def e2e_call():
+        if full:
+            return pipe.run(P_host, jc_host, unpack=False)
+        return pipe.net.forward(P_host, copy=False)
     for _ in range(2):
-        net.forward(P_host, copy=False)
+        e2e_call()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res = net.forward(P_host, copy=False)
+        r = e2e_call()
     e2e_s = time.perf_counter() - t0
-    h2d = P_host.nbytes
-    d2h = sum(v.nbytes for v in res.values())
+    h2d = P_host.nbytes + (jc_host.nbytes if full else 0)
+    d2h = sum(v.nbytes for v in r.values())
 
+    gathered = None
     if world > 1:
         t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_s = float(t[0]), float(t[1])
+        if full:   # the one collective of the path: gather the per-cloud pose records
+            rec = torch.cat([res["single_R"].reshape(B, -1), res["single_s"], res["single_t"].reshape(B, -1)], 1).contiguous()
+            allrec = [torch.empty_like(rec) for _ in range(world)]
+            dist.all_gather(allrec, rec)
+            gathered = sum(int(x.shape[0]) for x in allrec)
 
     if rank != 0:
         if world > 1:
@@ -241,41 +329,43 @@ def main():
         return
 
     peaks = measured_peaks()
-    fl = stage_flops(net, B, N)
-    dom = max(fl, key=lambda k: stage_ms[k])
+    fl = stage_flops(pipe.net, B, N)
+    dom = max(("sa1", "sa2"), key=lambda k: stage_ms[k])
     ach = fl[dom] / (stage_ms[dom] * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
-    roofline = {"bound": "tensor", "kernel": {"sa1": "sa_kernel<128> (layer1)", "sa2": "sa_kernel<128> (layer2)"}.get(dom, dom),
+    n_fwd = 2 if (full and two_nets) else 1
+    fwd_ms = sum(stage_ms.values())
+    roofline = {"bound": "tensor", "kernel": "sa_kernel<128> (%s, ANCSH net)" % dom,
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                 "peak_source": peaks["source"] + " bf16 sustained (kernel timed inside the step loop)",
                 "avg_launch_ms": stage_ms[dom], "flops_per_launch": fl[dom],
-                "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
-                "whole_forward_tflops": sum(fl.values()) / (total_ms / args.steps * 1e-3) / 1e12}
+                "stage_ms": {k: round(v, 4) for k, v in {**stage_ms, **extra_ms}.items()},
+                "forward_tflops": sum(fl.values()) / (fwd_ms * 1e-3) / 1e12}
 
     line = {"metric": METRIC, "value": world * B * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args, stages), "stages": stages, "l2_flush_between_steps": True,
-                       "weights": "seeded random (no checkpoint ships with the reference)",
-                       "wall_s_timed_region": round(t_wall, 4)},
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 network / f64 pose" if full else "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "stages": args.stages, "l2_flush_between_steps": True,
+                       "weights": "seeded random trunk, linear seg/NOCS heads ridge-fitted on %d synthetic clouds "
+                                  "(no checkpoint ships with the reference)" % CALIB_CLOUDS if full else "seeded random",
+                       "forwards_per_cloud": n_fwd, "mean_part_sizes": part_hist,
+                       "wall_s_timed_region": round(t_wall, 4), "all_gathered_records": gathered},
             "clocks": clocks,
             "e2e": {"value": world * B * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
-            "gpu_launches": 11 * args.steps,
+            "gpu_launches": (11 * n_fwd + (5 if full else 0)) * args.steps,
             "roofline": roofline}
 
     if not args.no_cpu_baseline:
         try:
-            from oracle import pnpp
-            cores = os.cpu_count() or 1
-            pnpp.set_threads(cores)
-            n_s = args.cpu_sample or 8
-            pnpp.forward(P_host[:1], w, K, nsample=args.nsample)
-            t0 = time.perf_counter()
-            pnpp.forward(P_host[:n_s], w, K, nsample=args.nsample)
-            dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": n_s / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "%d clouds of the same batch, network forward (oracle/pnpp.py, OpenMP over rows)" % n_s}
+            from oracle import pipeline_cpu
+            n_s = args.cpu_sample or (6 if full else 16)
+            cpu_reference_run(args, K, P_host, jc_host, w_a, w_n if full else None, 1, 1)       # warm (pool fork, page-in)
+            val, dt, cores, desc = cpu_reference_run(args, K, P_host, jc_host, w_a, w_n if full else None, n_s, 1)
+            pipeline_cpu.close_pool()
+            line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
+                                    "seconds": round(dt, 2)}
         except Exception as e:  # the baseline is reporting only; never lose the GPU line
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
     print(json.dumps(line))

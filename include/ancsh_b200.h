@@ -117,6 +117,8 @@ typedef struct {
     float *gocs_per_point;       /* (B,N,3K) nocs*scale+trans */
     float *global_scale;         /* (B,N,K)  sigmoid */
     float *global_translation;   /* (B,N,3K) tanh */
+    float *net;                  /* optional (may be NULL): (B,N,128) trunk feature after fc1 (architectures.py:89-93),
+                                    not part of pred_dict; used to fit synthetic head weights */
 } ancsh_pred_t;
 
 /* Byte offsets of the intermediates inside the caller-provided workspace (all 256-B aligned). */
@@ -220,9 +222,14 @@ typedef struct {
 
 int ancsh_pose_plan(const ancsh_pose_cfg_t *cfg, int B, int N, ancsh_pose_ws_t *layout);
 
-/* Solves B clouds.  N <= 4096, K <= 8. */
+enum {
+    ANCSH_POSE_STAGE_PARTITION = 0, ANCSH_POSE_STAGE_SINGLE_SCORE, ANCSH_POSE_STAGE_SINGLE_REFIT,
+    ANCSH_POSE_STAGE_JOINT_SCORE, ANCSH_POSE_STAGE_JOINT_REFIT, ANCSH_POSE_NSTAGES
+};
+
+/* Solves B clouds.  N <= 4096, K <= 8.  stage_events: NULL or ANCSH_POSE_NSTAGES+1 events (see ancsh_net_forward). */
 int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in_t *in, int B, int N, void *workspace,
-                     size_t workspace_bytes, const ancsh_pose_out_t *out, void *stream);
+                     size_t workspace_bytes, const ancsh_pose_out_t *out, void *const *stage_events, void *stream);
 
 /* Writes the sample positions the Philox generator produces for (seed, problem, hypothesis) so that a CPU
  * checker can replay them: idx (nprob,niter,3); n_per_problem (nprob) is the part size each problem samples

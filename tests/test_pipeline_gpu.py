@@ -1,0 +1,68 @@
+"""End-to-end plumbing of AncshPipeline (forward(s) -> pose, predictions never leaving HBM):
+the pipeline's poses equal PoseSolver run on the network's own host-copied predictions, the fitted synthetic heads
+give a realistic partition, and the whole chain agrees with the CPU oracle chain on the same clouds."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _weights(K, nsample):
+    from articulated_pose_b200 import synthetic, weights
+    from articulated_pose_b200.network import AncshNet
+    Pc, cc = synthetic.make_batch(range(900000, 900008))
+    cls = np.stack([c["cls_gt"] for c in cc]); nocs = np.stack([c["nocs_gt"] for c in cc])
+    w_a = weights.synthetic_weights(K, True, True, seed=7)
+    w_n = weights.synthetic_weights(K, False, False, seed=8)
+    w_a = weights.fit_heads(w_a, AncshNet(w_a, K, nsample=nsample).features(Pc), cls, nocs, K, True)
+    w_n = weights.fit_heads(w_n, AncshNet(w_n, K, mixed_pred=False, early_split_nocs=False, nsample=nsample).features(Pc),
+                            cls, nocs, K, False)
+    return w_a, w_n
+
+
+def test_pipeline_matches_stagewise_and_oracle():
+    from articulated_pose_b200 import synthetic
+    from articulated_pose_b200.network import AncshNet
+    from articulated_pose_b200.pipeline import AncshPipeline
+    from articulated_pose_b200.pose import PoseSolver
+    from oracle import pnpp, pose_np
+    K, ns, B = 3, 32, 3
+    w_a, w_n = _weights(K, ns)
+    P, clouds = synthetic.make_batch(range(60, 60 + B))
+    jc = np.stack([c["joint_cls_gt"] for c in clouds]).astype(np.int32)
+    pipe = AncshPipeline(w_a, K, weights_npcs=w_n, nsample=ns, niter_single=128, niter_joint=16, seed=5)
+    res = pipe.run(P, jc)
+    # (1) stage-wise on host copies of the same predictions
+    pa = AncshNet(w_a, K, nsample=ns).forward(P)
+    pn = AncshNet(w_n, K, mixed_pred=False, early_split_nocs=False, nsample=ns).forward(P)
+    solver = PoseSolver(K, niter_single=128, niter_joint=16, seed=5)
+    res2 = solver.solve(P, pn["nocs_per_point"], pn["W"], pa["joint_axis_per_point"], jc)
+    for b in range(B):
+        assert res[b]["part_count"].min() > 40, res[b]["part_count"]          # fitted heads: realistic partition
+        np.testing.assert_array_equal(res[b]["part_count"], res2[b]["part_count"])
+        for j in range(K):
+            np.testing.assert_array_equal(res[b]["baseline"][j]["rotation"], res2[b]["baseline"][j]["rotation"])
+        for j in range(K - 1):
+            np.testing.assert_array_equal(res[b]["nonlinear"][j]["rotation1"], res2[b]["nonlinear"][j]["rotation1"])
+    # (2) whole chain vs the CPU oracle chain (network outputs agree to 1e-4, so partitions can differ only for
+    #     points whose two best class scores are within that margin)
+    oa = pnpp.forward(P, w_a, K, nsample=ns)
+    on = pnpp.forward(P, w_n, K, nsample=ns, mixed_pred=False, early_split_nocs=False)
+    cnt = np.stack([r["part_count"] for r in res])
+    idx_s = solver.sample_indices(0, cnt.reshape(-1), 128).reshape(B, K, 128, 3)
+    idx_0 = solver.sample_indices(1, np.repeat(cnt[:, :1], K - 1, 1).reshape(-1), 16).reshape(B, K - 1, 16, 3)
+    idx_1 = solver.sample_indices(2, cnt[:, 1:].reshape(-1), 16).reshape(B, K - 1, 16, 3)
+    checked = 0
+    for b in range(B):
+        if not np.array_equal(np.argmax(on["W"][b], 1), np.argmax(pn["W"][b], 1)):
+            continue
+        ref = pose_np.solve_cloud(P[b], on["nocs_per_point"][b], on["W"][b], oa["joint_axis_per_point"][b], jc[b], K, 0.1,
+                                  idx_s[b], idx_0[b], idx_1[b])
+        for j in range(K):
+            same = np.array_equal(res[b]["inliers_single"][j], ref["inliers_single"][j])
+            if same:       # identical inlier sets -> the refit differs only by the 1e-4 input differences
+                assert np.abs(res[b]["baseline"][j]["rotation"] - ref["baseline"][j]["rotation"]).max() < 5e-3
+                assert abs(res[b]["baseline"][j]["scale"] - ref["baseline"][j]["scale"]) < 5e-3
+                checked += 1
+    assert checked >= 3

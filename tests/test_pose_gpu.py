@@ -47,7 +47,10 @@ def test_matches_reference_golden():
         assert (res["status"] == 0).all()
         for j in range(K):
             k = "c%d_p%d_" % (ci, j)
-            np.testing.assert_array_equal(inter["single_scores"][0, j], g[k + "scores"])
+            # hypotheses whose 3 samples repeat an index give a rank<=1 covariance: the rotation is then an
+            # arbitrary null-space choice inside LAPACK (and here) -- excluded from the exact comparison
+            ok = np.array([len(set(r)) == 3 for r in g[k + "idx"]])
+            np.testing.assert_array_equal(inter["single_scores"][0, j][ok], g[k + "scores"][ok])
             np.testing.assert_array_equal(res["inliers_single"][j], g[k + "inl"])
             m = res["baseline"][j]
             assert close(m["rotation"], g[k + "R"]) and close(m["scale"], g[k + "s"]) and close(m["translation"], g[k + "t"]), (ci, j)
@@ -55,7 +58,8 @@ def test_matches_reference_golden():
             k = "c%d_j%d_" % (ci, j)
             assert close(inter["axis_med"][0, j - 1], g[k + "axis"], 1e-12)
             sc = inter["joint_scores"][0, j - 1]
-            assert np.mean(sc == g[k + "scores"]) >= 0.95, (ci, j, np.mean(sc == g[k + "scores"]))
+            ok = np.array([len(set(a)) == 3 and len(set(b)) == 3 for a, b in zip(g[k + "idx0"], g[k + "idx1"])])
+            assert np.mean(sc[ok] == g[k + "scores"][ok]) >= 0.95, (ci, j, np.mean(sc[ok] == g[k + "scores"][ok]))
             assert int(inter["joint_best"][0, j - 1]) == int(np.argmax(g[k + "scores"]))
             np.testing.assert_array_equal(res["inliers_joint"][j - 1][0], g[k + "inl0"])
             np.testing.assert_array_equal(res["inliers_joint"][j - 1][1], g[k + "inl1"])
