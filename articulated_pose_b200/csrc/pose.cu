@@ -6,7 +6,8 @@
 //                          part's points staged in shared memory as f64            (:35-54)
 //   single_refit_kernel    first-max hypothesis, its inlier mask, refit on the inliers incl. the O(n^2)
 //                          pairwise-distance scale                                   (:28-32, d3_utils.py:223-246)
-//   joint_score_kernel     one thread per hypothesis: 3+3 samples, MINPACK-lmder LM (pose_math.cuh), score (:106-194)
+//   joint_estimate_kernel  one thread per hypothesis: 3+3 samples, MINPACK-lmder LM (pose_math.cuh / lm_fast.cuh) (:106-184)
+//   joint_verify_kernel    inlier counts of every hypothesis, warp per hypothesis                     (:186-194)
 //   joint_refit_kernel     first-max hypothesis, masks, block-cooperative LM refit on all inliers
 //   umeyama_kernel         lib/aligning.py:580-622 (GT poses, compute_gt_pose.py:87)
 #include "common.cuh"
@@ -340,6 +341,9 @@ struct JointArgs {
     const double *axis_med;             // (nprob, 3)
     const int *idx0, *idx1;             // NULL or (nprob, niter, 3)
     double *scores;                     // (nprob, niter)
+    int *nfev;                          // (nprob, niter)
+    pm::JointModel *models;             // (nprob, niter) per-hypothesis models
+    int nprob;
     int *best;                          // (nprob)
     int N, K, niter;
     double th2;
@@ -358,41 +362,65 @@ __device__ __forceinline__ void joint_parts(int prob, int K, int &pa, int &pb)
     pb = b * K + j;
 }
 
-constexpr int JT = 64;   // threads per block of the joint scoring kernel (one LM solve per thread)
+constexpr int JT = 64;   // threads per block of the joint estimation kernel (one LM solve per thread)
 
-__global__ void __launch_bounds__(JT) joint_score_kernel(const JointArgs a)
+// One thread per hypothesis: 3+3 samples -> joint_transformation_estimator (LM).  No shared memory, so the long
+// tail of slow LM solves (a few hypotheses need hundreds of residual evaluations, exactly as in MINPACK) holds only
+// registers and other kernels can share the SMs meanwhile.
+__global__ void __launch_bounds__(JT) joint_estimate_kernel(const JointArgs a)
 {
-    extern __shared__ double s_pts[];
-    const int prob = blockIdx.y;
+    const long t = (long)blockIdx.x * JT + threadIdx.x;
+    if (t >= (long)a.nprob * a.niter) return;
+    const int prob = (int)(t / a.niter), h = (int)(t - (long)prob * a.niter);
     int pa, pb;
     joint_parts(prob, a.K, pa, pb);
     const int n0 = a.part_count[pa], n1 = a.part_count[pb];
-    const int h = blockIdx.x * JT + threadIdx.x;
+    if (n0 <= 0 || n1 <= 0) { a.nfev[t] = 0; return; }
+    int i0[3], i1[3];
+    fetch_sample(a.idx0, a.seed, prob, h, 1u, a.niter, n0, i0);
+    fetch_sample(a.idx1, a.seed, prob, h, 2u, a.niter, n1, i1);
+    const float *gs0 = a.part_src + (size_t)pa * a.N * 3, *gt0 = a.part_tgt + (size_t)pa * a.N * 3;
+    const float *gs1 = a.part_src + (size_t)pb * a.N * 3, *gt1 = a.part_tgt + (size_t)pb * a.N * 3;
+    double S0[9], T0[9], S1[9], T1[9];
+    for (int i = 0; i < 3; ++i)
+        for (int c = 0; c < 3; ++c) {
+            S0[3 * i + c] = (double)gs0[3 * i0[i] + c]; T0[3 * i + c] = (double)gt0[3 * i0[i] + c];
+            S1[3 * i + c] = (double)gs1[3 * i1[i] + c]; T1[3 * i + c] = (double)gt1[3 * i1[i] + c];
+        }
+    pm::JointModel m;
+    const pm::LmResult lr = pm::joint_estimate3(S0, T0, S1, T1, a.axis_med + (size_t)prob * 3, m);
+    a.nfev[t] = lr.nfev;
+    a.models[t] = m;
+}
+
+// joint_transformation_verifier (:186-194): one block per problem, points staged in shared memory as f64, one
+// warp per hypothesis at a time, lanes over points.
+__global__ void __launch_bounds__(RT) joint_verify_kernel(const JointArgs a)
+{
+    extern __shared__ double s_pts[];
+    const int prob = blockIdx.x;
+    int pa, pb;
+    joint_parts(prob, a.K, pa, pb);
+    const int n0 = a.part_count[pa], n1 = a.part_count[pb];
     if (n0 <= 0 || n1 <= 0) {
-        if (h < a.niter) a.scores[(size_t)prob * a.niter + h] = 0.0;
+        for (int h = threadIdx.x; h < a.niter; h += RT) a.scores[(size_t)prob * a.niter + h] = 0.0;
         return;
     }
     double *s_src0 = s_pts, *s_tgt0 = s_src0 + 3 * n0, *s_src1 = s_tgt0 + 3 * n0, *s_tgt1 = s_src1 + 3 * n1;
     load_part_f64(a.part_src + (size_t)pa * a.N * 3, a.part_tgt + (size_t)pa * a.N * 3, n0, s_src0, s_tgt0);
     load_part_f64(a.part_src + (size_t)pb * a.N * 3, a.part_tgt + (size_t)pb * a.N * 3, n1, s_src1, s_tgt1);
     __syncthreads();
-    if (h >= a.niter) return;
-    int i0[3], i1[3];
-    fetch_sample(a.idx0, a.seed, prob, h, 1u, a.niter, n0, i0);
-    fetch_sample(a.idx1, a.seed, prob, h, 2u, a.niter, n1, i1);
-    double S0[9], T0[9], S1[9], T1[9];
-    for (int i = 0; i < 3; ++i)
-        for (int c = 0; c < 3; ++c) {
-            S0[3 * i + c] = s_src0[3 * i0[i] + c]; T0[3 * i + c] = s_tgt0[3 * i0[i] + c];
-            S1[3 * i + c] = s_src1[3 * i1[i] + c]; T1[3 * i + c] = s_tgt1[3 * i1[i] + c];
-        }
-    pm::JointModel m;
-    pm::joint_estimate3(S0, T0, S1, T1, a.axis_med + (size_t)prob * 3, m);
-    int c0 = 0, c1 = 0;
-    for (int i = 0; i < n0; ++i) c0 += is_inlier(m.R0, m.s0, m.t0, s_src0 + 3 * i, s_tgt0 + 3 * i, a.th2) ? 1 : 0;
-    for (int i = 0; i < n1; ++i) c1 += is_inlier(m.R1, m.s1, m.t1, s_src1 + 3 * i, s_tgt1 + 3 * i, a.th2) ? 1 : 0;
-    // score = (sum(inl0)/res0.shape[0] + sum(inl1)/res1.shape[0]) / 2 with shape[0] == 3   (:193)
-    a.scores[(size_t)prob * a.niter + h] = ((double)c0 / 3.0 + (double)c1 / 3.0) / 2.0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int h = warp; h < a.niter; h += RT / 32) {
+        const pm::JointModel &m = a.models[(size_t)prob * a.niter + h];
+        int c0 = 0, c1 = 0;
+        for (int i = lane; i < n0; i += 32) c0 += is_inlier(m.R0, m.s0, m.t0, s_src0 + 3 * i, s_tgt0 + 3 * i, a.th2) ? 1 : 0;
+        for (int i = lane; i < n1; i += 32) c1 += is_inlier(m.R1, m.s1, m.t1, s_src1 + 3 * i, s_tgt1 + 3 * i, a.th2) ? 1 : 0;
+        c0 = __reduce_add_sync(0xFFFFFFFFu, c0);
+        c1 = __reduce_add_sync(0xFFFFFFFFu, c1);
+        // score = (sum(inl0)/res0.shape[0] + sum(inl1)/res1.shape[0]) / 2 with shape[0] == 3   (:193)
+        if (lane == 0) a.scores[(size_t)prob * a.niter + h] = ((double)c0 / 3.0 + (double)c1 / 3.0) / 2.0;
+    }
 }
 
 // block-cooperative evaluator of objective_eval over the masked (inlier) points in shared memory
@@ -497,16 +525,7 @@ __global__ void __launch_bounds__(RT) joint_refit_kernel(const JointArgs a)
     const double *axis = a.axis_med + (size_t)prob * 3;
     const int hbest = block_first_argmax_f64(a.scores + (size_t)prob * a.niter, a.niter, s_val, s_idx);   // syncs
     if (tid == 0) {
-        int i0[3], i1[3];
-        fetch_sample(a.idx0, a.seed, prob, hbest, 1u, a.niter, n0, i0);
-        fetch_sample(a.idx1, a.seed, prob, hbest, 2u, a.niter, n1, i1);
-        double S0[9], T0[9], S1[9], T1[9];
-        for (int i = 0; i < 3; ++i)
-            for (int c = 0; c < 3; ++c) {
-                S0[3 * i + c] = s_src0[3 * i0[i] + c]; T0[3 * i + c] = s_tgt0[3 * i0[i] + c];
-                S1[3 * i + c] = s_src1[3 * i1[i] + c]; T1[3 * i + c] = s_tgt1[3 * i1[i] + c];
-            }
-        pm::joint_estimate3(S0, T0, S1, T1, axis, s_model);
+        s_model = a.models[(size_t)prob * a.niter + hbest];       // the winning hypothesis' model (joint_estimate_kernel)
         a.best[prob] = hbest;
         a.score_out[prob] = a.scores[(size_t)prob * a.niter + hbest];
     }
@@ -591,7 +610,7 @@ __global__ void __launch_bounds__(RT) joint_refit_kernel(const JointArgs a)
     P.u[0] = axis[0]; P.u[1] = axis[1]; P.u[2] = axis[2];
     P.nj = (double)min(nin0, nin1);
     P.s_red = s_red;
-    pm::lm_solve(P, x, 1e-4, 1e-8, 1e-8, 600, 100.0);            // uniform control flow: every thread sees the same sums
+    pm::lm_solve_fast(P, x, 1e-4, 1e-8, 1e-8, 600, 100.0);       // uniform control flow: every thread sees the same sums
     if (tid == 0) {
         pm::rotvec_to_matrix(x, R0);
         pm::rotvec_to_matrix(x + 3, R1);
@@ -690,6 +709,8 @@ extern "C" int ancsh_pose_plan(const ancsh_pose_cfg_t *cfg, int B, int N, ancsh_
     L->joint_scores = take(b * (K > 1 ? K - 1 : 1) * (size_t)cfg->niter_joint * 8);
     L->single_best = take(b * K * 4);
     L->joint_best = take(b * (K > 1 ? K - 1 : 1) * 4);
+    L->joint_nfev = take(b * (K > 1 ? K - 1 : 1) * (size_t)cfg->niter_joint * 4);
+    L->joint_models = take(b * (K > 1 ? K - 1 : 1) * (size_t)cfg->niter_joint * sizeof(pm::JointModel));
     L->total_bytes = off;
     return ANCSH_OK;
 }
@@ -759,14 +780,19 @@ extern "C" int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in
         JointArgs a{};
         a.part_src = part_src; a.part_tgt = part_tgt; a.part_count = out->part_count; a.axis_med = axis_med;
         a.idx0 = in->idx_joint0; a.idx1 = in->idx_joint1; a.scores = joint_scores; a.best = joint_best;
+        a.nfev = (int *)(ws + L.joint_nfev);
+        a.models = (pm::JointModel *)(ws + L.joint_models);
+        a.nprob = B * (K - 1);
         a.N = N; a.K = K; a.niter = cfg->niter_joint; a.th2 = th2; a.seed = cfg->seed;
         a.R0 = out->joint_R0; a.s0 = out->joint_s0; a.t0 = out->joint_t0;
         a.R1 = out->joint_R1; a.s1 = out->joint_s1; a.t1 = out->joint_t1; a.score_out = out->joint_score;
         a.inl0 = out->joint_inliers0; a.inl1 = out->joint_inliers1; a.status = out->status;
         size_t smem = (size_t)N * 6 * sizeof(double);          // n0 + n1 <= N
-        ANCSH_CUDA(cudaFuncSetAttribute(joint_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid(ancsh_cdiv(cfg->niter_joint, JT), B * (K - 1));
-        joint_score_kernel<<<grid, JT, smem, st>>>(a);
+        const long nthreads = (long)a.nprob * cfg->niter_joint;
+        joint_estimate_kernel<<<(unsigned)((nthreads + JT - 1) / JT), JT, 0, st>>>(a);
+        ANCSH_CHECK_LAUNCH();
+        ANCSH_CUDA(cudaFuncSetAttribute(joint_verify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        joint_verify_kernel<<<a.nprob, RT, smem, st>>>(a);
         ANCSH_CHECK_LAUNCH();
         STAGE_MARK();
         size_t smem2 = smem + N + 16;

@@ -658,6 +658,8 @@ PM_HDN inline LmResult lm_solve(const Prob &prob, double *x, double ftol, double
     return res;
 }
 
+#include "lm_fast.cuh"
+
 // ---------------------------------------------------------------------------------------------------
 // scale_pts (d3_utils.py:237-246) for a handful of points (all ordered pairs; i==j pairs contribute 0)
 // ---------------------------------------------------------------------------------------------------
@@ -762,7 +764,7 @@ PM_HDN inline LmResult joint_estimate3(const double *S0, const double *T0, const
     P.x0 = S0c; P.y0 = T0c; P.n0 = 3; P.x1 = S1c; P.y1 = T1c; P.n1 = 3;
     P.u[0] = u[0]; P.u[1] = u[1]; P.u[2] = u[2];
     P.nj = 3.0;                                                // min(n0,n1) copies of the joint direction, :134
-    LmResult r = lm_solve(P, x, 1e-4, 1e-8, 1e-8, 600, 100.0); // :154-155
+    LmResult r = lm_solve_fast(P, x, 1e-4, 1e-8, 1e-8, 600, 100.0); // :154-155
     rotvec_to_matrix(x, m.R0);                                 // :156-157
     rotvec_to_matrix(x + 3, m.R1);
     mean_translation(S0, T0, 3, m.R0, m.s0, m.t0);             // :174-175 (un-refined scale)

@@ -28,6 +28,8 @@ class AncshPipeline:
                                      device=device)
         self.pose = PoseSolver(n_parts, niter_single, niter_joint, inlier_th, seed, device)
         self._buf = {}
+        self._slots = {}
+        self._pose_stream = None
 
     def _buffers(self, B, N):
         key = (B, N)
@@ -53,6 +55,95 @@ class AncshPipeline:
             src = self.net_npcs.forward_device(P, buf["pred_b"], stage_events=net_b_events)
         return self.pose.solve_device(P, src["nocs_per_point"], src["W"], pred["joint_axis_per_point"], joint_cls,
                                       out=buf["pose"], stage_events=pose_events)
+
+    # ---- stream-pipelined submission: the pose stage of batch i overlaps the forwards of batch i+1 ----------
+    def _slot(self, B, N, slot):
+        key = (B, N, slot)
+        if key not in self._slots:
+            d = {"pred": self.net.alloc_outputs(B, N), "pose": self.pose.alloc_outputs(B, N), "fwd_done": torch.cuda.Event(),
+                 "pose_done": torch.cuda.Event(), "used": False}
+            if self.net_npcs is not None:
+                d["pred_b"] = self.net_npcs.alloc_outputs(B, N)
+            self._slots[key] = d
+        return self._slots[key]
+
+    def submit(self, P, joint_cls, slot=0, net_events=None, net_b_events=None, pose_events=None):
+        """Asynchronous run_device: the forwards are enqueued on the current stream, the pose stage on an
+        internal side stream that waits for them; buffers are per `slot` (use 2 slots, alternating).  The slow tail
+        of the joint LM solves then overlaps the next batch's forwards.  Returns the slot's pose tensors; call
+        `join()` (or wait on the returned dict's "done" event) before reading them."""
+        B, N, _ = P.shape
+        sl = self._slot(B, N, slot)
+        main = torch.cuda.current_stream()
+        if self._pose_stream is None:
+            self._pose_stream = torch.cuda.Stream(device=self.device)
+        if sl["used"]:
+            main.wait_event(sl["pose_done"])          # the slot's prediction buffers are still being read
+        pred = self.net.forward_device(P, sl["pred"], stage_events=net_events)
+        src = pred
+        if self.net_npcs is not None:
+            src = self.net_npcs.forward_device(P, sl["pred_b"], stage_events=net_b_events)
+        sl["fwd_done"].record(main)
+        with torch.cuda.stream(self._pose_stream):
+            self._pose_stream.wait_event(sl["fwd_done"])
+            out = self.pose.solve_device(P, src["nocs_per_point"], src["W"], pred["joint_axis_per_point"], joint_cls,
+                                         out=sl["pose"], stage_events=pose_events)
+            sl["pose_done"].record(self._pose_stream)
+        sl["used"] = True
+        return out
+
+    def join(self):
+        """Make the current stream wait for every submitted pose stage."""
+        main = torch.cuda.current_stream()
+        for sl in self._slots.values():
+            if sl["used"]:
+                main.wait_event(sl["pose_done"])
+
+    def run_many(self, batches, unpack=False):
+        """Host API for a stream of batches [(P, joint_cls), ...] (all the same shape): pinned H2D, forwards and
+        pose stages pipelined over two slots, D2H of the pose records.  Returns one result per batch."""
+        if not batches:
+            return []
+        B, N, _ = batches[0][0].shape
+        key = ("many", B, N)
+        if key not in self._buf:
+            self._buf[key] = [{"hP": torch.empty((B, N, 3), dtype=torch.float32).pin_memory(),
+                               "hjc": torch.empty((B, N), dtype=torch.int32).pin_memory(),
+                               "P": torch.empty((B, N, 3), dtype=torch.float32, device=self.device),
+                               "jc": torch.empty((B, N), dtype=torch.int32, device=self.device),
+                               "hpose": {k: torch.empty(v.shape, dtype=v.dtype).pin_memory()
+                                         for k, v in self.pose.alloc_outputs(B, N).items()},
+                               "copied": torch.cuda.Event()} for _ in range(2)]
+        bufs = self._buf[key]
+        results = [None] * len(batches)
+        pending = [None, None]
+        with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream()
+
+            def drain(slot):
+                if pending[slot] is None:
+                    return
+                i, out = pending[slot]
+                main.wait_event(self._slot(B, N, slot)["pose_done"])
+                for k, v in out.items():
+                    bufs[slot]["hpose"][k].copy_(v, non_blocking=True)
+                bufs[slot]["copied"].record(main)
+                bufs[slot]["copied"].synchronize()
+                h = {k: v.numpy().copy() for k, v in bufs[slot]["hpose"].items()}
+                results[i] = unpack_results(h, self.K) if unpack else h
+                pending[slot] = None
+
+            for i, (P, jc) in enumerate(batches):
+                slot = i % 2
+                drain(slot)                              # results of batch i-2 (its slot is about to be reused)
+                bufs[slot]["hP"].numpy()[...] = P
+                bufs[slot]["hjc"].numpy()[...] = jc
+                bufs[slot]["P"].copy_(bufs[slot]["hP"], non_blocking=True)
+                bufs[slot]["jc"].copy_(bufs[slot]["hjc"], non_blocking=True)
+                pending[slot] = (i, self.submit(bufs[slot]["P"], bufs[slot]["jc"], slot=slot))
+            for slot in ((len(batches)) % 2, (len(batches) + 1) % 2):
+                drain(slot)
+        return results
 
     def run(self, P, joint_cls, unpack=True):
         """Host arrays in, host results out: pinned H2D of the clouds, all stages on the device, D2H of the poses

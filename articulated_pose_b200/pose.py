@@ -46,6 +46,8 @@ _WS_SPEC = {
     "joint_scores": (torch.float64, lambda B, K, N, J, ns, nj: (B, J, nj)),
     "single_best": (torch.int32, lambda B, K, N, J, ns, nj: (B, K)),
     "joint_best": (torch.int32, lambda B, K, N, J, ns, nj: (B, J)),
+    "joint_nfev": (torch.int32, lambda B, K, N, J, ns, nj: (B, J, nj)),
+    "joint_models": (torch.float64, lambda B, K, N, J, ns, nj: (B, J, nj, 26)),
 }
 _ESIZE = {torch.int32: 4, torch.float32: 4, torch.float64: 8, torch.uint8: 1}
 

@@ -189,7 +189,7 @@ def flatten_packed(layers):
     return flat, offs
 
 
-def fit_heads(weights, features, cls_gt, nocs_gt, n_parts, early_split_nocs=True, prefix="SPFN", ridge=1e-2):
+def fit_heads(weights, features, cls_gt, nocs_gt, n_parts, early_split_nocs=True, prefix="SPFN", ridge=1e-6):
     """Synthetic-but-meaningful heads: keep the random trunk, fit the linear segmentation and NOCS heads by ridge
     regression of the trunk feature `net` (AncshNet.features) onto ground truth of a few synthetic clouds.
 

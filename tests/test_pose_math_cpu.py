@@ -115,10 +115,10 @@ def _problem(rng, n0, n1, noise, garbage=False):
     return x0, y0, x1, y1, u, init
 
 
-def _run_ours(lib, x0, y0, x1, y1, u, init, ftol=1e-4):
+def _run_ours(lib, x0, y0, x1, y1, u, init, ftol=1e-4, fast=True):
     x = init.copy(); out = np.zeros(3)
     c = np.ascontiguousarray
-    info = lib.hs_lm(dp(c(x0)), dp(c(y0)), len(x0), dp(c(x1)), dp(c(y1)), len(x1), dp(c(u)), ctypes.c_double(min(len(x0), len(x1))),
+    info = (lib.hs_lm_fast if fast else lib.hs_lm)(dp(c(x0)), dp(c(y0)), len(x0), dp(c(x1)), dp(c(y1)), len(x1), dp(c(u)), ctypes.c_double(min(len(x0), len(x1))),
                      dp(x), ctypes.c_double(ftol), ctypes.c_double(1e-8), ctypes.c_double(1e-8), 600, ctypes.c_double(100.0), dp(out))
     return x, info, int(out[0]), int(out[1])
 
@@ -218,3 +218,19 @@ def test_sample3_range_and_determinism(lib):
         assert (a == b).all() and (a >= 0).all() and (a < 341).all()
         seen.add(tuple(a))
     assert len(seen) > 190
+
+
+def test_fast_lm_equals_literal_minpack_port(lib):
+    """lm_fast.cuh (what the kernels run) vs the literal qrfac/qrsolv port: same iterates, same nfev."""
+    rng = np.random.default_rng(21)
+    same_nfev, worst = 0, 0.0
+    n = 300
+    for t in range(n):
+        prob = _problem(rng, 3, 3, 0.02, garbage=(t % 3 == 0))
+        xa, ia, na, _ = _run_ours(lib, *prob, fast=True)
+        xb, ib, nb, _ = _run_ours(lib, *prob, fast=False)
+        same_nfev += int(na == nb and ia == ib)
+        if na == nb:
+            worst = max(worst, np.abs(xa - xb).max())
+    assert same_nfev >= 0.97 * n, same_nfev
+    assert worst < 1e-8, worst
