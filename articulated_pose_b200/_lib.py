@@ -98,7 +98,7 @@ POSE_OUT_FIELDS = ("single_R", "single_s", "single_t", "single_score", "single_i
                    "joint_t0", "joint_R1", "joint_s1", "joint_t1", "joint_score", "joint_inliers0", "joint_inliers1",
                    "part_count", "status")
 POSE_WS_FIELDS = ("part_idx", "part_src", "part_tgt", "axis_med", "single_scores", "joint_scores", "single_best",
-                  "joint_best", "joint_nfev", "joint_models", "total_bytes")
+                  "joint_best", "joint_nfev", "joint_models", "joint_tail", "total_bytes")
 
 
 class PoseIn(ctypes.Structure):

@@ -70,16 +70,42 @@ PM_HD double norm6(const double (&v)[6])
     return sqrt(s);
 }
 
+// Resumable state of an LM solve, valid at the top of an outer iteration (before the Jacobian is evaluated).
+struct LmState {
+    double x[6], fnorm, par, delta, xnorm;
+    int iter, nfev, njev;
+};
+constexpr int LM_SUSPENDED = -1;
+
+// `state` != nullptr makes the solve resumable: a call with state->iter == 0 starts fresh, otherwise it continues
+// from the saved state; when res.nfev reaches `budget` at the top of an outer iteration the state is saved and
+// info = LM_SUSPENDED is returned.  The sequence of iterates is independent of where the solve was suspended.
 template <class Prob>
 PM_HDN inline LmResult lm_solve_fast(const Prob &prob, double *x, double ftol, double xtol, double gtol, int maxfev,
-                                     double factor)
+                                     double factor, LmState *state = nullptr, int budget = 0x7fffffff)
 {
     LmResult res;
     res.nfev = 1; res.njev = 0; res.info = 0;
-    double fnorm = sqrt(prob.cost(x));
-    double par = 0.0, delta = 0.0, xnorm = 0.0;
+    double fnorm, par = 0.0, delta = 0.0, xnorm = 0.0;
     int iter = 1;
+    if (state && state->iter > 0) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) x[j] = state->x[j];
+        fnorm = state->fnorm; par = state->par; delta = state->delta; xnorm = state->xnorm;
+        iter = state->iter; res.nfev = state->nfev; res.njev = state->njev;
+    } else {
+        fnorm = sqrt(prob.cost(x));
+    }
     for (;;) {
+        if (state && res.nfev >= budget) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) state->x[j] = x[j];
+            state->fnorm = fnorm; state->par = par; state->delta = delta; state->xnorm = xnorm;
+            state->iter = iter; state->nfev = res.nfev; state->njev = res.njev;
+            res.info = LM_SUSPENDED;
+            res.fnorm = fnorm;
+            return res;
+        }
         double A[6][6], g[6], acn[6];
         int perm[6];
         {

@@ -111,6 +111,7 @@ static int sa_launch(const SaArgs &a0, int B, cudaStream_t st)
     size_t smem = ((size_t)TM * (a.ldA + a.ldB) + WS_FLOATS) * sizeof(float);
     if (smem > 227 * 1024) return ANCSH_ERR_UNSUPPORTED;
     ANCSH_CUDA(cudaFuncSetAttribute(sa_kernel<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ANCSH_CUDA(cudaFuncSetAttribute(sa_kernel<TM>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     ANCSH_CUDA(cudaMemsetAsync(a.out, 0, (size_t)B * a.m * a.L[2].cout * sizeof(float), st));
     dim3 grid((unsigned)(rows / TM), B);
     sa_kernel<TM><<<grid, NT, smem, st>>>(a);
@@ -339,6 +340,7 @@ static int fp_launch(const FpArgs &a0, int B, cudaStream_t st)
     size_t smem = ((size_t)TM * (a.ldA + a.ldB + a.ldC) + WS_FLOATS + (size_t)a.m2 * 3 + (size_t)TM * 6) * sizeof(float);
     if (smem > 227 * 1024) return ANCSH_ERR_UNSUPPORTED;
     ANCSH_CUDA(cudaFuncSetAttribute(fp_kernel<TM, HEADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ANCSH_CUDA(cudaFuncSetAttribute(fp_kernel<TM, HEADS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     dim3 grid(a.n1 / TM, B);
     fp_kernel<TM, HEADS><<<grid, NT, smem, st>>>(a);
     ANCSH_CHECK_LAUNCH();

@@ -10,6 +10,7 @@
 //   joint_verify_kernel    inlier counts of every hypothesis, warp per hypothesis                     (:186-194)
 //   joint_refit_kernel     first-max hypothesis, masks, block-cooperative LM refit on all inliers
 //   umeyama_kernel         lib/aligning.py:580-622 (GT poses, compute_gt_pose.py:87)
+#include <stdlib.h>
 #include "common.cuh"
 #include "pose_math.cuh"
 
@@ -335,6 +336,7 @@ __global__ void __launch_bounds__(RT) single_refit_kernel(const SingleArgs a)
 // ================================================================================================
 // joint RANSAC
 // ================================================================================================
+struct TailItem;
 struct JointArgs {
     const float *part_src, *part_tgt;   // (nparts_total, N, 3)
     const int *part_count;              // (nparts_total)
@@ -344,6 +346,8 @@ struct JointArgs {
     int *nfev;                          // (nprob, niter)
     pm::JointModel *models;             // (nprob, niter) per-hypothesis models
     int nprob;
+    int *tail_count, *tail_next;        // work list of suspended LM solves
+    struct TailItem *tail_items;        // (nprob * niter)
     int *best;                          // (nprob)
     int N, K, niter;
     double th2;
@@ -362,12 +366,41 @@ __device__ __forceinline__ void joint_parts(int prob, int K, int &pa, int &pb)
     pb = b * K + j;
 }
 
-constexpr int JT = 64;   // threads per block of the joint estimation kernel (one LM solve per thread)
+constexpr int JT = 32;   // threads per block of the joint estimation kernels (one LM solve per thread).
+// __launch_bounds__(32, 9) caps them at 224 registers: 4 such warps (28.7k registers) still leave room for one
+// 256-thread MLP block (34.8k) on the same SM, so lingering LM warps never lock the forward kernels out.
 
-// One thread per hypothesis: 3+3 samples -> joint_transformation_estimator (LM).  No shared memory, so the long
-// tail of slow LM solves (a few hypotheses need hundreds of residual evaluations, exactly as in MINPACK) holds only
-// registers and other kernels can share the SMs meanwhile.
-__global__ void __launch_bounds__(JT) joint_estimate_kernel(const JointArgs a)
+// One thread per hypothesis: 3+3 samples -> joint_transformation_estimator (LM), in two phases.  MINPACK's LM needs
+// ~10 residual evaluations for most hypotheses but hundreds for a few (exactly as in the reference), and one thread
+// needs tens of microseconds per evaluation.  Phase 1 gives every hypothesis LM_BUDGET1 evaluations; solves that are
+// not finished by then are suspended (lm_fast.cuh, bit-identical to an uninterrupted solve) and appended to a
+// work list that phase 2 drains with a handful of densely packed warps, so the long tail holds ~1 warp per SM and
+// the rest of the machine is free for other kernels (the next batch's forwards run on another stream).
+constexpr int LM_BUDGET1 = 24;
+
+struct TailItem {
+    int t;
+    pm::LmState st;
+};
+
+static_assert(sizeof(TailItem) <= 112, "ancsh_pose_plan reserves 112 bytes per suspended solve");
+
+__device__ __forceinline__ void gather_joint_samples(const JointArgs &a, int prob, int h, int pa, int pb, int n0, int n1,
+                                                     double *S0, double *T0, double *S1, double *T1)
+{
+    int i0[3], i1[3];
+    fetch_sample(a.idx0, a.seed, prob, h, 1u, a.niter, n0, i0);
+    fetch_sample(a.idx1, a.seed, prob, h, 2u, a.niter, n1, i1);
+    const float *gs0 = a.part_src + (size_t)pa * a.N * 3, *gt0 = a.part_tgt + (size_t)pa * a.N * 3;
+    const float *gs1 = a.part_src + (size_t)pb * a.N * 3, *gt1 = a.part_tgt + (size_t)pb * a.N * 3;
+    for (int i = 0; i < 3; ++i)
+        for (int c = 0; c < 3; ++c) {
+            S0[3 * i + c] = (double)gs0[3 * i0[i] + c]; T0[3 * i + c] = (double)gt0[3 * i0[i] + c];
+            S1[3 * i + c] = (double)gs1[3 * i1[i] + c]; T1[3 * i + c] = (double)gt1[3 * i1[i] + c];
+        }
+}
+
+__global__ void __launch_bounds__(JT, 9) joint_estimate_kernel(const JointArgs a)
 {
     const long t = (long)blockIdx.x * JT + threadIdx.x;
     if (t >= (long)a.nprob * a.niter) return;
@@ -376,21 +409,41 @@ __global__ void __launch_bounds__(JT) joint_estimate_kernel(const JointArgs a)
     joint_parts(prob, a.K, pa, pb);
     const int n0 = a.part_count[pa], n1 = a.part_count[pb];
     if (n0 <= 0 || n1 <= 0) { a.nfev[t] = 0; return; }
-    int i0[3], i1[3];
-    fetch_sample(a.idx0, a.seed, prob, h, 1u, a.niter, n0, i0);
-    fetch_sample(a.idx1, a.seed, prob, h, 2u, a.niter, n1, i1);
-    const float *gs0 = a.part_src + (size_t)pa * a.N * 3, *gt0 = a.part_tgt + (size_t)pa * a.N * 3;
-    const float *gs1 = a.part_src + (size_t)pb * a.N * 3, *gt1 = a.part_tgt + (size_t)pb * a.N * 3;
     double S0[9], T0[9], S1[9], T1[9];
-    for (int i = 0; i < 3; ++i)
-        for (int c = 0; c < 3; ++c) {
-            S0[3 * i + c] = (double)gs0[3 * i0[i] + c]; T0[3 * i + c] = (double)gt0[3 * i0[i] + c];
-            S1[3 * i + c] = (double)gs1[3 * i1[i] + c]; T1[3 * i + c] = (double)gt1[3 * i1[i] + c];
-        }
+    gather_joint_samples(a, prob, h, pa, pb, n0, n1, S0, T0, S1, T1);
     pm::JointModel m;
-    const pm::LmResult lr = pm::joint_estimate3(S0, T0, S1, T1, a.axis_med + (size_t)prob * 3, m);
-    a.nfev[t] = lr.nfev;
-    a.models[t] = m;
+    pm::LmState st;
+    st.iter = 0;
+    const pm::LmResult lr = pm::joint_estimate3(S0, T0, S1, T1, a.axis_med + (size_t)prob * 3, m, &st, LM_BUDGET1);
+    if (lr.info == pm::LM_SUSPENDED) {
+        const int slot = atomicAdd(a.tail_count, 1);
+        a.tail_items[slot].t = (int)t;
+        a.tail_items[slot].st = st;
+    } else {
+        a.nfev[t] = lr.nfev;
+        a.models[t] = m;
+    }
+}
+
+__global__ void __launch_bounds__(JT, 9) joint_estimate_tail_kernel(const JointArgs a)
+{
+    const int count = *a.tail_count;
+    for (;;) {
+        const int w = atomicAdd(a.tail_next, 1);          // dynamic hand-out: lanes that finish early take more items
+        if (w >= count) break;
+        const int t = a.tail_items[w].t;
+        pm::LmState st = a.tail_items[w].st;
+        const int prob = t / a.niter, h = t - prob * a.niter;
+        int pa, pb;
+        joint_parts(prob, a.K, pa, pb);
+        const int n0 = a.part_count[pa], n1 = a.part_count[pb];
+        double S0[9], T0[9], S1[9], T1[9];
+        gather_joint_samples(a, prob, h, pa, pb, n0, n1, S0, T0, S1, T1);
+        pm::JointModel m;
+        const pm::LmResult lr = pm::joint_estimate3(S0, T0, S1, T1, a.axis_med + (size_t)prob * 3, m, &st, 0x7fffffff);
+        a.nfev[t] = lr.nfev;
+        a.models[t] = m;
+    }
 }
 
 // joint_transformation_verifier (:186-194): one block per problem, points staged in shared memory as f64, one
@@ -711,6 +764,7 @@ extern "C" int ancsh_pose_plan(const ancsh_pose_cfg_t *cfg, int B, int N, ancsh_
     L->joint_best = take(b * (K > 1 ? K - 1 : 1) * 4);
     L->joint_nfev = take(b * (K > 1 ? K - 1 : 1) * (size_t)cfg->niter_joint * 4);
     L->joint_models = take(b * (K > 1 ? K - 1 : 1) * (size_t)cfg->niter_joint * sizeof(pm::JointModel));
+    L->joint_tail = take(256 + b * (K > 1 ? K - 1 : 1) * (size_t)cfg->niter_joint * 112);   /* counters + TailItem[] */
     L->total_bytes = off;
     return ANCSH_OK;
 }
@@ -752,6 +806,7 @@ extern "C" int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in
         while (npow2 < N) npow2 <<= 1;
         size_t smem = ((N + 15) & ~15) + (size_t)RT * 8 * 4 + (size_t)3 * npow2 * 4;
         ANCSH_CUDA(cudaFuncSetAttribute(partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ANCSH_CUDA(cudaFuncSetAttribute(partition_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         partition_kernel<<<B, RT, smem, st>>>(a);
         ANCSH_CHECK_LAUNCH();
     }
@@ -766,12 +821,14 @@ extern "C" int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in
         a.inliers = out->single_inliers; a.status = out->status;
         size_t smem = (size_t)N * 6 * sizeof(double);
         ANCSH_CUDA(cudaFuncSetAttribute(single_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ANCSH_CUDA(cudaFuncSetAttribute(single_score_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         dim3 grid(ancsh_cdiv(cfg->niter_single, RT), B * K);
         single_score_kernel<<<grid, RT, smem, st>>>(a);
         ANCSH_CHECK_LAUNCH();
         STAGE_MARK();
         size_t smem2 = smem + N;
         ANCSH_CUDA(cudaFuncSetAttribute(single_refit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        ANCSH_CUDA(cudaFuncSetAttribute(single_refit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         single_refit_kernel<<<B * K, RT, smem2, st>>>(a);
         ANCSH_CHECK_LAUNCH();
     }
@@ -783,20 +840,36 @@ extern "C" int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in
         a.nfev = (int *)(ws + L.joint_nfev);
         a.models = (pm::JointModel *)(ws + L.joint_models);
         a.nprob = B * (K - 1);
+        a.tail_count = (int *)(ws + L.joint_tail);
+        a.tail_next = a.tail_count + 1;
+        a.tail_items = (TailItem *)(ws + L.joint_tail + 256);
+        ANCSH_CUDA(cudaMemsetAsync(a.tail_count, 0, 2 * sizeof(int), st));
         a.N = N; a.K = K; a.niter = cfg->niter_joint; a.th2 = th2; a.seed = cfg->seed;
         a.R0 = out->joint_R0; a.s0 = out->joint_s0; a.t0 = out->joint_t0;
         a.R1 = out->joint_R1; a.s1 = out->joint_s1; a.t1 = out->joint_t1; a.score_out = out->joint_score;
         a.inl0 = out->joint_inliers0; a.inl1 = out->joint_inliers1; a.status = out->status;
         size_t smem = (size_t)N * 6 * sizeof(double);          // n0 + n1 <= N
         const long nthreads = (long)a.nprob * cfg->niter_joint;
+        // Same shared-memory carveout as the MLP kernels these two overlap with (they use no shared memory themselves):
+        // SMs cannot host kernels with different L1/shared splits at the same time.
+        ANCSH_CUDA(cudaFuncSetAttribute(joint_estimate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        ANCSH_CUDA(cudaFuncSetAttribute(joint_estimate_tail_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         joint_estimate_kernel<<<(unsigned)((nthreads + JT - 1) / JT), JT, 0, st>>>(a);
         ANCSH_CHECK_LAUNCH();
+        {
+            const char *eb = getenv("ANCSH_TAIL_BLOCKS");
+            const int tb = eb ? atoi(eb) : 296;
+            joint_estimate_tail_kernel<<<tb, JT, 0, st>>>(a);
+        }
+        ANCSH_CHECK_LAUNCH();
         ANCSH_CUDA(cudaFuncSetAttribute(joint_verify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ANCSH_CUDA(cudaFuncSetAttribute(joint_verify_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         joint_verify_kernel<<<a.nprob, RT, smem, st>>>(a);
         ANCSH_CHECK_LAUNCH();
         STAGE_MARK();
         size_t smem2 = smem + N + 16;
         ANCSH_CUDA(cudaFuncSetAttribute(joint_refit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        ANCSH_CUDA(cudaFuncSetAttribute(joint_refit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         joint_refit_kernel<<<B * (K - 1), RT, smem2, st>>>(a);
         ANCSH_CHECK_LAUNCH();
     } else {

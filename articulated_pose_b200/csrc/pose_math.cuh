@@ -749,22 +749,26 @@ PM_HDN inline void mean_translation(const double *S, const double *T, int n, con
     for (int c = 0; c < 3; ++c) t[c] = acc[c] / n;
 }
 
+// state != nullptr: resumable (see lm_fast.cuh); the model is only valid when the returned info != LM_SUSPENDED.
 PM_HDN inline LmResult joint_estimate3(const double *S0, const double *T0, const double *S1, const double *T1,
-                                       const double *u, JointModel &m)
+                                       const double *u, JointModel &m, LmState *state = nullptr, int budget = 0x7fffffff)
 {
     double S0c[9], T0c[9], S1c[9], T1c[9];
     centre_scale3(S0, T0, S0c, T0c, &m.s0);
     centre_scale3(S1, T1, S1c, T1c, &m.s1);
-    kabsch_points(S0c, T0c, 3, m.R0);                          // :138-139
-    kabsch_points(S1c, T1c, 3, m.R1);
     double x[6];
-    matrix_to_rotvec(m.R0, x);                                 // :147-148
-    matrix_to_rotvec(m.R1, x + 3);
+    if (!(state && state->iter > 0)) {
+        kabsch_points(S0c, T0c, 3, m.R0);                      // :138-139
+        kabsch_points(S1c, T1c, 3, m.R1);
+        matrix_to_rotvec(m.R0, x);                             // :147-148
+        matrix_to_rotvec(m.R1, x + 3);
+    }
     SerialProb P;
     P.x0 = S0c; P.y0 = T0c; P.n0 = 3; P.x1 = S1c; P.y1 = T1c; P.n1 = 3;
     P.u[0] = u[0]; P.u[1] = u[1]; P.u[2] = u[2];
     P.nj = 3.0;                                                // min(n0,n1) copies of the joint direction, :134
-    LmResult r = lm_solve_fast(P, x, 1e-4, 1e-8, 1e-8, 600, 100.0); // :154-155
+    LmResult r = lm_solve_fast(P, x, 1e-4, 1e-8, 1e-8, 600, 100.0, state, budget); // :154-155
+    if (r.info == LM_SUSPENDED) return r;
     rotvec_to_matrix(x, m.R0);                                 // :156-157
     rotvec_to_matrix(x + 3, m.R1);
     mean_translation(S0, T0, 3, m.R0, m.s0, m.t0);             // :174-175 (un-refined scale)

@@ -16,6 +16,8 @@ from .pose import PoseSolver, unpack_results
 
 
 class AncshPipeline:
+    N_SLOTS = 4      # batches in flight in submit()/run_many(): pose tails of several batches overlap later forwards
+
     def __init__(self, weights_ancsh, n_parts, weights_npcs=None, use_baseline=True, nsample=64, niter_single=10000,
                  niter_joint=200, inlier_th=0.1, seed=0, device="cuda:0"):
         self.device = torch.device(device)
@@ -29,7 +31,7 @@ class AncshPipeline:
         self.pose = PoseSolver(n_parts, niter_single, niter_joint, inlier_th, seed, device)
         self._buf = {}
         self._slots = {}
-        self._pose_stream = None
+        self._pose_streams = {}
 
     def _buffers(self, B, N):
         key = (B, N)
@@ -69,14 +71,18 @@ class AncshPipeline:
 
     def submit(self, P, joint_cls, slot=0, net_events=None, net_b_events=None, pose_events=None):
         """Asynchronous run_device: the forwards are enqueued on the current stream, the pose stage on an
-        internal side stream that waits for them; buffers are per `slot` (use 2 slots, alternating).  The slow tail
+        internal high-priority side stream (one per slot) that waits for them; buffers are per `slot` (cycle through
+        N_SLOTS slots).  The slow tail
         of the joint LM solves then overlaps the next batch's forwards.  Returns the slot's pose tensors; call
         `join()` (or wait on the returned dict's "done" event) before reading them."""
         B, N, _ = P.shape
         sl = self._slot(B, N, slot)
         main = torch.cuda.current_stream()
-        if self._pose_stream is None:
-            self._pose_stream = torch.cuda.Stream(device=self.device)
+        if slot not in self._pose_streams:
+            # high priority: the pose kernels are latency-bound (a few long LM solves); they should grab an SM slot as
+            # soon as one frees up while the forwards of later batches fill the rest of the machine
+            self._pose_streams[slot] = torch.cuda.Stream(device=self.device, priority=int(__import__('os').environ.get('ANCSH_POSE_PRIO', '-1')))
+        ps = self._pose_streams[slot]
         if sl["used"]:
             main.wait_event(sl["pose_done"])          # the slot's prediction buffers are still being read
         pred = self.net.forward_device(P, sl["pred"], stage_events=net_events)
@@ -84,11 +90,11 @@ class AncshPipeline:
         if self.net_npcs is not None:
             src = self.net_npcs.forward_device(P, sl["pred_b"], stage_events=net_b_events)
         sl["fwd_done"].record(main)
-        with torch.cuda.stream(self._pose_stream):
-            self._pose_stream.wait_event(sl["fwd_done"])
+        with torch.cuda.stream(ps):
+            ps.wait_event(sl["fwd_done"])
             out = self.pose.solve_device(P, src["nocs_per_point"], src["W"], pred["joint_axis_per_point"], joint_cls,
-                                         out=sl["pose"], stage_events=pose_events)
-            sl["pose_done"].record(self._pose_stream)
+                                         out=sl["pose"], stage_events=pose_events, ws_slot=slot)
+            sl["pose_done"].record(ps)
         sl["used"] = True
         return out
 
@@ -113,10 +119,10 @@ class AncshPipeline:
                                "jc": torch.empty((B, N), dtype=torch.int32, device=self.device),
                                "hpose": {k: torch.empty(v.shape, dtype=v.dtype).pin_memory()
                                          for k, v in self.pose.alloc_outputs(B, N).items()},
-                               "copied": torch.cuda.Event()} for _ in range(2)]
+                               "copied": torch.cuda.Event()} for _ in range(self.N_SLOTS)]
         bufs = self._buf[key]
         results = [None] * len(batches)
-        pending = [None, None]
+        pending = [None] * self.N_SLOTS
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream()
 
@@ -134,15 +140,15 @@ class AncshPipeline:
                 pending[slot] = None
 
             for i, (P, jc) in enumerate(batches):
-                slot = i % 2
-                drain(slot)                              # results of batch i-2 (its slot is about to be reused)
+                slot = i % self.N_SLOTS
+                drain(slot)                              # results of the batch that used this slot last
                 bufs[slot]["hP"].numpy()[...] = P
                 bufs[slot]["hjc"].numpy()[...] = jc
                 bufs[slot]["P"].copy_(bufs[slot]["hP"], non_blocking=True)
                 bufs[slot]["jc"].copy_(bufs[slot]["hjc"], non_blocking=True)
                 pending[slot] = (i, self.submit(bufs[slot]["P"], bufs[slot]["jc"], slot=slot))
-            for slot in ((len(batches)) % 2, (len(batches) + 1) % 2):
-                drain(slot)
+            for k in range(self.N_SLOTS):              # oldest first
+                drain((len(batches) + k) % self.N_SLOTS)
         return results
 
     def run(self, P, joint_cls, unpack=True):

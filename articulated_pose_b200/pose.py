@@ -64,8 +64,8 @@ class PoseSolver:
         self._ws = {}
         self.last = None
 
-    def _plan(self, B, N):
-        key = (B, N)
+    def _plan(self, B, N, ws_slot=0):
+        key = (B, N, ws_slot)
         if key not in self._ws:
             lay = _lib.PoseWs()
             _lib.check(_lib.ancsh_pose_plan(ctypes.byref(self.cfg), B, N, ctypes.byref(lay)), "ancsh_pose_plan")
@@ -77,7 +77,7 @@ class PoseSolver:
         return {k: torch.empty(shp(B, self.K, N, J), dtype=dt, device=self.device) for k, (dt, shp) in _OUT_SPEC.items()}
 
     def solve_device(self, P, nocs, mask, joint_axis=None, joint_cls=None, idx_single=None, idx_joint0=None,
-                     idx_joint1=None, out=None, stage_events=None):
+                     idx_joint1=None, out=None, stage_events=None, ws_slot=0):
         """P (B,N,3) f32, nocs (B,N,3K) f32, mask (B,N,K) f32, joint_axis (B,N,3) f32, joint_cls (B,N) int32;
         optional idx_single (B,K,niter_single,3), idx_joint0/1 (B,K-1,niter_joint,3) int32.  Launches on torch's
         current stream and returns a dict of CUDA tensors (see include/ancsh_b200.h: ancsh_pose_out_t)."""
@@ -101,7 +101,7 @@ class PoseSolver:
         idx_joint1 = chk(idx_joint1, "idx_joint1", torch.int32, (B, max(K - 1, 0), self.cfg.niter_joint, 3))
         if K > 1 and (joint_axis is None or joint_cls is None):
             raise ValueError("joint_axis and joint_cls are required when n_parts > 1")
-        ws, lay = self._plan(B, N)
+        ws, lay = self._plan(B, N, ws_slot)       # one workspace per slot: slots may be in flight concurrently
         if out is None:
             out = self.alloc_outputs(B, N)
         pin = _lib.PoseIn()

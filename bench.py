@@ -256,7 +256,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         res = step()
     if full:
-        for i in range(2):                 # warm the pipelined path too (slot buffers, side stream)
+        for i in range(pipe.N_SLOTS):      # warm the pipelined path too (slot buffers, side streams)
             pipe.submit(P_dev, jc_dev, slot=i)
         pipe.join()
     torch.cuda.synchronize()
@@ -298,7 +298,7 @@ def main():
     for i in range(args.steps):
         flush.zero_()                       # L2 flush between timed iterations (256 MB memset, ~0.1 ms, counted)
         if full:
-            res = pipe.submit(P_dev, jc_dev, slot=i % 2)
+            res = pipe.submit(P_dev, jc_dev, slot=i % pipe.N_SLOTS)
         else:
             step()
     if full:
@@ -375,7 +375,7 @@ def main():
                                   "(no checkpoint ships with the reference)" % CALIB_CLOUDS if full else "seeded random",
                        "forwards_per_cloud": n_fwd, "mean_part_sizes": part_hist, "joint_lm": lm_stats,
                        "serialized_ms_per_step": round(serial_ms, 3),
-                       "streams": "pose stage of step i overlaps forwards of step i+1 (2 buffer slots)" if full else "single",
+                       "streams": "pose stage of step i (high-priority side stream) overlaps forwards of later steps (%d buffer slots)" % pipe.N_SLOTS if full else "single",
                        "wall_s_timed_region": round(t_wall, 4), "all_gathered_records": gathered},
             "clocks": clocks,
             "e2e": {"value": world * B * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,

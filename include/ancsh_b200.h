@@ -219,6 +219,7 @@ typedef struct {
     size_t joint_best;     /* int32 (B,K-1) */
     size_t joint_nfev;     /* int32 (B,K-1,niter_joint) residual evaluations each hypothesis' LM solve took */
     size_t joint_models;   /* f64 (B,K-1,niter_joint,26) per-hypothesis {R0[9],s0,t0[3],R1[9],s1,t1[3]} */
+    size_t joint_tail;     /* internal: work list of LM solves suspended after their first-phase budget */
     size_t total_bytes;
 } ancsh_pose_ws_t;
 

@@ -51,6 +51,25 @@ int hs_joint_estimate3(const double *S0, const double *T0, const double *S1, con
     out[0] = r.nfev; out[1] = r.njev; out[2] = r.fnorm;
     return r.info;
 }
+// the same estimate, suspended every `budget` residual evaluations and resumed (what the two-phase kernels do)
+int hs_joint_estimate3_resumed(const double *S0, const double *T0, const double *S1, const double *T1, const double *u,
+                               int budget, double *model26, double *out)
+{
+    pm::JointModel m;
+    pm::LmState st;
+    st.iter = 0;
+    pm::LmResult r;
+    int limit = budget, rounds = 0;
+    do {
+        r = pm::joint_estimate3(S0, T0, S1, T1, u, m, &st, limit);
+        limit += budget;
+        ++rounds;
+    } while (r.info == pm::LM_SUSPENDED);
+    const double *src = reinterpret_cast<const double *>(&m);
+    for (int i = 0; i < 26; ++i) model26[i] = src[i];
+    out[0] = r.nfev; out[1] = r.njev; out[2] = rounds;
+    return r.info;
+}
 void hs_sample3(unsigned long long seed, unsigned prob, unsigned hyp, unsigned stream, int n, int *idx)
 {
     pm::sample3(seed, prob, hyp, stream, n, idx);

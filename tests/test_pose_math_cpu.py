@@ -234,3 +234,21 @@ def test_fast_lm_equals_literal_minpack_port(lib):
             worst = max(worst, np.abs(xa - xb).max())
     assert same_nfev >= 0.97 * n, same_nfev
     assert worst < 1e-8, worst
+
+
+def test_suspend_resume_is_bit_identical(lib):
+    """Two-phase scheduling of the joint kernels: suspending an LM solve at an outer-iteration boundary and resuming
+    it from the saved state gives bit-identical models and nfev."""
+    rng = np.random.default_rng(33)
+    c = np.ascontiguousarray
+    multi = 0
+    for t in range(200):
+        x0, y0, x1, y1, u, _ = _problem(rng, 3, 3, 0.05, garbage=(t % 2 == 0))
+        S0, T0, S1, T1 = c(x0 + 0.3), c(0.7 * y0 + 0.1), c(x1 - 0.2), c(0.6 * y1 + 0.2)
+        a = np.zeros(26); b = np.zeros(26); oa = np.zeros(3); ob = np.zeros(3)
+        ia = lib.hs_joint_estimate3(dp(S0), dp(T0), dp(S1), dp(T1), dp(c(u)), dp(a), dp(oa))
+        ib = lib.hs_joint_estimate3_resumed(dp(S0), dp(T0), dp(S1), dp(T1), dp(c(u)), 5, dp(b), dp(ob))
+        assert ia == ib and oa[0] == ob[0]
+        np.testing.assert_array_equal(a, b)
+        multi += int(ob[2] > 1)
+    assert multi > 100
