@@ -34,12 +34,12 @@ def check(rc, what):
 
 
 class Layer(ctypes.Structure):
-    _fields_ = [("W", ctypes.c_void_p), ("b", ctypes.c_void_p), ("cin", c_int), ("cout", c_int),
+    _fields_ = [("W", ctypes.c_void_p), ("b", ctypes.c_void_p), ("W_tc", ctypes.c_void_p), ("cin", c_int), ("cout", c_int),
                 ("cin_pad", c_int), ("cout_pad", c_int), ("relu", c_int)]
 
 
 class Net(ctypes.Structure):
-    _fields_ = [("n_parts", c_int), ("mixed_pred", c_int),
+    _fields_ = [("use_tensor_cores", c_int), ("n_parts", c_int), ("mixed_pred", c_int),
                 ("npoint1", c_int), ("nsample1", c_int), ("radius1", ctypes.c_float),
                 ("npoint2", c_int), ("nsample2", c_int), ("radius2", ctypes.c_float),
                 ("sa1", Layer * 3), ("sa2", Layer * 3), ("sa3", Layer * 3),

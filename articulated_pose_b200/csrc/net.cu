@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "ops.cuh"
 #include "mlp_simt.cuh"
+#include "net_tc.cuh"
 
 using namespace mlp;
 
@@ -117,6 +118,20 @@ static int sa_launch(const SaArgs &a0, int B, cudaStream_t st)
     sa_kernel<TM><<<grid, NT, smem, st>>>(a);
     ANCSH_CHECK_LAUNCH();
     return ANCSH_OK;
+}
+
+// tensor-core variant of a set-abstraction stage (net_tc.cu); falls back to nothing: errors propagate
+static int sa_tc_from(const SaArgs &s, int B, cudaStream_t st)
+{
+    SaTcArgs t{};
+    t.xyz = s.xyz; t.points = s.points; t.new_xyz = s.new_xyz; t.idx = s.idx; t.out = s.out;
+    t.n = s.n; t.m = s.m; t.S = s.S; t.C = s.C;
+    for (int l = 0; l < 3; ++l) {
+        t.L[l].Wimg = reinterpret_cast<const __nv_bfloat16 *>(s.L[l].W_tc);
+        t.L[l].bias = s.L[l].b; t.L[l].K = s.L[l].cin_pad; t.L[l].N = s.L[l].cout_pad; t.L[l].relu = s.L[l].relu;
+    }
+    if (s.L[2].cout != s.L[2].cout_pad) return ANCSH_ERR_INVALID_ARG;
+    return sa_tc_launch(t, B, st);
 }
 
 // ================================================================================================
@@ -419,7 +434,7 @@ extern "C" int ancsh_net_forward(const ancsh_net_t *net, int B, int N, const flo
         a.xyz = P; a.points = nullptr; a.new_xyz = l1_xyz; a.idx = bidx1; a.out = l1_points;
         a.L[0] = net->sa1[0]; a.L[1] = net->sa1[1]; a.L[2] = net->sa1[2];
         a.n = N; a.m = m1; a.S = net->nsample1; a.C = 0;
-        if ((rc = sa_launch<128>(a, B, st))) return rc;
+        if ((rc = net->use_tensor_cores ? sa_tc_from(a, B, st) : sa_launch<128>(a, B, st))) return rc;
     }
     // layer2
     STAGE_MARK();
@@ -430,7 +445,7 @@ extern "C" int ancsh_net_forward(const ancsh_net_t *net, int B, int N, const flo
         a.xyz = l1_xyz; a.points = l1_points; a.new_xyz = l2_xyz; a.idx = bidx2; a.out = l2_points;
         a.L[0] = net->sa2[0]; a.L[1] = net->sa2[1]; a.L[2] = net->sa2[2];
         a.n = m1; a.m = m2; a.S = net->nsample2; a.C = net->sa1[2].cout;
-        if ((rc = sa_launch<128>(a, B, st))) return rc;
+        if ((rc = net->use_tensor_cores ? sa_tc_from(a, B, st) : sa_launch<128>(a, B, st))) return rc;
     }
     // layer3 (group_all)
     STAGE_MARK();

@@ -1,0 +1,22 @@
+// net_tc.cuh -- argument structs of the tensor-core (tcgen05) network kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+struct TcLayer {
+    const __nv_bfloat16 *Wimg;   // [K/8][2 (hi,lo)][N][8] bf16: W^T pre-split and pre-tiled (weights.tc_image)
+    const float *bias;           // [N] f32 (BN folded)
+    int K, N, relu;              // K = cin_pad (multiple of 16), N = cout_pad (64 / 128 / 256)
+};
+
+struct SaTcArgs {
+    const float *xyz, *points, *new_xyz;
+    const int *idx;
+    float *out;
+    TcLayer L[3];
+    int n, m, S, C;
+    int kmax8, nmax;             // filled by the launcher
+    uint32_t tmem_cols;
+};
+
+int sa_tc_launch(const SaTcArgs &a, int B, cudaStream_t st);

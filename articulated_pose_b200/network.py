@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .weights import flatten_packed, pack_network
+from .weights import flatten_packed, flatten_tc_images, pack_network
 
 _PRED_WIDTH = {
     "W": lambda K: K, "nocs_per_point": lambda K: 3 * K, "confi_per_point": lambda K: 1,
@@ -44,10 +44,15 @@ _WS_VIEWS = {  # name -> (dtype, shape builder)
 
 class AncshNet:
     def __init__(self, weights, n_parts, mixed_pred=True, early_split_nocs=True, nsample=64, npoint1=512, npoint2=128,
-                 radius1=0.2, radius2=0.4, device="cuda:0", prefix="SPFN"):
+                 radius1=0.2, radius2=0.4, device="cuda:0", prefix="SPFN", precision="bf16x3"):
         """weights: dict TF-variable-name -> ndarray (see weights.variable_shapes).
         ANCSH (exp 3.9): mixed_pred=True, early_split_nocs=True (main.py:42-49);
-        NPCS baseline (exp 3.91): mixed_pred=False, early_split_nocs=False."""
+        NPCS baseline (exp 3.91): mixed_pred=False, early_split_nocs=False.
+        precision: "bf16x3" = grouped MLPs on the tcgen05 tensor cores with the bf16 hi/lo split (f32-class accuracy,
+        default); "f32" = exact f32 FMA kernels on the CUDA cores."""
+        if precision not in ("bf16x3", "f32"):
+            raise ValueError("precision must be 'bf16x3' or 'f32'")
+        self.precision = precision
         if not torch.cuda.is_available():
             raise RuntimeError("AncshNet needs a CUDA device (no CPU fallback)")
         self.device = torch.device(device)
@@ -58,8 +63,12 @@ class AncshNet:
         flat, offs = flatten_packed(self.layers)
         self._wbuf = torch.from_numpy(flat).to(self.device)
         base = self._wbuf.data_ptr()
+        tc_flat, tc_offs = flatten_tc_images(self.layers)
+        self._tcbuf = torch.from_numpy(tc_flat.view(np.int16)).to(self.device)
+        tc_base = self._tcbuf.data_ptr()
 
         net = _lib.Net()
+        net.use_tensor_cores = int(precision == "bf16x3")
         net.n_parts, net.mixed_pred = self.n_parts, int(self.mixed_pred)
         net.npoint1, net.nsample1, net.radius1 = self.npoint1, self.nsample1, float(radius1)
         net.npoint2, net.nsample2, net.radius2 = self.npoint2, self.nsample2, float(radius2)
@@ -71,6 +80,7 @@ class AncshNet:
             else:
                 dst = getattr(net, slot)
             dst.W, dst.b = base + 4 * wo, base + 4 * bo
+            dst.W_tc = tc_base + 2 * tc_offs[slot] if slot in tc_offs else None
             dst.cin, dst.cout, dst.cin_pad, dst.cout_pad, dst.relu = pl.cin, pl.cout, pl.cin_pad, pl.cout_pad, pl.relu
         self._net = net
         self._ws = {}       # (B,N) -> (workspace tensor, layout)

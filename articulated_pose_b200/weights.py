@@ -170,6 +170,44 @@ def pack_network(weights, n_parts, mixed_pred=True, early_split_nocs=True, prefi
     return L
 
 
+def f32_to_bf16_bits(x):
+    """round-to-nearest-even f32 -> bf16 bit patterns (uint16)"""
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32)
+    return ((u + (((u >> 16) & 1) + 0x7FFF)) >> 16).astype(np.uint16)
+
+
+def bf16_bits_to_f32(b):
+    return (b.astype(np.uint32) << 16).view(np.float32)
+
+
+def tc_image(W):
+    """Tensor-core operand image of a padded weight matrix W [cin_pad][cout_pad] (f32): W^T split into
+    hi = bf16(w), lo = bf16(w - hi), tiled as [cin_pad/8][2][cout_pad][8] bf16 (csrc/tc_common.cuh)."""
+    K, N = W.shape
+    Wt = np.ascontiguousarray(W.T, np.float32)                       # [N][K]
+    hi = f32_to_bf16_bits(Wt)
+    lo = f32_to_bf16_bits(Wt - bf16_bits_to_f32(hi))
+    img = np.stack([hi.reshape(N, K // 8, 8), lo.reshape(N, K // 8, 8)], axis=0)   # [2][N][K/8][8]
+    return np.ascontiguousarray(img.transpose(2, 0, 1, 3))          # [K/8][2][N][8]
+
+
+TC_SLOTS = ("sa1[0]", "sa1[1]", "sa1[2]", "sa2[0]", "sa2[1]", "sa2[2]")
+
+
+def flatten_tc_images(layers):
+    """uint16 buffer with the tensor-core images of the layers that run on tcgen05, 256-byte aligned offsets."""
+    off, offs, parts = 0, {}, []
+    for slot in TC_SLOTS:
+        img = tc_image(layers[slot].W).ravel()
+        offs[slot] = off
+        parts.append((off, img))
+        off = (off + img.size + 127) // 128 * 128
+    flat = np.zeros((off,), np.uint16)
+    for o, img in parts:
+        flat[o:o + img.size] = img
+    return flat, offs
+
+
 def flatten_packed(layers):
     """Lay all W/b arrays out in one f32 buffer with 256-byte aligned offsets.
     Returns (flat float32 array, {slot: (w_offset_floats, b_offset_floats)})."""

@@ -33,10 +33,10 @@ def test_version_string():
 def test_struct_sizes_match_header():
     """ctypes mirrors must have the C layout (2 pointers + 5 ints, padded to 8)."""
     from articulated_pose_b200 import _lib
-    assert ctypes.sizeof(_lib.Layer) == 40
+    assert ctypes.sizeof(_lib.Layer) == 48
     assert ctypes.sizeof(_lib.Pred) == 88
     assert ctypes.sizeof(_lib.WsLayout) == 15 * 8
-    assert ctypes.sizeof(_lib.Net) == 32 + 22 * 40
+    assert ctypes.sizeof(_lib.Net) == 40 + 22 * 48
 
 
 def test_product_does_not_import_oracle():

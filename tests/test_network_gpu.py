@@ -59,6 +59,28 @@ def test_forward_matches_oracle(cat, K, B, ns, mixed):
         assert_close(got[k], ref[k], k)
 
 
+@pytest.mark.parametrize("ns", [32, 64])
+def test_exact_f32_path_matches_oracle_and_tensor_core_path(ns):
+    """precision='f32' (CUDA-core FMA kernels) vs oracle, and the tcgen05 bf16x3 path vs the f32 path."""
+    from articulated_pose_b200 import synthetic, weights
+    from articulated_pose_b200.network import AncshNet
+    from oracle import pnpp
+    P, _ = synthetic.make_batch(range(30, 33))
+    w = weights.synthetic_weights(3)
+    ref = pnpp.forward(P, w, 3, nsample=ns)
+    f32 = AncshNet(w, 3, nsample=ns, precision="f32")
+    tc = AncshNet(w, 3, nsample=ns, precision="bf16x3")
+    a, b = f32.forward(P), tc.forward(P)
+    ia = {k: v.cpu().numpy() for k, v in f32.intermediates().items()}
+    ib = {k: v.cpu().numpy() for k, v in tc.intermediates().items()}
+    np.testing.assert_array_equal(ia["ball_idx2"], ib["ball_idx2"])
+    assert_close(ib["l1_points"], ia["l1_points"], "l1_points tc vs f32")
+    assert_close(ib["l2_points"], ia["l2_points"], "l2_points tc vs f32")
+    for k in ref:
+        assert_close(a[k], ref[k], k + " (f32)")
+        assert_close(b[k], ref[k], k + " (bf16x3)")
+
+
 def test_forward_is_deterministic_and_batch_invariant():
     from articulated_pose_b200 import synthetic, weights
     from articulated_pose_b200.network import AncshNet
