@@ -12,6 +12,7 @@
 //   * the last layer's epilogue max-pools each group with one redux.sync per column.
 // Two CTAs per SM (<= 113 KB shared memory, <= 256 TMEM columns each) overlap one CTA's epilogue / weight fetch
 // with the other's MMAs.
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "net_tc.cuh"
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(TM) sa_tc_kernel(const SaTcArgs a)
                     tc::mma_bf16(tmem, ah, bh, idesc, kk > 0 ? 1u : 0u);
                     tc::mma_bf16(tmem, ah, bl, idesc, 1u);
                     tc::mma_bf16(tmem, al, bh, idesc, 1u);
+                    if (a.terms >= 4) tc::mma_bf16(tmem, al, bl, idesc, 1u);
                 }
                 tc::mma_commit(bar);
             }
@@ -170,6 +172,10 @@ int sa_tc_launch(const SaTcArgs &a0, int B, cudaStream_t st)
         nmax = a.L[l].N > nmax ? a.L[l].N : nmax;
     }
     if (a.L[0].K < a.C + 3 || !a.L[2].relu) return ANCSH_ERR_INVALID_ARG;
+    {
+        const char *e = getenv("ANCSH_TC_TERMS");
+        a.terms = e ? atoi(e) : 3;
+    }
     a.kmax8 = kmax / 8;
     a.nmax = nmax;
     a.tmem_cols = nmax <= 32 ? 32 : nmax <= 64 ? 64 : nmax <= 128 ? 128 : 256;

@@ -17,6 +17,7 @@ struct SaTcArgs {
     int n, m, S, C;
     int kmax8, nmax;             // filled by the launcher
     uint32_t tmem_cols;
+    int terms;                   // products per k-step: 3 = hi*hi + hi*lo + lo*hi (default), 4 adds lo*lo
 };
 
 int sa_tc_launch(const SaTcArgs &a, int B, cudaStream_t st);

@@ -19,15 +19,16 @@ class AncshPipeline:
     N_SLOTS = 4      # batches in flight in submit()/run_many(): pose tails of several batches overlap later forwards
 
     def __init__(self, weights_ancsh, n_parts, weights_npcs=None, use_baseline=True, nsample=64, niter_single=10000,
-                 niter_joint=200, inlier_th=0.1, seed=0, device="cuda:0"):
+                 niter_joint=200, inlier_th=0.1, seed=0, device="cuda:0", precision="bf16x3"):
         self.device = torch.device(device)
         self.K = int(n_parts)
         self.use_baseline = bool(use_baseline and weights_npcs is not None)
-        self.net = AncshNet(weights_ancsh, n_parts, mixed_pred=True, early_split_nocs=True, nsample=nsample, device=device)
+        self.net = AncshNet(weights_ancsh, n_parts, mixed_pred=True, early_split_nocs=True, nsample=nsample, device=device,
+                            precision=precision)
         self.net_npcs = None
         if self.use_baseline:
             self.net_npcs = AncshNet(weights_npcs, n_parts, mixed_pred=False, early_split_nocs=False, nsample=nsample,
-                                     device=device)
+                                     device=device, precision=precision)
         self.pose = PoseSolver(n_parts, niter_single, niter_joint, inlier_th, seed, device)
         self._buf = {}
         self._slots = {}

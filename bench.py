@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--no-baseline-net", action="store_true", help="USE_BASELINE=False: one forward per cloud")
     ap.add_argument("--cpu-sample", type=int, default=0, help="clouds in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "f32"],
+                    help="bf16x3: grouped MLPs on tcgen05 (bf16 hi/lo split, f32 accumulate); f32: CUDA-core FMA kernels")
     return ap.parse_args()
 
 
@@ -230,12 +232,13 @@ def main():
     full = args.stages == "full"
 
     def feats(kind, w, Pc):
-        n = AncshNet(w, K, mixed_pred=(kind == "ancsh"), early_split_nocs=(kind == "ancsh"), nsample=args.nsample, device=dev)
+        n = AncshNet(w, K, mixed_pred=(kind == "ancsh"), early_split_nocs=(kind == "ancsh"), nsample=args.nsample, device=dev,
+                     precision=args.precision)
         return n.features(Pc)
     w_a, w_n = synthetic_weight_sets(K, args, feats if full else None)
     pipe = AncshPipeline(w_a, K, weights_npcs=w_n if full else None, use_baseline=full and not args.no_baseline_net,
                          nsample=args.nsample, niter_single=args.hyp, niter_joint=args.joint_hyp, seed=1234 + rank,
-                         device=dev)
+                         device=dev, precision=args.precision)
     P_host, clouds = synthetic.make_batch(range(rank * B, rank * B + B), args.category)
     jc_host = np.stack([c["joint_cls_gt"] for c in clouds]).astype(np.int32)
     N = P_host.shape[1]
@@ -359,7 +362,7 @@ def main():
     peak = peaks["bf16_tflops_sustained"]
     n_fwd = 2 if (full and two_nets) else 1
     fwd_ms = sum(stage_ms.values())
-    roofline = {"bound": "tensor", "kernel": "sa_kernel<128> (%s, ANCSH net)" % dom,
+    roofline = {"bound": "tensor", "kernel": ("sa_tc_kernel" if args.precision == "bf16x3" else "sa_kernel<128>") + " (%s, ANCSH net)" % dom,
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                 "peak_source": peaks["source"] + " bf16 sustained; kernel duration from per-stage CUDA events of a serialized pass in the same run",
                 "avg_launch_ms": stage_ms[dom], "flops_per_launch": fl[dom],
@@ -369,7 +372,8 @@ def main():
     line = {"metric": METRIC, "value": world * B * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 network / f64 pose" if full else "f32", "data": "synthetic",
+            "dtype": ("bf16x3->f32" if args.precision == "bf16x3" else "f32") + (" network / f64 pose" if full else ""),
+            "data": "synthetic",
             "config": {"workload": workload_name(args), "stages": args.stages, "l2_flush_between_steps": True,
                        "weights": "seeded random trunk, linear seg/NOCS heads ridge-fitted on %d synthetic clouds "
                                   "(no checkpoint ships with the reference)" % CALIB_CLOUDS if full else "seeded random",
