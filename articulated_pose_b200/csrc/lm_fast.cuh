@@ -13,7 +13,9 @@
 
 // upper Cholesky of the symmetric 6x6 A (full storage) plus `shift` on the diagonal: S^T S = A + shift I.
 // Pivots that are not > tiny are treated as zero (row zeroed); returns the index of the first zero pivot (6 = none).
-PM_HD int chol6(const double (&A)[6][6], double shift, double tiny, double (&S)[6][6])
+// rinv[j] receives 1 / S[j][j] (0 for zero pivots): the triangular solves multiply instead of dividing -- f64 division
+// and sqrt are long software sequences on the GPU and dominate the latency of one LM iteration otherwise.
+PM_HD int chol6(const double (&A)[6][6], double shift, double tiny, double (&S)[6][6], double (&rinv)[6])
 {
     int nsing = 6;
 #pragma unroll
@@ -22,10 +24,11 @@ PM_HD int chol6(const double (&A)[6][6], double shift, double tiny, double (&S)[
 #pragma unroll
         for (int k = 0; k < j; ++k) d -= S[k][j] * S[k][j];
         const bool ok = d > tiny && nsing == 6;
-        const double sjj = ok ? sqrt(d) : 0.0;
+        const double inv = ok ? 1.0 / sqrt(d) : 0.0;
+        const double sjj = ok ? d * inv : 0.0;
         if (!ok && nsing == 6) nsing = j;
         S[j][j] = sjj;
-        const double inv = ok ? 1.0 / sjj : 0.0;
+        rinv[j] = inv;
 #pragma unroll
         for (int i = j + 1; i < 6; ++i) {
             double v = A[j][i];
@@ -40,18 +43,18 @@ PM_HD int chol6(const double (&A)[6][6], double shift, double tiny, double (&S)[
 }
 
 // w = S^-T b  (forward substitution with the upper factor), rows >= nsing give 0
-PM_HD void solve_lower6(const double (&S)[6][6], int nsing, const double (&b)[6], double (&w)[6])
+PM_HD void solve_lower6(const double (&S)[6][6], const double (&rinv)[6], int nsing, const double (&b)[6], double (&w)[6])
 {
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
         double v = b[j];
 #pragma unroll
         for (int i = 0; i < j; ++i) v -= S[i][j] * w[i];
-        w[j] = (j < nsing) ? v / S[j][j] : 0.0;
+        w[j] = (j < nsing) ? v * rinv[j] : 0.0;
     }
 }
 // x = S^-1 b  (back substitution), components >= nsing are 0
-PM_HD void solve_upper6(const double (&S)[6][6], int nsing, const double (&b)[6], double (&x)[6])
+PM_HD void solve_upper6(const double (&S)[6][6], const double (&rinv)[6], int nsing, const double (&b)[6], double (&x)[6])
 {
 #pragma unroll
     for (int jj = 0; jj < 6; ++jj) {
@@ -59,7 +62,7 @@ PM_HD void solve_upper6(const double (&S)[6][6], int nsing, const double (&b)[6]
         double v = b[j];
 #pragma unroll
         for (int i = j + 1; i < 6; ++i) v -= S[j][i] * x[i];
-        x[j] = (j < nsing) ? v / S[j][j] : 0.0;
+        x[j] = (j < nsing) ? v * rinv[j] : 0.0;
     }
 }
 PM_HD double norm6(const double (&v)[6])
@@ -173,10 +176,10 @@ PM_HDN inline LmResult lm_solve_fast(const Prob &prob, double *x, double ftol, d
 #pragma unroll
         for (int j = 0; j < 6; ++j) tiny = fmax(tiny, A[j][j]);
         tiny *= 1e-28;
-        double R[6][6];
-        const int nsing = chol6(A, 0.0, tiny, R);
+        double R[6][6], Rinv[6];
+        const int nsing = chol6(A, 0.0, tiny, R, Rinv);
         double qtf[6];
-        solve_lower6(R, nsing, g, qtf);                      // (Q^T f)[:n] = R^-T P^T J^T f
+        solve_lower6(R, Rinv, nsing, g, qtf);                      // (Q^T f)[:n] = R^-T P^T J^T f
         if (iter == 1) {
             xnorm = 0.0;
             for (int j = 0; j < 6; ++j) xnorm += x[j] * x[j];
@@ -198,7 +201,7 @@ PM_HDN inline LmResult lm_solve_fast(const Prob &prob, double *x, double ftol, d
         if (gnorm <= gtol) { res.info = 4; break; }
         // quantities of lmpar that do not depend on par
         double gn[6];                                        // Gauss-Newton direction (permuted)
-        solve_upper6(R, nsing, qtf, gn);
+        solve_upper6(R, Rinv, nsing, qtf, gn);
         double rtq[6];                                       // R^T qtb
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
@@ -224,9 +227,10 @@ PM_HDN inline LmResult lm_solve_fast(const Prob &prob, double *x, double ftol, d
                     double parl = 0.0;
                     if (nsing >= 6) {
                         double w1[6], w2[6];
+                        const double idx = 1.0 / dxnorm;
 #pragma unroll
-                        for (int j = 0; j < 6; ++j) w1[j] = p[j] / dxnorm;
-                        solve_lower6(R, 6, w1, w2);
+                        for (int j = 0; j < 6; ++j) w1[j] = p[j] * idx;
+                        solve_lower6(R, Rinv, 6, w1, w2);
                         const double t = norm6(w2);
                         parl = ((fp / delta) / t) / t;
                     }
@@ -237,19 +241,20 @@ PM_HDN inline LmResult lm_solve_fast(const Prob &prob, double *x, double ftol, d
                     if (par == 0.0) par = gradnorm / dxnorm;
                     for (int it = 1;; ++it) {
                         if (par == 0.0) par = fmax(DWARF, 0.001 * paru);
-                        double S[6][6];
-                        const int ns = chol6(A, par, 0.0, S);       // S^T S = R^T R + par I
+                        double S[6][6], Sinv[6];
+                        const int ns = chol6(A, par, 0.0, S, Sinv);  // S^T S = R^T R + par I
                         double w[6];
-                        solve_lower6(S, ns, rtq, w);
-                        solve_upper6(S, ns, w, p);
+                        solve_lower6(S, Sinv, ns, rtq, w);
+                        solve_upper6(S, Sinv, ns, w, p);
                         dxnorm = norm6(p);
                         const double temp = fp;
                         fp = dxnorm - delta;
                         if (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || it == 10) break;
                         double w1[6], w2[6];
+                        const double idx = 1.0 / dxnorm;
 #pragma unroll
-                        for (int j = 0; j < 6; ++j) w1[j] = p[j] / dxnorm;
-                        solve_lower6(S, ns, w1, w2);
+                        for (int j = 0; j < 6; ++j) w1[j] = p[j] * idx;
+                        solve_lower6(S, Sinv, ns, w1, w2);
                         const double t = norm6(w2);
                         const double parc = ((fp / delta) / t) / t;
                         if (fp > 0.0) parl = fmax(parl, par);

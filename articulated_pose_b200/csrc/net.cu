@@ -127,7 +127,7 @@ static int sa_tc_from(const SaArgs &s, int B, cudaStream_t st)
     t.xyz = s.xyz; t.points = s.points; t.new_xyz = s.new_xyz; t.idx = s.idx; t.out = s.out;
     t.n = s.n; t.m = s.m; t.S = s.S; t.C = s.C;
     for (int l = 0; l < 3; ++l) {
-        t.L[l].Wimg = reinterpret_cast<const __nv_bfloat16 *>(s.L[l].W_tc);
+        t.L[l].Wimg = reinterpret_cast<const __half *>(s.L[l].W_tc);
         t.L[l].bias = s.L[l].b; t.L[l].K = s.L[l].cin_pad; t.L[l].N = s.L[l].cout_pad; t.L[l].relu = s.L[l].relu;
     }
     if (s.L[2].cout != s.L[2].cout_pad) return ANCSH_ERR_INVALID_ARG;

@@ -5,10 +5,10 @@
 // 128 x N x K tcgen05.mma contraction with the f32 accumulator in tensor memory:
 //   * one CTA = 128 threads = 128 rows (thread t owns row t for the gather, for TMEM lane t in the epilogue and for
 //     the write-back of the next layer's operand);
-//   * activations live in shared memory as bf16 hi/lo operand images (tc_common.cuh), overwritten in place by the
+//   * activations live in shared memory as fp16 hi/lo operand images (tc_common.cuh), overwritten in place by the
 //     epilogue of each layer; weights are pre-split / pre-tiled on the host into the same image layout and streamed
 //     from L2 in 32-wide k slices with cp.async;
-//   * 3 MMAs per k-step (hi*hi + hi*lo + lo*hi) give f32-class accuracy from bf16 tensor-core throughput;
+//   * 3 MMAs per k-step (hi*hi + hi*lo + lo*hi) give f32-class accuracy at fp16 tensor-core throughput;
 //   * the last layer's epilogue max-pools each group with one redux.sync per column.
 // Two CTAs per SM (<= 113 KB shared memory, <= 256 TMEM columns each) overlap one CTA's epilogue / weight fetch
 // with the other's MMAs.
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(TM) sa_tc_kernel(const SaTcArgs a)
     for (int l = 0; l < 3; ++l) {
         const TcLayer &L = a.L[l];
         const int N = L.N, nk16 = L.K / 16;
-        const uint32_t idesc = tc::instr_desc_bf16(TM, N);
+        const uint32_t idesc = tc::instr_desc_f16(TM, N);
         const uint32_t slab = 2u * N * 16u;                  // one group of 8 k: hi rows then lo rows
         for (int k16 = 0; k16 < nk16; k16 += KSLICE / 16) {
             const int steps = min(KSLICE / 16, nk16 - k16);
@@ -99,10 +99,10 @@ __global__ void __launch_bounds__(TM) sa_tc_kernel(const SaTcArgs a)
                     const uint64_t al = tc::smem_desc(a_lo0 + (uint32_t)(2 * kk) * 2048u, 2048u, 128u);
                     const uint64_t bh = tc::smem_desc(w0 + (uint32_t)(2 * s) * slab, slab, 128u);
                     const uint64_t bl = tc::smem_desc(w0 + (uint32_t)(2 * s) * slab + (uint32_t)N * 16u, slab, 128u);
-                    tc::mma_bf16(tmem, ah, bh, idesc, kk > 0 ? 1u : 0u);
-                    tc::mma_bf16(tmem, ah, bl, idesc, 1u);
-                    tc::mma_bf16(tmem, al, bh, idesc, 1u);
-                    if (a.terms >= 4) tc::mma_bf16(tmem, al, bl, idesc, 1u);
+                    tc::mma_f16(tmem, ah, bh, idesc, kk > 0 ? 1u : 0u);
+                    tc::mma_f16(tmem, ah, bl, idesc, 1u);
+                    tc::mma_f16(tmem, al, bh, idesc, 1u);
+                    if (a.terms >= 4) tc::mma_f16(tmem, al, bl, idesc, 1u);
                 }
                 tc::mma_commit(bar);
             }
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(TM) sa_tc_kernel(const SaTcArgs a)
         tc::fence_after_sync();
         const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
         if (l < 2) {
-            // bias + ReLU, split to bf16 hi/lo, becomes the next layer's operand (in place)
+            // bias + ReLU, split to fp16 hi/lo, becomes the next layer's operand (in place)
             for (int c0 = 0; c0 < N; c0 += 32) {
                 float v[32];
                 tc::tmem_ld32(trow + c0, v);

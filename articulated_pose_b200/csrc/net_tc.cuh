@@ -1,10 +1,10 @@
 // net_tc.cuh -- argument structs of the tensor-core (tcgen05) network kernels.
 #pragma once
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 struct TcLayer {
-    const __nv_bfloat16 *Wimg;   // [K/8][2 (hi,lo)][N][8] bf16: W^T pre-split and pre-tiled (weights.tc_image)
+    const __half *Wimg;   // [K/8][2 (hi,lo)][N][8] fp16: W^T pre-split and pre-tiled (weights.tc_image)
     const float *bias;           // [N] f32 (BN folded)
     int K, N, relu;              // K = cin_pad (multiple of 16), N = cout_pad (64 / 128 / 256)
 };

@@ -346,8 +346,8 @@ struct JointArgs {
     int *nfev;                          // (nprob, niter)
     pm::JointModel *models;             // (nprob, niter) per-hypothesis models
     int nprob;
-    int *tail_count, *tail_next;        // work list of suspended LM solves
-    struct TailItem *tail_items;        // (nprob * niter)
+    int *tail_count;                    // [LM_TAIL_ROUNDS + 1] sizes of the per-round work lists of suspended LM solves
+    struct TailItem *tail_items;        // 2 x (nprob * niter), ping-pong between rounds
     int *best;                          // (nprob)
     int N, K, niter;
     double th2;
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(JT, 9) joint_estimate_kernel(const JointArgs a
     st.iter = 0;
     const pm::LmResult lr = pm::joint_estimate3(S0, T0, S1, T1, a.axis_med + (size_t)prob * 3, m, &st, LM_BUDGET1);
     if (lr.info == pm::LM_SUSPENDED) {
-        const int slot = atomicAdd(a.tail_count, 1);
+        const int slot = atomicAdd(a.tail_count, 1);          // work list of round 0
         a.tail_items[slot].t = (int)t;
         a.tail_items[slot].st = st;
     } else {
@@ -425,14 +425,20 @@ __global__ void __launch_bounds__(JT, 9) joint_estimate_kernel(const JointArgs a
     }
 }
 
-__global__ void __launch_bounds__(JT, 9) joint_estimate_tail_kernel(const JointArgs a)
+// Round r of the tail: every suspended solve gets LM_BUDGET_ROUND more evaluations (all lanes of a warp start their
+// items together, so the warp stays convergent); still-unfinished solves are re-queued, densely packed, for the next
+// round.  The last round runs to completion (MINPACK's own maxfev = 600 bounds it).
+constexpr int LM_BUDGET_ROUND = 64;
+constexpr int LM_TAIL_ROUNDS = 9;     // 24 + 8*64 = 536 evaluations, then one unbounded round
+
+__global__ void __launch_bounds__(JT, 9) joint_estimate_round_kernel(const JointArgs a, int round, int last)
 {
-    const int count = *a.tail_count;
-    for (;;) {
-        const int w = atomicAdd(a.tail_next, 1);          // dynamic hand-out: lanes that finish early take more items
-        if (w >= count) break;
-        const int t = a.tail_items[w].t;
-        pm::LmState st = a.tail_items[w].st;
+    const int count = a.tail_count[round];
+    const TailItem *in = a.tail_items + (size_t)(round & 1) * a.nprob * a.niter;
+    TailItem *out = a.tail_items + (size_t)((round + 1) & 1) * a.nprob * a.niter;
+    for (int w = blockIdx.x * JT + threadIdx.x; w < count; w += gridDim.x * JT) {
+        const int t = in[w].t;
+        pm::LmState st = in[w].st;
         const int prob = t / a.niter, h = t - prob * a.niter;
         int pa, pb;
         joint_parts(prob, a.K, pa, pb);
@@ -440,9 +446,16 @@ __global__ void __launch_bounds__(JT, 9) joint_estimate_tail_kernel(const JointA
         double S0[9], T0[9], S1[9], T1[9];
         gather_joint_samples(a, prob, h, pa, pb, n0, n1, S0, T0, S1, T1);
         pm::JointModel m;
-        const pm::LmResult lr = pm::joint_estimate3(S0, T0, S1, T1, a.axis_med + (size_t)prob * 3, m, &st, 0x7fffffff);
-        a.nfev[t] = lr.nfev;
-        a.models[t] = m;
+        const int budget = last ? 0x7fffffff : st.nfev + LM_BUDGET_ROUND;
+        const pm::LmResult lr = pm::joint_estimate3(S0, T0, S1, T1, a.axis_med + (size_t)prob * 3, m, &st, budget);
+        if (lr.info == pm::LM_SUSPENDED) {
+            const int slot = atomicAdd(a.tail_count + round + 1, 1);
+            out[slot].t = t;
+            out[slot].st = st;
+        } else {
+            a.nfev[t] = lr.nfev;
+            a.models[t] = m;
+        }
     }
 }
 
@@ -764,7 +777,7 @@ extern "C" int ancsh_pose_plan(const ancsh_pose_cfg_t *cfg, int B, int N, ancsh_
     L->joint_best = take(b * (K > 1 ? K - 1 : 1) * 4);
     L->joint_nfev = take(b * (K > 1 ? K - 1 : 1) * (size_t)cfg->niter_joint * 4);
     L->joint_models = take(b * (K > 1 ? K - 1 : 1) * (size_t)cfg->niter_joint * sizeof(pm::JointModel));
-    L->joint_tail = take(256 + b * (K > 1 ? K - 1 : 1) * (size_t)cfg->niter_joint * 112);   /* counters + TailItem[] */
+    L->joint_tail = take(256 + 2 * b * (K > 1 ? K - 1 : 1) * (size_t)cfg->niter_joint * 112);   /* counters + 2 x TailItem[] */
     L->total_bytes = off;
     return ANCSH_OK;
 }
@@ -841,27 +854,20 @@ extern "C" int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in
         a.models = (pm::JointModel *)(ws + L.joint_models);
         a.nprob = B * (K - 1);
         a.tail_count = (int *)(ws + L.joint_tail);
-        a.tail_next = a.tail_count + 1;
         a.tail_items = (TailItem *)(ws + L.joint_tail + 256);
-        ANCSH_CUDA(cudaMemsetAsync(a.tail_count, 0, 2 * sizeof(int), st));
+        ANCSH_CUDA(cudaMemsetAsync(a.tail_count, 0, 64 * sizeof(int), st));
         a.N = N; a.K = K; a.niter = cfg->niter_joint; a.th2 = th2; a.seed = cfg->seed;
         a.R0 = out->joint_R0; a.s0 = out->joint_s0; a.t0 = out->joint_t0;
         a.R1 = out->joint_R1; a.s1 = out->joint_s1; a.t1 = out->joint_t1; a.score_out = out->joint_score;
         a.inl0 = out->joint_inliers0; a.inl1 = out->joint_inliers1; a.status = out->status;
         size_t smem = (size_t)N * 6 * sizeof(double);          // n0 + n1 <= N
         const long nthreads = (long)a.nprob * cfg->niter_joint;
-        // Same shared-memory carveout as the MLP kernels these two overlap with (they use no shared memory themselves):
-        // SMs cannot host kernels with different L1/shared splits at the same time.
-        ANCSH_CUDA(cudaFuncSetAttribute(joint_estimate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        ANCSH_CUDA(cudaFuncSetAttribute(joint_estimate_tail_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         joint_estimate_kernel<<<(unsigned)((nthreads + JT - 1) / JT), JT, 0, st>>>(a);
         ANCSH_CHECK_LAUNCH();
-        {
-            const char *eb = getenv("ANCSH_TAIL_BLOCKS");
-            const int tb = eb ? atoi(eb) : 296;
-            joint_estimate_tail_kernel<<<tb, JT, 0, st>>>(a);
+        for (int r = 0; r < LM_TAIL_ROUNDS; ++r) {
+            joint_estimate_round_kernel<<<296, JT, 0, st>>>(a, r, r == LM_TAIL_ROUNDS - 1 ? 1 : 0);
+            ANCSH_CHECK_LAUNCH();
         }
-        ANCSH_CHECK_LAUNCH();
         ANCSH_CUDA(cudaFuncSetAttribute(joint_verify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ANCSH_CUDA(cudaFuncSetAttribute(joint_verify_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         joint_verify_kernel<<<a.nprob, RT, smem, st>>>(a);

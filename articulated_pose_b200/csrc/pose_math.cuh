@@ -230,10 +230,9 @@ struct RotVec {
     PM_HD void set(const double *r)
     {
         theta = norm3(r);
-        if (theta > 0.0) { v[0] = r[0] / theta; v[1] = r[1] / theta; v[2] = r[2] / theta; }
+        if (theta > 0.0) { const double it = 1.0 / theta; v[0] = r[0] * it; v[1] = r[1] * it; v[2] = r[2] * it; }
         else { v[0] = v[1] = v[2] = 0.0; }                 // nan_to_num(r / 0) == 0
-        c = cos(theta);
-        s = sin(theta);
+        sincos(theta, &s, &c);
     }
     PM_HD void rotate(const double *p, double *o) const
     {

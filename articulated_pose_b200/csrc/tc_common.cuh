@@ -1,16 +1,19 @@
 // tc_common.cuh -- thin inline-PTX layer for Blackwell tensor cores (sm_100a): tcgen05.mma with the accumulator in
 // tensor memory (TMEM), shared-memory matrix descriptors, mbarrier completion, TMEM load for the epilogue.
 //
-// Operand layout used throughout (no swizzle, K-major "core matrices"): a [ROWS][K] bf16 operand is stored as
+// Operand layout used throughout (no swizzle, K-major "core matrices"): a [ROWS][K] fp16 operand is stored as
 //     byte_addr(r, k) = (k / 8) * (ROWS * 16) + r * 16 + (k % 8) * 2
 // i.e. for every group of 8 consecutive k the 16-byte pieces of all rows are contiguous.  A core matrix (8 rows x 16
 // bytes) is then 128 contiguous bytes; descriptor strides: SBO (next 8 rows) = 128 B, LBO (next 8 k) = ROWS * 16 B.
 // One thread per row writes 16-byte pieces with consecutive lanes on consecutive rows -> conflict-free stores.
 //
-// Split precision (hard part 3): a = a_hi + a_lo, b = b_hi + b_lo in bf16; the product is
-// a_hi*b_hi + a_hi*b_lo + a_lo*b_hi accumulated in f32 in TMEM (3 MMAs per k-step), ~2^-16 relative per product.
+// Split precision (hard part 3): a = a_hi + a_lo, b = b_hi + b_lo with hi = fp16(x),
+// lo = fp16(x - hi); the product is a_hi*b_hi + a_hi*b_lo + a_lo*b_hi accumulated in f32 in TMEM (3 MMAs per k-step).
+// fp16 keeps 11 significant bits per piece, so hi + lo carries ~22 bits (error ~2^-21 per product, f32-class); the
+// bf16 split the survey proposed carries only ~16 bits and measured 1.2e-4 on the network outputs -- over the 1e-4
+// parity bar.  Range: |x| must stay below 65504 (BN-normalised PointNet++ activations are O(1..100)).
 #pragma once
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace tc {
@@ -70,13 +73,14 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
     d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
     return d;                                            // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
 }
-// instruction descriptor: D f32, A/B bf16, both K-major, dense (cute::UMMA::InstrDescriptor bit layout)
-__host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N)
+// instruction descriptor: D f32 (c_format 1), A/B fp16 (a_format = b_format = 0), both K-major, dense
+// (cute::UMMA::InstrDescriptor bit layout)
+__host__ __device__ constexpr uint32_t instr_desc_f16(int M, int N)
 {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // D[tmem] (+)= A[smem] * B[smem]^T ; one elected thread
-__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -105,23 +109,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// ---- bf16 hi/lo split ---------------------------------------------------------------------------------
-__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16 &hi, __nv_bfloat16 &lo)
+// ---- fp16 hi/lo split ---------------------------------------------------------------------------------
+__device__ __forceinline__ void split_f16(float v, __half &hi, __half &lo)
 {
-    hi = __float2bfloat16_rn(v);
-    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
 }
-// 8 consecutive k of one row -> one 16-byte piece each for the hi and lo operand images
+// 8 consecutive k of one row -> one 16-byte piece each for the hi and lo operand images (fp16)
 __device__ __forceinline__ void store_split8(const float (&v)[8], uint4 *dst_hi, uint4 *dst_lo)
 {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(v[2 * i], h0, l0);
-        split_bf16(v[2 * i + 1], h1, l1);
-        h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        __half h0, l0, h1, l1;
+        split_f16(v[2 * i], h0, l0);
+        split_f16(v[2 * i + 1], h1, l1);
+        h[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        l[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
     }
     *dst_hi = make_uint4(h[0], h[1], h[2], h[3]);
     *dst_lo = make_uint4(l[0], l[1], l[2], l[3]);

@@ -44,14 +44,14 @@ _WS_VIEWS = {  # name -> (dtype, shape builder)
 
 class AncshNet:
     def __init__(self, weights, n_parts, mixed_pred=True, early_split_nocs=True, nsample=64, npoint1=512, npoint2=128,
-                 radius1=0.2, radius2=0.4, device="cuda:0", prefix="SPFN", precision="bf16x3"):
+                 radius1=0.2, radius2=0.4, device="cuda:0", prefix="SPFN", precision="f16x3"):
         """weights: dict TF-variable-name -> ndarray (see weights.variable_shapes).
         ANCSH (exp 3.9): mixed_pred=True, early_split_nocs=True (main.py:42-49);
         NPCS baseline (exp 3.91): mixed_pred=False, early_split_nocs=False.
-        precision: "bf16x3" = grouped MLPs on the tcgen05 tensor cores with the bf16 hi/lo split (f32-class accuracy,
+        precision: "f16x3" = grouped MLPs on the tcgen05 tensor cores with the fp16 hi/lo split (3 products, f32-class accuracy,
         default); "f32" = exact f32 FMA kernels on the CUDA cores."""
-        if precision not in ("bf16x3", "f32"):
-            raise ValueError("precision must be 'bf16x3' or 'f32'")
+        if precision not in ("f16x3", "f32"):
+            raise ValueError("precision must be 'f16x3' or 'f32'")
         self.precision = precision
         if not torch.cuda.is_available():
             raise RuntimeError("AncshNet needs a CUDA device (no CPU fallback)")
@@ -68,7 +68,7 @@ class AncshNet:
         tc_base = self._tcbuf.data_ptr()
 
         net = _lib.Net()
-        net.use_tensor_cores = int(precision == "bf16x3")
+        net.use_tensor_cores = int(precision == "f16x3")
         net.n_parts, net.mixed_pred = self.n_parts, int(self.mixed_pred)
         net.npoint1, net.nsample1, net.radius1 = self.npoint1, self.nsample1, float(radius1)
         net.npoint2, net.nsample2, net.radius2 = self.npoint2, self.nsample2, float(radius2)

@@ -19,7 +19,7 @@ class AncshPipeline:
     N_SLOTS = 4      # batches in flight in submit()/run_many(): pose tails of several batches overlap later forwards
 
     def __init__(self, weights_ancsh, n_parts, weights_npcs=None, use_baseline=True, nsample=64, niter_single=10000,
-                 niter_joint=200, inlier_th=0.1, seed=0, device="cuda:0", precision="bf16x3"):
+                 niter_joint=200, inlier_th=0.1, seed=0, device="cuda:0", precision="f16x3"):
         self.device = torch.device(device)
         self.K = int(n_parts)
         self.use_baseline = bool(use_baseline and weights_npcs is not None)

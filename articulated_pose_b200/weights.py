@@ -182,11 +182,15 @@ def bf16_bits_to_f32(b):
 
 def tc_image(W):
     """Tensor-core operand image of a padded weight matrix W [cin_pad][cout_pad] (f32): W^T split into
-    hi = bf16(w), lo = bf16(w - hi), tiled as [cin_pad/8][2][cout_pad][8] bf16 (csrc/tc_common.cuh)."""
+    hi = fp16(w), lo = fp16(w - hi) (round to nearest even), tiled as [cin_pad/8][2][cout_pad][8] fp16 bit patterns
+    (csrc/tc_common.cuh).  hi + lo carries ~22 significant bits of w."""
     K, N = W.shape
     Wt = np.ascontiguousarray(W.T, np.float32)                       # [N][K]
-    hi = f32_to_bf16_bits(Wt)
-    lo = f32_to_bf16_bits(Wt - bf16_bits_to_f32(hi))
+    if np.abs(Wt).max() >= 65504:
+        raise ValueError("weights exceed the fp16 range of the tensor-core path")
+    hi16 = Wt.astype(np.float16)
+    lo16 = (Wt - hi16.astype(np.float32)).astype(np.float16)
+    hi, lo = hi16.view(np.uint16), lo16.view(np.uint16)
     img = np.stack([hi.reshape(N, K // 8, 8), lo.reshape(N, K // 8, 8)], axis=0)   # [2][N][K/8][8]
     return np.ascontiguousarray(img.transpose(2, 0, 1, 3))          # [K/8][2][N][8]
 

@@ -55,8 +55,8 @@ def parse_args():
     ap.add_argument("--no-baseline-net", action="store_true", help="USE_BASELINE=False: one forward per cloud")
     ap.add_argument("--cpu-sample", type=int, default=0, help="clouds in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "f32"],
-                    help="bf16x3: grouped MLPs on tcgen05 (bf16 hi/lo split, f32 accumulate); f32: CUDA-core FMA kernels")
+    ap.add_argument("--precision", default="f16x3", choices=["f16x3", "f32"],
+                    help="f16x3: grouped MLPs on tcgen05 (fp16 hi/lo split, f32 accumulate); f32: CUDA-core FMA kernels")
     return ap.parse_args()
 
 
@@ -362,7 +362,7 @@ def main():
     peak = peaks["bf16_tflops_sustained"]
     n_fwd = 2 if (full and two_nets) else 1
     fwd_ms = sum(stage_ms.values())
-    roofline = {"bound": "tensor", "kernel": ("sa_tc_kernel" if args.precision == "bf16x3" else "sa_kernel<128>") + " (%s, ANCSH net)" % dom,
+    roofline = {"bound": "tensor", "kernel": ("sa_tc_kernel" if args.precision == "f16x3" else "sa_kernel<128>") + " (%s, ANCSH net)" % dom,
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                 "peak_source": peaks["source"] + " bf16 sustained; kernel duration from per-stage CUDA events of a serialized pass in the same run",
                 "avg_launch_ms": stage_ms[dom], "flops_per_launch": fl[dom],
@@ -372,7 +372,7 @@ def main():
     line = {"metric": METRIC, "value": world * B * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": ("bf16x3->f32" if args.precision == "bf16x3" else "f32") + (" network / f64 pose" if full else ""),
+            "dtype": ("f16x3->f32" if args.precision == "f16x3" else "f32") + (" network / f64 pose" if full else ""),
             "data": "synthetic",
             "config": {"workload": workload_name(args), "stages": args.stages, "l2_flush_between_steps": True,
                        "weights": "seeded random trunk, linear seg/NOCS heads ridge-fitted on %d synthetic clouds "

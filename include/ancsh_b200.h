@@ -81,14 +81,14 @@ int ancsh_three_interpolate(int b, int m, int c, int n, const float *points, con
 typedef struct {
     const float *W;
     const float *b;
-    const void *W_tc; /* NULL, or the tensor-core operand image of W: bf16 [cin_pad/8][2 (hi,lo)][cout_pad][8] with
-                         W^T split as hi = bf16(w), lo = bf16(w - hi) (weights.tc_image); used when use_tensor_cores */
+    const void *W_tc; /* NULL, or the tensor-core operand image of W: fp16 [cin_pad/8][2 (hi,lo)][cout_pad][8] with
+                         W^T split as hi = fp16(w), lo = fp16(w - hi) (weights.tc_image); used when use_tensor_cores */
     int cin, cout, cin_pad, cout_pad;
     int relu;
 } ancsh_layer_t;
 
 typedef struct {
-    int use_tensor_cores; /* 1: grouped MLPs on tcgen05 (bf16 hi/lo split, f32 accumulate in TMEM); 0: exact-f32 CUDA cores */
+    int use_tensor_cores; /* 1: grouped MLPs on tcgen05 (fp16 hi/lo split, 3 products, f32 accumulate in TMEM); 0: exact-f32 CUDA cores */
     int n_parts;    /* K = n_max_parts (eyeglasses 3, drawer 4) */
     int mixed_pred; /* 1: ANCSH heads [K,3K,K,3K,1] (architecture.py:98-102); 0: NPCS heads [K,3K,1] */
     int npoint1, nsample1;

@@ -1,4 +1,4 @@
-"""GPU probe: error of the f32 and bf16x3 network paths against the CPU oracle, per tensor."""
+"""GPU probe: error of the f32 and f16x3 network paths against the CPU oracle, per tensor."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -13,7 +13,7 @@ ref = pnpp.forward(P, w, 3, nsample=ns, trace=tr)
 def err(a, b):
     e = np.abs(a.astype(np.float64) - b) / np.maximum(np.abs(b), 1e-2)
     return e.max(), np.percentile(e, 99.9), e.mean()
-for prec in ("f32", "bf16x3"):
+for prec in ("f32", "f16x3"):
     net = AncshNet(w, 3, nsample=ns, precision=prec)
     out = net.forward(P)
     it = {k: v.cpu().numpy() for k, v in net.intermediates().items()}

@@ -56,9 +56,9 @@ def test_tc_image_layout_and_split():
     Wm = rng.normal(size=(32, 64)).astype(np.float32)
     img = W.tc_image(Wm)
     assert img.shape == (4, 2, 64, 8) and img.dtype == np.uint16
-    hi = W.bf16_bits_to_f32(img[:, 0]).transpose(1, 0, 2).reshape(64, 32)     # [N][K]
-    lo = W.bf16_bits_to_f32(img[:, 1]).transpose(1, 0, 2).reshape(64, 32)
-    np.testing.assert_allclose(hi + lo, Wm.T, rtol=2 ** -15, atol=1e-30)      # hi + lo carries ~16 mantissa bits
-    assert np.abs(lo).max() <= np.abs(Wm).max() * 2 ** -7
+    hi = img[:, 0].view(np.float16).astype(np.float32).transpose(1, 0, 2).reshape(64, 32)     # [N][K]
+    lo = img[:, 1].view(np.float16).astype(np.float32).transpose(1, 0, 2).reshape(64, 32)
+    np.testing.assert_allclose(hi + lo, Wm.T, rtol=2 ** -20, atol=1e-7)       # hi + lo carries ~22 mantissa bits
+    assert np.abs(lo).max() <= np.abs(Wm).max() * 2 ** -10
     flat, offs = W.flatten_tc_images(W.pack_network(W.synthetic_weights(3), 3))
     assert all(o % 128 == 0 for o in offs.values()) and set(offs) == set(W.TC_SLOTS)
