@@ -345,10 +345,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_s = float(t[0]), float(t[1])
         if full:   # the one collective of the path: gather the per-cloud pose records
-            rec = torch.cat([res["single_R"].reshape(B, -1), res["single_s"], res["single_t"].reshape(B, -1)], 1).contiguous()
-            allrec = [torch.empty_like(rec) for _ in range(world)]
-            dist.all_gather(allrec, rec)
-            gathered = sum(int(x.shape[0]) for x in allrec)
+            from articulated_pose_b200 import dist as adist
+            rec = torch.cat([res[k].reshape(B, -1).double() for k in
+                             ("single_R", "single_s", "single_t", "joint_R0", "joint_s0", "joint_t0", "joint_R1",
+                              "joint_s1", "joint_t1", "joint_score")], 1).contiguous()
+            gathered = int(adist.gather_records(rec, device=dev).shape[0])
 
     if rank != 0:
         if world > 1:
