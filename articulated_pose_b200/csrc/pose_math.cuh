@@ -16,9 +16,11 @@
 #ifdef __CUDACC__
 #define PM_HD __host__ __device__ __forceinline__
 #define PM_HDN __host__ __device__
+#define PM_NOINLINE __host__ __device__ __noinline__
 #else
 #define PM_HD inline
 #define PM_HDN
+#define PM_NOINLINE
 #endif
 
 namespace pm {
