@@ -363,6 +363,118 @@ static int fp_launch(const FpArgs &a0, int B, cudaStream_t st)
 }
 
 // ================================================================================================
+// Tensor-core path of the point-wise stages: interpolation and head activations as light kernels around
+// chain_tc_kernel (net_tc.cu)
+// ================================================================================================
+// three_nn + inverse-distance weights + three_interpolate -> (B,n1,C2) in global memory (pointnet_util.py:217-223)
+__global__ void __launch_bounds__(NT) fp_interp_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                                                       const float *__restrict__ points2, int n1, int m2, int C2,
+                                                       float *__restrict__ out)
+{
+    constexpr int TMI = 64, PARTS = NT / TMI;
+    extern __shared__ __align__(16) float s_known[];   // m2*3
+    __shared__ float s_w[TMI * 3];
+    __shared__ int s_i[TMI * 3];
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long row0 = (long)blockIdx.x * TMI;
+    for (int i = tid; i < m2 * 3; i += NT) s_known[i] = __ldg(xyz2 + (size_t)b * m2 * 3 + i);
+    __syncthreads();
+    {
+        const int row = tid / PARTS, part = tid % PARTS;
+        const float *q = xyz1 + ((size_t)b * n1 + row0 + row) * 3;
+        const float x1 = __ldg(q), y1 = __ldg(q + 1), z1 = __ldg(q + 2);
+        const int chunk = (m2 + PARTS - 1) / PARTS;
+        const int k0 = part * chunk, k1 = min(m2, k0 + chunk);
+        Best3 best;
+        best.init();
+        for (int k = k0; k < k1; ++k)
+            best.insert(nn_dist_unfused(s_known[k * 3], s_known[k * 3 + 1], s_known[k * 3 + 2], x1, y1, z1), k);
+#pragma unroll
+        for (int off = 1; off < PARTS; off <<= 1) {
+            Best3 o;
+            o.d1 = __shfl_xor_sync(0xFFFFFFFFu, best.d1, off); o.i1 = __shfl_xor_sync(0xFFFFFFFFu, best.i1, off);
+            o.d2 = __shfl_xor_sync(0xFFFFFFFFu, best.d2, off); o.i2 = __shfl_xor_sync(0xFFFFFFFFu, best.i2, off);
+            o.d3 = __shfl_xor_sync(0xFFFFFFFFu, best.d3, off); o.i3 = __shfl_xor_sync(0xFFFFFFFFu, best.i3, off);
+            if ((part & off) == 0) {
+                best.merge_higher(o);
+            } else {
+                o.merge_higher(best);
+                best = o;
+            }
+        }
+        if (part == 0) {
+            float w1, w2, w3;
+            three_weights(best.d1, best.d2, best.d3, w1, w2, w3);
+            s_w[row * 3 + 0] = w1; s_w[row * 3 + 1] = w2; s_w[row * 3 + 2] = w3;
+            s_i[row * 3 + 0] = best.i1; s_i[row * 3 + 1] = best.i2; s_i[row * 3 + 2] = best.i3;
+        }
+    }
+    __syncthreads();
+    for (int r = warp; r < TMI; r += NT / 32) {
+        const float w1 = s_w[r * 3], w2 = s_w[r * 3 + 1], w3 = s_w[r * 3 + 2];
+        const float *p1 = points2 + ((size_t)b * m2 + s_i[r * 3 + 0]) * C2;
+        const float *p2 = points2 + ((size_t)b * m2 + s_i[r * 3 + 1]) * C2;
+        const float *p3 = points2 + ((size_t)b * m2 + s_i[r * 3 + 2]) * C2;
+        float *o = out + ((size_t)b * n1 + row0 + r) * C2;
+        for (int c4 = lane; c4 < C2 / 4; c4 += 32) {
+            const float4 u = ldg4(p1 + c4 * 4), v = ldg4(p2 + c4 * 4), w = ldg4(p3 + c4 * 4);
+            float4 x;
+            x.x = interp3_unfused(u.x, v.x, w.x, w1, w2, w3);
+            x.y = interp3_unfused(u.y, v.y, w.y, w1, w2, w3);
+            x.z = interp3_unfused(u.z, v.z, w.z, w1, w2, w3);
+            x.w = interp3_unfused(u.w, v.w, w.w, w1, w2, w3);
+            *reinterpret_cast<float4 *>(o + c4 * 4) = x;
+        }
+    }
+}
+
+// activations of all heads (lib/architecture.py:122-139, 150-157) from the raw linear outputs, one thread per point
+__global__ void __launch_bounds__(256) heads_act_kernel(const float *__restrict__ raw1, const float *__restrict__ raw2,
+                                                        long rows, int K, int mixed, const ancsh_pred_t o)
+{
+    const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    float x[64];
+    const float4 *s1 = reinterpret_cast<const float4 *>(raw1 + (size_t)r * 64);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { const float4 t = __ldg(s1 + q); x[4 * q] = t.x; x[4 * q + 1] = t.y; x[4 * q + 2] = t.z; x[4 * q + 3] = t.w; }
+    float mx = x[0];
+    for (int k = 1; k < K; ++k) mx = fmaxf(mx, x[k]);
+    float sum = 0.f;
+    for (int k = 0; k < K; ++k) { x[k] = expf(x[k] - mx); sum += x[k]; }
+    for (int k = 0; k < K; ++k) o.W[(size_t)r * K + k] = x[k] / sum;
+    for (int k = K; k < 4 * K; ++k) { x[k] = sigmoidf_(x[k]); o.nocs_per_point[(size_t)r * 3 * K + (k - K)] = x[k]; }
+    if (mixed) {
+        for (int k = 4 * K; k < 5 * K; ++k) { x[k] = sigmoidf_(x[k]); o.global_scale[(size_t)r * K + (k - 4 * K)] = x[k]; }
+        for (int k = 5 * K; k < 8 * K; ++k) { x[k] = tanhf(x[k]); o.global_translation[(size_t)r * 3 * K + (k - 5 * K)] = x[k]; }
+        o.confi_per_point[r] = sigmoidf_(x[8 * K]);
+        for (int k = 0; k < 3 * K; ++k)
+            o.gocs_per_point[(size_t)r * 3 * K + k] = __fadd_rn(__fmul_rn(x[K + k], x[4 * K + k / 3]), x[5 * K + k]);
+    } else {
+        o.confi_per_point[r] = sigmoidf_(x[4 * K]);
+    }
+    const float4 *s2 = reinterpret_cast<const float4 *>(raw2 + (size_t)r * 64);
+    const float4 j0 = __ldg(s2), j1 = __ldg(s2 + 1), j2 = __ldg(s2 + 2);
+    const float y[10] = {j0.x, j0.y, j0.z, j0.w, j1.x, j1.y, j1.z, j1.w, j2.x, j2.y};
+    for (int k = 0; k < 3; ++k) o.joint_axis_per_point[(size_t)r * 3 + k] = tanhf(y[k]);
+    for (int k = 0; k < 3; ++k) o.unitvec_per_point[(size_t)r * 3 + k] = tanhf(y[3 + k]);
+    o.heatmap_per_point[r] = sigmoidf_(y[6]);
+    const float m2 = fmaxf(y[7], fmaxf(y[8], y[9]));
+    const float e0 = expf(y[7] - m2), e1 = expf(y[8] - m2), e2 = expf(y[9] - m2), es = e0 + e1 + e2;
+    o.index_per_point[(size_t)r * 3 + 0] = e0 / es;
+    o.index_per_point[(size_t)r * 3 + 1] = e1 / es;
+    o.index_per_point[(size_t)r * 3 + 2] = e2 / es;
+}
+
+static TcLayer tc_layer(const ancsh_layer_t &l)
+{
+    TcLayer t;
+    t.Wimg = reinterpret_cast<const __half *>(l.W_tc);
+    t.bias = l.b; t.K = l.cin_pad; t.N = l.cout_pad; t.relu = l.relu;
+    return t;
+}
+
+// ================================================================================================
 // plan + forward
 // ================================================================================================
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -388,6 +500,8 @@ extern "C" int ancsh_net_plan(const ancsh_net_t *net, int B, int N, ancsh_ws_lay
     L->fp1_bias = take(b * net->fp1_global.cout_pad * 4);
     L->l2_points_fp = take(b * m2 * net->fp1[1].cout * 4);
     L->l1_points_fp = take(b * m1 * net->fp2[1].cout * 4);
+    L->interp3 = take(net->use_tensor_cores ? b * N * net->fp2[1].cout * 4 : 0);
+    L->raw_heads = take(net->use_tensor_cores ? b * N * 64 * 4 * 2 : 0);
     L->total_bytes = off;
     return ANCSH_OK;
 }
@@ -469,7 +583,16 @@ extern "C" int ancsh_net_forward(const ancsh_net_t *net, int B, int N, const flo
         a.L[0] = net->fp1[0]; a.L[1] = net->fp1[1]; a.nl = 2;
         a.bias0 = fp1_bias; a.bias0_stride = G.cout_pad;
         a.out = l2_fp;
-        if ((rc = fp_launch<64, false>(a, B, st))) return rc;
+        if (net->use_tensor_cores && net->fp1[0].W_tc && net->fp1[1].W_tc) {
+            ChainTcArgs c{};
+            c.X1 = l2_points; c.C1 = net->sa2[2].cout; c.X2 = nullptr; c.C2 = 0;
+            c.rows_per_cloud = m2; c.bias0 = fp1_bias; c.bias0_stride = G.cout_pad;
+            c.S[0].L = tc_layer(net->fp1[0]); c.S[0].dst = TC_DST_INPLACE; c.S[0].out = nullptr; c.S[0].ldo = 0;
+            c.S[1].L = tc_layer(net->fp1[1]); c.S[1].dst = TC_DST_GLOBAL; c.S[1].out = l2_fp; c.S[1].ldo = net->fp1[1].cout;
+            c.nsteps = 2;
+            if (net->fp1[1].cout != net->fp1[1].cout_pad) return ANCSH_ERR_INVALID_ARG;
+            if ((rc = chain_tc_launch(c, (long)B * m2, st))) return rc;
+        } else if ((rc = fp_launch<64, false>(a, B, st))) return rc;
     }
     // fa_layer2
     STAGE_MARK();
@@ -480,7 +603,22 @@ extern "C" int ancsh_net_forward(const ancsh_net_t *net, int B, int N, const flo
         a.L[0] = net->fp2[0]; a.L[1] = net->fp2[1]; a.nl = 2;
         a.bias0 = net->fp2[0].b; a.bias0_stride = 0;
         a.out = l1_fp;
-        if ((rc = fp_launch<64, false>(a, B, st))) return rc;
+        if (net->use_tensor_cores && net->fp2[0].W_tc && net->fp2[1].W_tc) {
+            // interpolate into the (not yet used) fa_layer3 buffer, then [interp(256) | l1_points(128)] -> 256 -> 128
+            float *interp2 = (float *)(ws + L.interp3);
+            const int C2 = net->fp1[1].cout;
+            if (m1 % 64 != 0 || (size_t)m1 * C2 > (size_t)N * net->fp2[1].cout) return ANCSH_ERR_UNSUPPORTED;
+            fp_interp_kernel<<<dim3(m1 / 64, B), NT, (size_t)m2 * 3 * sizeof(float), st>>>(l1_xyz, l2_xyz, l2_fp, m1, m2, C2, interp2);
+            ANCSH_CHECK_LAUNCH();
+            ChainTcArgs c{};
+            c.X1 = interp2; c.C1 = C2; c.X2 = l1_points; c.C2 = net->sa1[2].cout; c.rows_per_cloud = m1;
+            c.bias0 = nullptr; c.bias0_stride = 0;
+            c.S[0].L = tc_layer(net->fp2[0]); c.S[0].dst = TC_DST_INPLACE; c.S[0].out = nullptr; c.S[0].ldo = 0;
+            c.S[1].L = tc_layer(net->fp2[1]); c.S[1].dst = TC_DST_GLOBAL; c.S[1].out = l1_fp; c.S[1].ldo = net->fp2[1].cout;
+            c.nsteps = 2;
+            if (net->fp2[1].cout != net->fp2[1].cout_pad) return ANCSH_ERR_INVALID_ARG;
+            if ((rc = chain_tc_launch(c, (long)B * m1, st))) return rc;
+        } else if ((rc = fp_launch<64, false>(a, B, st))) return rc;
     }
     // fa_layer3 + fc1 + heads
     STAGE_MARK();
@@ -493,7 +631,32 @@ extern "C" int ancsh_net_forward(const ancsh_net_t *net, int B, int N, const flo
         a.fc1 = net->fc1; a.nocs_heads = net->nocs_heads; a.fc3[0] = net->fc3[0]; a.fc3[1] = net->fc3[1];
         a.joint_heads = net->joint_heads;
         a.pred = *pred; a.K = net->n_parts; a.mixed = net->mixed_pred;
-        if ((rc = fp_launch<128, true>(a, B, st))) return rc;
+        if (net->use_tensor_cores && net->fp3[0].W_tc && net->joint_heads.W_tc) {
+            float *interp3 = (float *)(ws + L.interp3);
+            float *raw1 = (float *)(ws + L.raw_heads), *raw2 = raw1 + (size_t)B * N * 64;
+            const int C2 = net->fp2[1].cout;
+            if (N % 64 != 0 || C2 % 8 != 0 || net->nocs_heads.cout_pad != 64 || net->joint_heads.cout_pad != 64 ||
+                11 * net->n_parts + 1 > 64)
+                return ANCSH_ERR_UNSUPPORTED;
+            fp_interp_kernel<<<dim3(N / 64, B), NT, (size_t)m1 * 3 * sizeof(float), st>>>(P, l1_xyz, l1_fp, N, m1, C2, interp3);
+            ANCSH_CHECK_LAUNCH();
+            ChainTcArgs c{};
+            c.X1 = interp3; c.C1 = C2; c.X2 = P; c.C2 = 3; c.rows_per_cloud = N; c.bias0 = nullptr; c.bias0_stride = 0;
+            const ancsh_layer_t *seq[8] = {&net->fp3[0], &net->fp3[1], &net->fp3[2], &net->fc1, &net->nocs_heads,
+                                           &net->fc3[0], &net->fc3[1], &net->joint_heads};
+            for (int i = 0; i < 8; ++i) {
+                c.S[i].L = tc_layer(*seq[i]);
+                c.S[i].dst = TC_DST_INPLACE; c.S[i].out = nullptr; c.S[i].ldo = 0;
+            }
+            c.S[3].out = pred->net; c.S[3].ldo = net->fc1.cout;                       // optional copy of the trunk feature
+            c.S[4].dst = TC_DST_GLOBAL; c.S[4].out = raw1; c.S[4].ldo = 64;           // raw nocs_net outputs (net kept)
+            c.S[7].dst = TC_DST_GLOBAL; c.S[7].out = raw2; c.S[7].ldo = 64;           // raw joint_net outputs
+            c.nsteps = 8;
+            if ((rc = chain_tc_launch(c, (long)B * N, st))) return rc;
+            const long rows = (long)B * N;
+            heads_act_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(raw1, raw2, rows, net->n_parts, net->mixed_pred, *pred);
+            ANCSH_CHECK_LAUNCH();
+        } else if ((rc = fp_launch<128, true>(a, B, st))) return rc;
     }
     STAGE_MARK();
 #undef STAGE_MARK

@@ -157,6 +157,123 @@ __global__ void __launch_bounds__(TM) sa_tc_kernel(const SaTcArgs a)
     if (warp == 0) tc::tmem_dealloc(tmem, a.tmem_cols);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Row-tile chain for the point-wise stages (fa_layer1, fa_layer3 + fc1 + all heads): same operand-in-place scheme as
+// sa_tc_kernel, rows come straight from global memory, and every step either feeds the next one or writes rows out.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TM) chain_tc_kernel(const ChainTcArgs a)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *A_hi = smem;
+    uint8_t *A_lo = A_hi + (size_t)a.kmax8 * 2048;
+    uint8_t *Wst = A_lo + (size_t)a.kmax8 * 2048;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(Wst + (size_t)(KSLICE / 8) * 2 * a.nmax * 16);
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const long R = (long)blockIdx.x * TM + tid;
+
+    if (warp == 0) tc::tmem_alloc(s_tmem, a.tmem_cols);
+    if (tid == 0) tc::mbar_init(bar, 1);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *s_tmem;
+    uint32_t phase = 0;
+
+    {
+        const float *r1 = a.X1 + (size_t)R * a.C1;
+        const float *r2 = a.X2 ? a.X2 + (size_t)R * a.C2 : nullptr;
+        const int K0 = a.S[0].L.K;
+        for (int kc = 0; kc < K0 / 8; ++kc) {
+            float v[8];
+            if (kc * 8 + 8 <= a.C1) {
+                const float4 p0 = ldg4(r1 + kc * 8), p1 = ldg4(r1 + kc * 8 + 4);
+                v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
+            } else if (r2 && (a.C2 & 7) == 0 && kc * 8 >= a.C1 && kc * 8 + 8 <= a.C1 + a.C2) {
+                const float4 p0 = ldg4(r2 + (kc * 8 - a.C1)), p1 = ldg4(r2 + (kc * 8 - a.C1) + 4);
+                v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int c = kc * 8 + i;
+                    v[i] = c < a.C1 ? __ldg(r1 + c) : (r2 && c < a.C1 + a.C2 ? __ldg(r2 + (c - a.C1)) : 0.f);
+                }
+            }
+            tc::store_split8(v, reinterpret_cast<uint4 *>(A_hi + (size_t)kc * 2048 + tid * 16),
+                             reinterpret_cast<uint4 *>(A_lo + (size_t)kc * 2048 + tid * 16));
+        }
+    }
+    tc::fence_proxy_async();
+    const uint32_t a_hi0 = tc::smem_u32(A_hi), a_lo0 = tc::smem_u32(A_lo), w0 = tc::smem_u32(Wst);
+
+    for (int st = 0; st < a.nsteps; ++st) {
+        const ChainStep &S = a.S[st];
+        const TcLayer &L = S.L;
+        const int N = L.N, nk16 = L.K / 16;
+        const uint32_t idesc = tc::instr_desc_f16(TM, N);
+        const uint32_t slab = 2u * N * 16u;
+        for (int k16 = 0; k16 < nk16; k16 += KSLICE / 16) {
+            const int steps = min(KSLICE / 16, nk16 - k16);
+            const uint32_t bytes = (uint32_t)steps * 2u * slab;
+            const uint8_t *src = reinterpret_cast<const uint8_t *>(L.Wimg) + (size_t)k16 * 2 * slab;
+            for (uint32_t off = tid * 16; off < bytes; off += TM * 16) cp_async16(Wst + off, src + off);
+            cp_async_commit();
+            cp_async_wait<0>();
+            tc::fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) {
+                tc::fence_after_sync();
+                for (int s = 0; s < steps; ++s) {
+                    const int kk = k16 + s;
+                    const uint64_t ah = tc::smem_desc(a_hi0 + (uint32_t)(2 * kk) * 2048u, 2048u, 128u);
+                    const uint64_t al = tc::smem_desc(a_lo0 + (uint32_t)(2 * kk) * 2048u, 2048u, 128u);
+                    const uint64_t bh = tc::smem_desc(w0 + (uint32_t)(2 * s) * slab, slab, 128u);
+                    const uint64_t bl = tc::smem_desc(w0 + (uint32_t)(2 * s) * slab + (uint32_t)N * 16u, slab, 128u);
+                    tc::mma_f16(tmem, ah, bh, idesc, kk > 0 ? 1u : 0u);
+                    tc::mma_f16(tmem, ah, bl, idesc, 1u);
+                    tc::mma_f16(tmem, al, bh, idesc, 1u);
+                }
+                tc::mma_commit(bar);
+            }
+            tc::mbar_wait(bar, phase);
+            phase ^= 1;
+        }
+        tc::fence_after_sync();
+        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        const float *bias = (st == 0 && a.bias0) ? a.bias0 + (size_t)(R / a.rows_per_cloud) * a.bias0_stride : L.bias;
+        for (int c0 = 0; c0 < N; c0 += 32) {
+            float v[32];
+            tc::tmem_ld32(trow + c0, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float x = v[i] + __ldg(bias + c0 + i);
+                v[i] = L.relu ? fmaxf(x, 0.f) : x;
+            }
+            if (S.out) {
+                float4 *o = reinterpret_cast<float4 *>(S.out + (size_t)R * S.ldo + c0);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+            if (S.dst == TC_DST_INPLACE) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float w[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) w[i] = v[q * 8 + i];
+                    const int kc = (c0 >> 3) + q;
+                    tc::store_split8(w, reinterpret_cast<uint4 *>(A_hi + (size_t)kc * 2048 + tid * 16),
+                                     reinterpret_cast<uint4 *>(A_lo + (size_t)kc * 2048 + tid * 16));
+                }
+            }
+        }
+        tc::fence_proxy_async();
+        tc::fence_before_sync();
+        __syncthreads();
+    }
+    if (warp == 0) tc::tmem_dealloc(tmem, a.tmem_cols);
+}
+
 }  // namespace
 
 int sa_tc_launch(const SaTcArgs &a0, int B, cudaStream_t st)
@@ -186,6 +303,33 @@ int sa_tc_launch(const SaTcArgs &a0, int B, cudaStream_t st)
     if (a.S != 32) ANCSH_CUDA(cudaMemsetAsync(a.out, 0, (size_t)B * a.m * a.L[2].N * sizeof(float), st));
     dim3 grid((unsigned)(rows / TM), B);
     sa_tc_kernel<<<grid, TM, smem, st>>>(a);
+    ANCSH_CHECK_LAUNCH();
+    return ANCSH_OK;
+}
+
+int chain_tc_launch(const ChainTcArgs &a0, long rows_total, cudaStream_t st)
+{
+    ChainTcArgs a = a0;
+    if (rows_total % TM != 0 || a.C1 % 8 != 0 || a.nsteps < 1 || a.nsteps > 8) return ANCSH_ERR_UNSUPPORTED;
+    int kmax = 0, nmax = 0;
+    for (int i = 0; i < a.nsteps; ++i) {
+        const TcLayer &L = a.S[i].L;
+        if (!L.Wimg || L.K % 16 != 0 || L.N % 32 != 0 || L.N > 256) return ANCSH_ERR_INVALID_ARG;
+        if (a.S[i].dst == TC_DST_GLOBAL && !a.S[i].out) return ANCSH_ERR_INVALID_ARG;
+        if (a.S[i].out && (a.S[i].ldo < L.N || a.S[i].ldo % 4 != 0)) return ANCSH_ERR_INVALID_ARG;
+        kmax = L.K > kmax ? L.K : kmax;
+        if (a.S[i].dst == TC_DST_INPLACE && L.N > kmax) kmax = L.N;
+        nmax = L.N > nmax ? L.N : nmax;
+    }
+    if (a.S[0].L.K < a.C1 + (a.X2 ? a.C2 : 0)) return ANCSH_ERR_INVALID_ARG;
+    a.kmax8 = kmax / 8;
+    a.nmax = nmax;
+    a.tmem_cols = nmax <= 32 ? 32 : nmax <= 64 ? 64 : nmax <= 128 ? 128 : 256;
+    const size_t smem = (size_t)2 * a.kmax8 * 2048 + (size_t)(KSLICE / 8) * 2 * nmax * 16 + 16;
+    if (smem > 227 * 1024) return ANCSH_ERR_UNSUPPORTED;
+    ANCSH_CUDA(cudaFuncSetAttribute(chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ANCSH_CUDA(cudaFuncSetAttribute(chain_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    chain_tc_kernel<<<(unsigned)(rows_total / TM), TM, smem, st>>>(a);
     ANCSH_CHECK_LAUNCH();
     return ANCSH_OK;
 }

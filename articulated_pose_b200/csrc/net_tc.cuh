@@ -21,3 +21,28 @@ struct SaTcArgs {
 };
 
 int sa_tc_launch(const SaTcArgs &a, int B, cudaStream_t st);
+
+// ---- generic row-tile chain (feature propagation / heads) ------------------------------------------------------
+enum { TC_DST_INPLACE = 0, TC_DST_GLOBAL = 1 };
+
+struct ChainStep {
+    TcLayer L;
+    int dst;        // TC_DST_INPLACE: output becomes the next step's operand; TC_DST_GLOBAL: rows go to `out`, operand kept
+    float *out;     // [rows_total][ldo] f32; with TC_DST_INPLACE and out != NULL the rows are written as well
+    int ldo;
+};
+
+struct ChainTcArgs {
+    const float *X1;          // [rows_total][C1]
+    const float *X2;          // [rows_total][C2] appended after X1 (or NULL)
+    int C1, C2;
+    long rows_per_cloud;      // for the per-cloud bias of step 0
+    const float *bias0;       // NULL, or [clouds][bias0_stride] bias of step 0
+    long bias0_stride;
+    ChainStep S[8];
+    int nsteps;
+    int kmax8, nmax;          // filled by the launcher
+    uint32_t tmem_cols;
+};
+
+int chain_tc_launch(const ChainTcArgs &a, long rows_total, cudaStream_t st);

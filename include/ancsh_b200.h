@@ -140,6 +140,8 @@ typedef struct {
     size_t fp1_bias;  /* f32 (B,256)          per-cloud bias of fa_layer1/conv_0 */
     size_t l2_points_fp; /* f32 (B,npoint2,256) fa_layer1 output */
     size_t l1_points_fp; /* f32 (B,npoint1,128) fa_layer2 output */
+    size_t interp3;      /* f32 (B,N,128) interpolated features of fa_layer3 (tensor-core path only) */
+    size_t raw_heads;    /* f32 2 x (B,N,64) raw linear outputs of nocs_net / joint_net (tensor-core path only) */
     size_t total_bytes;
 } ancsh_ws_layout_t;
 
