@@ -568,7 +568,24 @@ extern "C" int ancsh_net_forward(const ancsh_net_t *net, int B, int N, const flo
         a.xyz = l2_xyz; a.points = l2_points; a.new_xyz = nullptr; a.idx = nullptr; a.out = l3_points;
         a.L[0] = net->sa3[0]; a.L[1] = net->sa3[1]; a.L[2] = net->sa3[2];
         a.n = m2; a.m = 1; a.S = m2; a.C = net->sa2[2].cout;
-        if ((rc = sa_launch<64>(a, B, st))) return rc;
+        if (net->use_tensor_cores && net->sa3[0].W_tc && net->sa3[2].W_tc) {
+            // group_all: three streaming GEMMs over the B*npoint2 rows; temporaries live in the fa_layer3 scratch
+            float *t1 = (float *)(ws + L.interp3);
+            float *t2 = t1 + (size_t)B * m2 * net->sa3[0].cout_pad;
+            if ((size_t)m2 * (net->sa3[0].cout_pad + net->sa3[1].cout_pad) > (size_t)N * net->fp2[1].cout || m2 % 32 != 0 ||
+                net->sa3[2].cout != net->sa3[2].cout_pad)
+                return ANCSH_ERR_UNSUPPORTED;
+            GemmTcArgs g{};
+            g.X1 = l2_points; g.C1 = net->sa2[2].cout; g.X2 = l2_xyz; g.C2 = 3; g.L = tc_layer(net->sa3[0]);
+            g.out = t1; g.ldo = net->sa3[0].cout_pad; g.pool_S = 0;
+            if ((rc = gemm_tc_launch(g, (long)B * m2, st))) return rc;
+            g.X1 = t1; g.C1 = net->sa3[0].cout_pad; g.X2 = nullptr; g.C2 = 0; g.L = tc_layer(net->sa3[1]);
+            g.out = t2; g.ldo = net->sa3[1].cout_pad;
+            if ((rc = gemm_tc_launch(g, (long)B * m2, st))) return rc;
+            g.X1 = t2; g.C1 = net->sa3[1].cout_pad; g.L = tc_layer(net->sa3[2]);
+            g.out = l3_points; g.ldo = 0; g.pool_S = m2;
+            if ((rc = gemm_tc_launch(g, (long)B * m2, st))) return rc;
+        } else if ((rc = sa_launch<64>(a, B, st))) return rc;
     }
     // fa_layer1
     STAGE_MARK();

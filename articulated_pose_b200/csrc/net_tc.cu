@@ -274,6 +274,119 @@ __global__ void __launch_bounds__(TM) chain_tc_kernel(const ChainTcArgs a)
     if (warp == 0) tc::tmem_dealloc(tmem, a.tmem_cols);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Streaming GEMM: neither operand is resident.  Per 32-wide k slice every thread converts its row's 32 f32 inputs to
+// the fp16 hi/lo images, the weight slice arrives by cp.async, 2 k-steps x 3 MMAs are issued.  blockIdx.y selects a
+// chunk of <= 256 output columns.  Used for layer3 (259 -> 256 -> 512 -> 1024 on the 128 points of each cloud).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TM) gemm_tc_kernel(const GemmTcArgs a)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *A_hi = smem;                                   // (KSLICE/8) * 2048
+    uint8_t *A_lo = A_hi + (KSLICE / 8) * 2048;
+    uint8_t *Wst = A_lo + (KSLICE / 8) * 2048;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(Wst + (size_t)(KSLICE / 8) * 2 * a.nchunk * 16);
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long R = (long)blockIdx.x * TM + tid;
+    const int n0 = blockIdx.y * a.nchunk;
+    const int NC = min(a.nchunk, a.L.N - n0);
+
+    if (warp == 0) tc::tmem_alloc(s_tmem, a.tmem_cols);
+    if (tid == 0) tc::mbar_init(bar, 1);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *s_tmem;
+    uint32_t phase = 0;
+
+    const float *r1 = a.X1 + (size_t)R * a.C1;
+    const float *r2 = a.X2 ? a.X2 + (size_t)R * a.C2 : nullptr;
+    const uint32_t a_hi0 = tc::smem_u32(A_hi), a_lo0 = tc::smem_u32(A_lo), w0 = tc::smem_u32(Wst);
+    const uint32_t idesc = tc::instr_desc_f16(TM, NC);
+    const uint32_t gslab = 2u * a.L.N * 16u;                 // global image: [K/8][2][N][8]
+    const uint32_t sslab = 2u * NC * 16u;                    // staged slice: [kc][2][NC][8]
+    const int nk16 = a.L.K / 16;
+    for (int k16 = 0; k16 < nk16; k16 += KSLICE / 16) {
+        const int steps = min(KSLICE / 16, nk16 - k16);
+        // weights: for each of the steps*2 k-groups copy the hi and lo rows [n0, n0+NC)
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(a.L.Wimg);
+        const int pieces = steps * 2 * 2 * NC;                // 16-byte pieces
+        for (int p = tid; p < pieces; p += TM) {
+            const int row = p % NC, part = (p / NC) & 1, kc = p / (2 * NC);
+            cp_async16(Wst + (size_t)kc * sslab + (size_t)part * NC * 16 + row * 16,
+                       src + (size_t)(k16 * 2 + kc) * gslab + (size_t)part * a.L.N * 16 + (size_t)(n0 + row) * 16);
+        }
+        cp_async_commit();
+        // activations: this thread's row, k in [k16*16, k16*16 + steps*16)
+        for (int kc = 0; kc < steps * 2; ++kc) {
+            const int c0 = (k16 * 2 + kc) * 8;
+            float v[8];
+            if (c0 + 8 <= a.C1) {
+                const float4 p0 = ldg4(r1 + c0), p1 = ldg4(r1 + c0 + 4);
+                v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int c = c0 + i;
+                    v[i] = c < a.C1 ? __ldg(r1 + c) : (r2 && c < a.C1 + a.C2 ? __ldg(r2 + (c - a.C1)) : 0.f);
+                }
+            }
+            tc::store_split8(v, reinterpret_cast<uint4 *>(A_hi + (size_t)kc * 2048 + tid * 16),
+                             reinterpret_cast<uint4 *>(A_lo + (size_t)kc * 2048 + tid * 16));
+        }
+        cp_async_wait<0>();
+        tc::fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            for (int s = 0; s < steps; ++s) {
+                const uint64_t ah = tc::smem_desc(a_hi0 + (uint32_t)(2 * s) * 2048u, 2048u, 128u);
+                const uint64_t al = tc::smem_desc(a_lo0 + (uint32_t)(2 * s) * 2048u, 2048u, 128u);
+                const uint64_t bh = tc::smem_desc(w0 + (uint32_t)(2 * s) * sslab, sslab, 128u);
+                const uint64_t bl = tc::smem_desc(w0 + (uint32_t)(2 * s) * sslab + (uint32_t)NC * 16u, sslab, 128u);
+                tc::mma_f16(tmem, ah, bh, idesc, (k16 + s) > 0 ? 1u : 0u);
+                tc::mma_f16(tmem, ah, bl, idesc, 1u);
+                tc::mma_f16(tmem, al, bh, idesc, 1u);
+            }
+            tc::mma_commit(bar);
+        }
+        tc::mbar_wait(bar, phase);
+        phase ^= 1;
+    }
+    tc::fence_after_sync();
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < NC; c0 += 32) {
+        float v[32];
+        tc::tmem_ld32(trow + c0, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const float x = v[i] + __ldg(a.L.bias + n0 + c0 + i);
+            v[i] = a.L.relu ? fmaxf(x, 0.f) : x;
+        }
+        if (a.pool_S == 0) {
+            float4 *o = reinterpret_cast<float4 *>(a.out + (size_t)R * a.ldo + n0 + c0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
+            const long g = ((long)blockIdx.x * TM + warp * 32) / a.pool_S;
+            float *orow = a.out + (size_t)g * a.L.N + n0 + c0;
+            uint32_t keep = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const uint32_t mx = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(v[i]));
+                if (lane == i) keep = mx;
+            }
+            if (a.pool_S == 32) orow[lane] = __uint_as_float(keep);
+            else atomicMax(reinterpret_cast<int *>(orow + lane), (int)keep);
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, a.tmem_cols);
+}
+
 }  // namespace
 
 int sa_tc_launch(const SaTcArgs &a0, int B, cudaStream_t st)
@@ -330,6 +443,27 @@ int chain_tc_launch(const ChainTcArgs &a0, long rows_total, cudaStream_t st)
     ANCSH_CUDA(cudaFuncSetAttribute(chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ANCSH_CUDA(cudaFuncSetAttribute(chain_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     chain_tc_kernel<<<(unsigned)(rows_total / TM), TM, smem, st>>>(a);
+    ANCSH_CHECK_LAUNCH();
+    return ANCSH_OK;
+}
+
+int gemm_tc_launch(const GemmTcArgs &a0, long rows_total, cudaStream_t st)
+{
+    GemmTcArgs a = a0;
+    if (rows_total % TM != 0 || a.C1 % 8 != 0) return ANCSH_ERR_UNSUPPORTED;
+    if (!a.L.Wimg || a.L.K % 16 != 0 || a.L.N % 32 != 0 || a.L.K < a.C1 + (a.X2 ? a.C2 : 0)) return ANCSH_ERR_INVALID_ARG;
+    if (a.pool_S && (a.pool_S % 32 != 0 || !a.L.relu)) return ANCSH_ERR_INVALID_ARG;
+    if (!a.pool_S && (a.ldo < a.L.N || a.ldo % 4 != 0)) return ANCSH_ERR_INVALID_ARG;
+    a.nchunk = a.L.N <= 256 ? a.L.N : 256;
+    if (a.L.N % a.nchunk != 0) return ANCSH_ERR_UNSUPPORTED;
+    a.tmem_cols = a.nchunk <= 32 ? 32 : a.nchunk <= 64 ? 64 : a.nchunk <= 128 ? 128 : 256;
+    const size_t smem = (size_t)2 * (KSLICE / 8) * 2048 + (size_t)(KSLICE / 8) * 2 * a.nchunk * 16 + 16;
+    ANCSH_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ANCSH_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    if (a.pool_S && a.pool_S != 32)
+        ANCSH_CUDA(cudaMemsetAsync(a.out, 0, (size_t)(rows_total / a.pool_S) * a.L.N * sizeof(float), st));
+    dim3 grid((unsigned)(rows_total / TM), (unsigned)(a.L.N / a.nchunk));
+    gemm_tc_kernel<<<grid, TM, smem, st>>>(a);
     ANCSH_CHECK_LAUNCH();
     return ANCSH_OK;
 }

@@ -46,3 +46,16 @@ struct ChainTcArgs {
 };
 
 int chain_tc_launch(const ChainTcArgs &a, long rows_total, cudaStream_t st);
+
+// ---- streaming GEMM (layers whose K or N do not fit the operand-resident chain: layer3 / group_all) -------------
+struct GemmTcArgs {
+    const float *X1, *X2;     // rows [rows_total][C1] (+ [rows_total][C2] appended), f32
+    int C1, C2;
+    TcLayer L;                // K >= C1 + C2 (zero padded), N arbitrary multiple of 32 (processed in chunks of <= 256)
+    float *out;               // pool_S == 0: [rows_total][ldo] rows;  pool_S > 0: [rows_total / pool_S][N] zero-initialised max-pool
+    int ldo;
+    int pool_S;               // rows per pooled group (multiple of 32), 0 = no pooling
+    int nchunk;               // filled by the launcher: columns per CTA
+    uint32_t tmem_cols;
+};
+int gemm_tc_launch(const GemmTcArgs &a, long rows_total, cudaStream_t st);

@@ -195,7 +195,7 @@ def tc_image(W):
     return np.ascontiguousarray(img.transpose(2, 0, 1, 3))          # [K/8][2][N][8]
 
 
-TC_SLOTS = ("sa1[0]", "sa1[1]", "sa1[2]", "sa2[0]", "sa2[1]", "sa2[2]", "fp1[0]", "fp1[1]", "fp2[0]", "fp2[1]", "fp3[0]", "fp3[1]", "fp3[2]",
+TC_SLOTS = ("sa1[0]", "sa1[1]", "sa1[2]", "sa2[0]", "sa2[1]", "sa2[2]", "sa3[0]", "sa3[1]", "sa3[2]", "fp1[0]", "fp1[1]", "fp2[0]", "fp2[1]", "fp3[0]", "fp3[1]", "fp3[2]",
             "fc1", "nocs_heads", "fc3[0]", "fc3[1]", "joint_heads")
 
 
