@@ -11,14 +11,13 @@
 // Included from pose_math.cuh (inside namespace pm).
 #pragma once
 
-// The 6x6 primitives below are __noinline__ on the device: lm_solve_fast calls them from several places and the fully
-// unrolled bodies would otherwise be replicated, blowing the kernels up to ~230 KB of SASS (far beyond the
-// instruction caches, which also evicts the code of kernels running concurrently on the same SM).
+// (Making the 6x6 primitives __noinline__ was measured: the code shrinks by 3% only -- the f64 sqrt / div / sincos
+// expansions dominate the ~230 KB of SASS -- and the by-reference arrays cost 50% in the block-cooperative refit.)
 // upper Cholesky of the symmetric 6x6 A (full storage) plus `shift` on the diagonal: S^T S = A + shift I.
 // Pivots that are not > tiny are treated as zero (row zeroed); returns the index of the first zero pivot (6 = none).
 // rinv[j] receives 1 / S[j][j] (0 for zero pivots): the triangular solves multiply instead of dividing -- f64 division
 // and sqrt are long software sequences on the GPU and dominate the latency of one LM iteration otherwise.
-PM_NOINLINE int chol6(const double (&A)[6][6], double shift, double tiny, double (&S)[6][6], double (&rinv)[6])
+PM_HD int chol6(const double (&A)[6][6], double shift, double tiny, double (&S)[6][6], double (&rinv)[6])
 {
     int nsing = 6;
 #pragma unroll
@@ -46,7 +45,7 @@ PM_NOINLINE int chol6(const double (&A)[6][6], double shift, double tiny, double
 }
 
 // w = S^-T b  (forward substitution with the upper factor), rows >= nsing give 0
-PM_NOINLINE void solve_lower6(const double (&S)[6][6], const double (&rinv)[6], int nsing, const double (&b)[6], double (&w)[6])
+PM_HD void solve_lower6(const double (&S)[6][6], const double (&rinv)[6], int nsing, const double (&b)[6], double (&w)[6])
 {
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
@@ -57,7 +56,7 @@ PM_NOINLINE void solve_lower6(const double (&S)[6][6], const double (&rinv)[6], 
     }
 }
 // x = S^-1 b  (back substitution), components >= nsing are 0
-PM_NOINLINE void solve_upper6(const double (&S)[6][6], const double (&rinv)[6], int nsing, const double (&b)[6], double (&x)[6])
+PM_HD void solve_upper6(const double (&S)[6][6], const double (&rinv)[6], int nsing, const double (&b)[6], double (&x)[6])
 {
 #pragma unroll
     for (int jj = 0; jj < 6; ++jj) {

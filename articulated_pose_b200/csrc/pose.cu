@@ -490,6 +490,9 @@ __global__ void __launch_bounds__(RT) joint_verify_kernel(const JointArgs a)
 }
 
 // block-cooperative evaluator of objective_eval over the masked (inlier) points in shared memory
+// Only warp 0 runs the LM control code (~230 KB of SASS); the other warps of the block sit in serve() and take part
+// in the residual / normal-equation sums when warp 0 posts a command.  Barrier protocol per evaluation: one
+// __syncthreads publishing (cmd, x), then block_sum's two.
 struct BlockProb {
     const double *x0, *y0, *x1, *y1;
     const unsigned char *m0, *m1;
@@ -497,9 +500,11 @@ struct BlockProb {
     double u[3];
     double nj;
     double *s_red;
-    __host__ __device__ double cost(const double *p) const
+    int *s_cmd;        // 0 = exit, 1 = cost, 2 = normal equations
+    double *s_x;       // [6] evaluation point
+
+    __device__ void part_cost(const double *p) const
     {
-#ifdef __CUDA_ARCH__
         pm::RotVec r0, r1;
         r0.set(p);
         r1.set(p + 3);
@@ -510,14 +515,10 @@ struct BlockProb {
             if (m1[i]) pm::accum_part(r1, 1, x1 + 3 * i, y1 + 3 * i, nullptr, fsq[0]);
         if (threadIdx.x == 0) pm::accum_joint(r0, r1, u, nj, nullptr, fsq[0]);
         block_sum<1, RT>(fsq, s_red);
-        return fsq[0];
-#else
-        return 0.0;
-#endif
+        s_result = fsq[0];
     }
-    __host__ __device__ void normal(const double *p, pm::Normal6 &N) const
+    __device__ void part_normal(const double *p, pm::Normal6 &N) const
     {
-#ifdef __CUDA_ARCH__
         pm::RotVec r0, r1;
         r0.set(p);
         r1.set(p + 3);
@@ -530,7 +531,49 @@ struct BlockProb {
         if (threadIdx.x == 0) pm::accum_joint(r0, r1, u, nj, &N, fsq);
         N.fsq = fsq;
         block_sum<43, RT>(N.JtJ, s_red);     // JtJ[36], Jtf[6], fsq are contiguous in Normal6
+    }
+    mutable double s_result;
+    // ---- called by warp 0 only (through pm::lm_solve_fast) ----
+    __host__ __device__ double cost(const double *p) const
+    {
+#ifdef __CUDA_ARCH__
+        if (threadIdx.x == 0) { *s_cmd = 1; for (int j = 0; j < 6; ++j) s_x[j] = p[j]; }
+        __syncthreads();
+        part_cost(p);
+        return s_result;
+#else
+        return 0.0;
 #endif
+    }
+    __host__ __device__ void normal(const double *p, pm::Normal6 &N) const
+    {
+#ifdef __CUDA_ARCH__
+        if (threadIdx.x == 0) { *s_cmd = 2; for (int j = 0; j < 6; ++j) s_x[j] = p[j]; }
+        __syncthreads();
+        part_normal(p, N);
+#endif
+    }
+    // ---- warps 1.. ----
+    __device__ void serve() const
+    {
+        for (;;) {
+            __syncthreads();
+            const int cmd = *s_cmd;
+            if (cmd == 0) break;
+            double p[6];
+            for (int j = 0; j < 6; ++j) p[j] = s_x[j];
+            if (cmd == 1) {
+                part_cost(p);
+            } else {
+                pm::Normal6 N;
+                part_normal(p, N);
+            }
+        }
+    }
+    __device__ void finish() const       // warp 0, after the solve
+    {
+        if (threadIdx.x == 0) *s_cmd = 0;
+        __syncthreads();
     }
 };
 static_assert(sizeof(pm::Normal6) == 43 * sizeof(double), "Normal6 must be 43 contiguous doubles");
@@ -564,6 +607,8 @@ __global__ void __launch_bounds__(RT) joint_refit_kernel(const JointArgs a)
     __shared__ double s_val[RT / 32];
     __shared__ int s_idx[RT / 32];
     __shared__ pm::JointModel s_model;
+    __shared__ int s_cmd;
+    __shared__ double s_x[6];
     const int prob = blockIdx.x, tid = threadIdx.x;
     int pa, pb;
     joint_parts(prob, a.K, pa, pb);
@@ -676,7 +721,14 @@ __global__ void __launch_bounds__(RT) joint_refit_kernel(const JointArgs a)
     P.u[0] = axis[0]; P.u[1] = axis[1]; P.u[2] = axis[2];
     P.nj = (double)min(nin0, nin1);
     P.s_red = s_red;
-    pm::lm_solve_fast(P, x, 1e-4, 1e-8, 1e-8, 600, 100.0);       // uniform control flow: every thread sees the same sums
+    P.s_cmd = &s_cmd;
+    P.s_x = s_x;
+    if (tid < 32) {
+        pm::lm_solve_fast(P, x, 1e-4, 1e-8, 1e-8, 600, 100.0);   // warp 0: LM control; all its lanes see the same sums
+        P.finish();
+    } else {
+        P.serve();
+    }
     if (tid == 0) {
         pm::rotvec_to_matrix(x, R0);
         pm::rotvec_to_matrix(x + 3, R1);
