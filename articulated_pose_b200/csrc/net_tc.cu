@@ -213,6 +213,8 @@ __global__ void __launch_bounds__(TM) chain_tc_kernel(const ChainTcArgs a)
         const int N = L.N, nk16 = L.K / 16;
         const uint32_t idesc = tc::instr_desc_f16(TM, N);
         const uint32_t slab = 2u * N * 16u;
+        const int G = tc_num_acc(L.K, a.max_acc);
+        uint32_t started = 0;
         for (int k16 = 0; k16 < nk16; k16 += KSLICE / 16) {
             const int steps = min(KSLICE / 16, nk16 - k16);
             const uint32_t bytes = (uint32_t)steps * 2u * slab;
@@ -230,9 +232,12 @@ __global__ void __launch_bounds__(TM) chain_tc_kernel(const ChainTcArgs a)
                     const uint64_t al = tc::smem_desc(a_lo0 + (uint32_t)(2 * kk) * 2048u, 2048u, 128u);
                     const uint64_t bh = tc::smem_desc(w0 + (uint32_t)(2 * s) * slab, slab, 128u);
                     const uint64_t bl = tc::smem_desc(w0 + (uint32_t)(2 * s) * slab + (uint32_t)N * 16u, slab, 128u);
-                    tc::mma_f16(tmem, ah, bh, idesc, kk > 0 ? 1u : 0u);
-                    tc::mma_f16(tmem, ah, bl, idesc, 1u);
-                    tc::mma_f16(tmem, al, bh, idesc, 1u);
+                    const int g = kk * G / nk16;                       // accumulator of this k-step
+                    const uint32_t d = tmem + (uint32_t)(g * a.acc_stride);
+                    tc::mma_f16(d, ah, bh, idesc, (started >> g) & 1u);
+                    started |= 1u << g;
+                    tc::mma_f16(d, ah, bl, idesc, 1u);
+                    tc::mma_f16(d, al, bh, idesc, 1u);
                 }
                 tc::mma_commit(bar);
             }
@@ -245,6 +250,12 @@ __global__ void __launch_bounds__(TM) chain_tc_kernel(const ChainTcArgs a)
         for (int c0 = 0; c0 < N; c0 += 32) {
             float v[32];
             tc::tmem_ld32(trow + c0, v);
+            for (int g = 1; g < G; ++g) {
+                float u[32];
+                tc::tmem_ld32(trow + g * a.acc_stride + c0, u);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += u[i];
+            }
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 const float x = v[i] + __ldg(bias + c0 + i);
@@ -308,6 +319,8 @@ __global__ void __launch_bounds__(TM) gemm_tc_kernel(const GemmTcArgs a)
     const uint32_t gslab = 2u * a.L.N * 16u;                 // global image: [K/8][2][N][8]
     const uint32_t sslab = 2u * NC * 16u;                    // staged slice: [kc][2][NC][8]
     const int nk16 = a.L.K / 16;
+    const int G = tc_num_acc(a.L.K, a.max_acc);
+    uint32_t started = 0;
     for (int k16 = 0; k16 < nk16; k16 += KSLICE / 16) {
         const int steps = min(KSLICE / 16, nk16 - k16);
         // weights: for each of the steps*2 k-groups copy the hi and lo rows [n0, n0+NC)
@@ -346,9 +359,12 @@ __global__ void __launch_bounds__(TM) gemm_tc_kernel(const GemmTcArgs a)
                 const uint64_t al = tc::smem_desc(a_lo0 + (uint32_t)(2 * s) * 2048u, 2048u, 128u);
                 const uint64_t bh = tc::smem_desc(w0 + (uint32_t)(2 * s) * sslab, sslab, 128u);
                 const uint64_t bl = tc::smem_desc(w0 + (uint32_t)(2 * s) * sslab + (uint32_t)NC * 16u, sslab, 128u);
-                tc::mma_f16(tmem, ah, bh, idesc, (k16 + s) > 0 ? 1u : 0u);
-                tc::mma_f16(tmem, ah, bl, idesc, 1u);
-                tc::mma_f16(tmem, al, bh, idesc, 1u);
+                const int g = (k16 + s) * G / nk16;
+                const uint32_t d = tmem + (uint32_t)(g * a.acc_stride);
+                tc::mma_f16(d, ah, bh, idesc, (started >> g) & 1u);
+                started |= 1u << g;
+                tc::mma_f16(d, ah, bl, idesc, 1u);
+                tc::mma_f16(d, al, bh, idesc, 1u);
             }
             tc::mma_commit(bar);
         }
@@ -360,6 +376,12 @@ __global__ void __launch_bounds__(TM) gemm_tc_kernel(const GemmTcArgs a)
     for (int c0 = 0; c0 < NC; c0 += 32) {
         float v[32];
         tc::tmem_ld32(trow + c0, v);
+        for (int g = 1; g < G; ++g) {
+            float u[32];
+            tc::tmem_ld32(trow + g * a.acc_stride + c0, u);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += u[i];
+        }
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
             const float x = v[i] + __ldg(a.L.bias + n0 + c0 + i);
@@ -437,9 +459,21 @@ int chain_tc_launch(const ChainTcArgs &a0, long rows_total, cudaStream_t st)
     if (a.S[0].L.K < a.C1 + (a.X2 ? a.C2 : 0)) return ANCSH_ERR_INVALID_ARG;
     a.kmax8 = kmax / 8;
     a.nmax = nmax;
-    a.tmem_cols = nmax <= 32 ? 32 : nmax <= 64 ? 64 : nmax <= 128 ? 128 : 256;
+    a.acc_stride = nmax <= 32 ? 32 : nmax <= 64 ? 64 : nmax <= 128 ? 128 : 256;
     const size_t smem = (size_t)2 * a.kmax8 * 2048 + (size_t)(KSLICE / 8) * 2 * nmax * 16 + 16;
     if (smem > 227 * 1024) return ANCSH_ERR_UNSUPPORTED;
+    {
+        // two CTAs per SM (<= 256 columns each) while shared memory allows it, else the whole 512-column TMEM
+        const int budget = smem > 113 * 1024 ? 512 : 256;
+        int need = 1;
+        for (int i = 0; i < a.nsteps; ++i) {
+            const int g = tc_num_acc(a.S[i].L.K, budget / a.acc_stride);
+            need = g > need ? g : need;
+        }
+        a.max_acc = need;
+        int cols = a.acc_stride * need;
+        a.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+    }
     ANCSH_CUDA(cudaFuncSetAttribute(chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ANCSH_CUDA(cudaFuncSetAttribute(chain_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     chain_tc_kernel<<<(unsigned)(rows_total / TM), TM, smem, st>>>(a);
@@ -454,9 +488,14 @@ int gemm_tc_launch(const GemmTcArgs &a0, long rows_total, cudaStream_t st)
     if (!a.L.Wimg || a.L.K % 16 != 0 || a.L.N % 32 != 0 || a.L.K < a.C1 + (a.X2 ? a.C2 : 0)) return ANCSH_ERR_INVALID_ARG;
     if (a.pool_S && (a.pool_S % 32 != 0 || !a.L.relu)) return ANCSH_ERR_INVALID_ARG;
     if (!a.pool_S && (a.ldo < a.L.N || a.ldo % 4 != 0)) return ANCSH_ERR_INVALID_ARG;
-    a.nchunk = a.L.N <= 256 ? a.L.N : 256;
+    a.nchunk = a.L.N <= 128 ? a.L.N : 128;               // 128-column chunks leave room for up to 4 accumulators
     if (a.L.N % a.nchunk != 0) return ANCSH_ERR_UNSUPPORTED;
-    a.tmem_cols = a.nchunk <= 32 ? 32 : a.nchunk <= 64 ? 64 : a.nchunk <= 128 ? 128 : 256;
+    a.acc_stride = a.nchunk <= 32 ? 32 : a.nchunk <= 64 ? 64 : 128;
+    a.max_acc = tc_num_acc(a.L.K, 256 / a.acc_stride);   // <= 256 columns per CTA: two CTAs per SM
+    {
+        const int cols = a.acc_stride * a.max_acc;
+        a.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : 256;
+    }
     const size_t smem = (size_t)2 * (KSLICE / 8) * 2048 + (size_t)(KSLICE / 8) * 2 * a.nchunk * 16 + 16;
     ANCSH_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ANCSH_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));

@@ -43,7 +43,17 @@ struct ChainTcArgs {
     int nsteps;
     int kmax8, nmax;          // filled by the launcher
     uint32_t tmem_cols;
+    int acc_stride, max_acc;  // TMEM columns per accumulator / accumulators available (see tc_num_acc)
 };
+
+// The tensor core adds into its f32 accumulator with truncation, so the error grows linearly with the number of MMAs
+// chained into one accumulator (measured: K = 512 gives 4x the error of K = 128).  Layers with K > 144 therefore split
+// their k range over several TMEM accumulators that the epilogue adds in round-to-nearest f32.
+__host__ __device__ inline int tc_num_acc(int K, int max_acc)
+{
+    const int g = (K + 143) / 144;
+    return g < max_acc ? (g < 1 ? 1 : g) : max_acc;
+}
 
 int chain_tc_launch(const ChainTcArgs &a, long rows_total, cudaStream_t st);
 
@@ -57,5 +67,6 @@ struct GemmTcArgs {
     int pool_S;               // rows per pooled group (multiple of 32), 0 = no pooling
     int nchunk;               // filled by the launcher: columns per CTA
     uint32_t tmem_cols;
+    int acc_stride, max_acc;
 };
 int gemm_tc_launch(const GemmTcArgs &a, long rows_total, cudaStream_t st);

@@ -16,7 +16,7 @@ from .pose import PoseSolver, unpack_results
 
 
 class AncshPipeline:
-    N_SLOTS = 4      # batches in flight in submit()/run_many(): pose tails of several batches overlap later forwards
+    N_SLOTS = int(__import__('os').environ.get('ANCSH_SLOTS', '4'))      # batches in flight in submit()/run_many(): pose tails of several batches overlap later forwards
 
     def __init__(self, weights_ancsh, n_parts, weights_npcs=None, use_baseline=True, nsample=64, niter_single=10000,
                  niter_joint=200, inlier_th=0.1, seed=0, device="cuda:0", precision="f16x3"):
