@@ -15,9 +15,8 @@ struct SaTcArgs {
     float *out;
     TcLayer L[3];
     int n, m, S, C;
-    int kmax8, nmax;             // filled by the launcher
+    int kmax8, nch;              // filled by the launcher: operand width / 8, output chunk width
     uint32_t tmem_cols;
-    int terms;                   // products per k-step: 3 = hi*hi + hi*lo + lo*hi (default), 4 adds lo*lo
 };
 
 int sa_tc_launch(const SaTcArgs &a, int B, cudaStream_t st);
@@ -41,14 +40,11 @@ struct ChainTcArgs {
     long bias0_stride;
     ChainStep S[8];
     int nsteps;
-    int kmax8, nmax;          // filled by the launcher
+    int kmax8;                // filled by the launcher
     uint32_t tmem_cols;
-    int acc_stride, max_acc;  // TMEM columns per accumulator / accumulators available (see tc_num_acc)
 };
 
-// The tensor core adds into its f32 accumulator with truncation, so the error grows linearly with the number of MMAs
-// chained into one accumulator (measured: K = 512 gives 4x the error of K = 128).  Layers with K > 144 therefore split
-// their k range over several TMEM accumulators that the epilogue adds in round-to-nearest f32.
+// number of hi*hi accumulators a layer's k range is split over (net_tc.cu, "Numerics")
 __host__ __device__ inline int tc_num_acc(int K, int max_acc)
 {
     const int g = (K + 143) / 144;
@@ -65,8 +61,7 @@ struct GemmTcArgs {
     float *out;               // pool_S == 0: [rows_total][ldo] rows;  pool_S > 0: [rows_total / pool_S][N] zero-initialised max-pool
     int ldo;
     int pool_S;               // rows per pooled group (multiple of 32), 0 = no pooling
-    int nchunk;               // filled by the launcher: columns per CTA
-    uint32_t tmem_cols;
-    int acc_stride, max_acc;
+    uint32_t tmem_cols;       // filled by the launcher
+    int max_acc;              // hi*hi accumulators (k range split), see tc_num_acc
 };
 int gemm_tc_launch(const GemmTcArgs &a, long rows_total, cudaStream_t st);
