@@ -16,7 +16,7 @@ from .pose import PoseSolver, unpack_results
 
 
 class AncshPipeline:
-    N_SLOTS = int(__import__('os').environ.get('ANCSH_SLOTS', '4'))      # batches in flight in submit()/run_many(): pose tails of several batches overlap later forwards
+    N_SLOTS = 4      # batches in flight in submit()/run_many(): pose tails of several batches overlap later forwards
 
     def __init__(self, weights_ancsh, n_parts, weights_npcs=None, use_baseline=True, nsample=64, niter_single=10000,
                  niter_joint=200, inlier_th=0.1, seed=0, device="cuda:0", precision="f16x3"):
@@ -82,7 +82,7 @@ class AncshPipeline:
         if slot not in self._pose_streams:
             # high priority: the pose kernels are latency-bound (a few long LM solves); they should grab an SM slot as
             # soon as one frees up while the forwards of later batches fill the rest of the machine
-            self._pose_streams[slot] = torch.cuda.Stream(device=self.device, priority=int(__import__('os').environ.get('ANCSH_POSE_PRIO', '-1')))
+            self._pose_streams[slot] = torch.cuda.Stream(device=self.device, priority=-1)
         ps = self._pose_streams[slot]
         if sl["used"]:
             main.wait_event(sl["pose_done"])          # the slot's prediction buffers are still being read
