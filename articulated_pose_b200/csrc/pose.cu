@@ -6,7 +6,8 @@
 //                          part's points staged in shared memory as f64            (:35-54)
 //   single_refit_kernel    first-max hypothesis, its inlier mask, refit on the inliers incl. the O(n^2)
 //                          pairwise-distance scale                                   (:28-32, d3_utils.py:223-246)
-//   joint_estimate_kernel  one thread per hypothesis: 3+3 samples, MINPACK-lmder LM (pose_math.cuh / lm_fast.cuh) (:106-184)
+//   joint_init / joint_lm / joint_model kernels   per hypothesis: 3+3 samples, MINPACK-lmder LM as a SIMT state machine
+//                          (pose_math.cuh / lm_tick.cuh), model assembly                                (:106-184)
 //   joint_verify_kernel    inlier counts of every hypothesis, warp per hypothesis                     (:186-194)
 //   joint_refit_kernel     first-max hypothesis, masks, block-cooperative LM refit on all inliers
 //   umeyama_kernel         lib/aligning.py:580-622 (GT poses, compute_gt_pose.py:87)
@@ -336,7 +337,6 @@ __global__ void __launch_bounds__(RT) single_refit_kernel(const SingleArgs a)
 // ================================================================================================
 // joint RANSAC
 // ================================================================================================
-struct TailItem;
 struct JointArgs {
     const float *part_src, *part_tgt;   // (nparts_total, N, 3)
     const int *part_count;              // (nparts_total)
@@ -346,8 +346,7 @@ struct JointArgs {
     int *nfev;                          // (nprob, niter)
     pm::JointModel *models;             // (nprob, niter) per-hypothesis models
     int nprob;
-    int *tail_count;                    // [LM_TAIL_ROUNDS + 1] sizes of the per-round work lists of suspended LM solves
-    struct TailItem *tail_items;        // 2 x (nprob * niter), ping-pong between rounds
+    int *tail_count;                    // work counter of joint_lm_kernel (next unclaimed hypothesis)
     int *best;                          // (nprob)
     int N, K, niter;
     double th2;
@@ -366,25 +365,6 @@ __device__ __forceinline__ void joint_parts(int prob, int K, int &pa, int &pb)
     pb = b * K + j;
 }
 
-constexpr int JT = 32;   // threads per block of the joint estimation kernels (one LM solve per thread).
-// __launch_bounds__(32, 9) caps them at 224 registers: 4 such warps (28.7k registers) still leave room for one
-// 256-thread MLP block (34.8k) on the same SM, so lingering LM warps never lock the forward kernels out.
-
-// One thread per hypothesis: 3+3 samples -> joint_transformation_estimator (LM), in two phases.  MINPACK's LM needs
-// ~10 residual evaluations for most hypotheses but hundreds for a few (exactly as in the reference), and one thread
-// needs tens of microseconds per evaluation.  Phase 1 gives every hypothesis LM_BUDGET1 evaluations; solves that are
-// not finished by then are suspended (lm_fast.cuh, bit-identical to an uninterrupted solve) and appended to a
-// work list that phase 2 drains with a handful of densely packed warps, so the long tail holds ~1 warp per SM and
-// the rest of the machine is free for other kernels (the next batch's forwards run on another stream).
-constexpr int LM_BUDGET1 = 24;
-
-struct TailItem {
-    int t;
-    pm::LmState st;
-};
-
-static_assert(sizeof(TailItem) <= 112, "ancsh_pose_plan reserves 112 bytes per suspended solve");
-
 __device__ __forceinline__ void gather_joint_samples(const JointArgs &a, int prob, int h, int pa, int pb, int n0, int n1,
                                                      double *S0, double *T0, double *S1, double *T1)
 {
@@ -400,63 +380,169 @@ __device__ __forceinline__ void gather_joint_samples(const JointArgs &a, int pro
         }
 }
 
-__global__ void __launch_bounds__(JT, 9) joint_estimate_kernel(const JointArgs a)
+// ---- joint estimation = three kernels --------------------------------------------------------------------------
+//   joint_init_kernel   thread per hypothesis: 3+3 samples, scale_pts / centring / Kabsch start (:121-148) -> JointRec
+//   joint_lm_kernel     the LM solves (:154-155) as a SIMT state machine (lm_tick.cuh): persistent warps, one solve
+//                       per lane, every loop trip = one trial step for all lanes; a lane whose solve terminated takes
+//                       the next unsolved record, so short solves (median 12 evaluations) and long ones (MINPACK's
+//                       maxfev = 600) share warps without idling lanes
+//   joint_model_kernel  thread per hypothesis: rotation vectors -> {R0,s0,t0,R1,s1,t1} (:156-184)
+struct JointRec {
+    double pts[36];                            // x0[9] y0[9] x1[9] y1[9]: centred sources, pre-scaled centred targets
+    double x[6];                               // rotation vectors: Kabsch start, overwritten with the LM solution
+    double fnorm0;                             // |f(x)| at the start
+    double s0, s1;                             // scale_pts of each part (:121; never refined, :174)
+    double mS0[3], mT0[3], mS1[3], mT1[3];     // sample means: t = mean(T - s R S) = mean(T) - s R mean(S)
+    int valid, pad;
+};
+static_assert(sizeof(JointRec) == 464, "ancsh_pose_plan reserves 464 bytes per joint hypothesis");
+
+constexpr int JIT = 128;   // threads per block of the init / model kernels
+
+__global__ void __launch_bounds__(JIT) joint_init_kernel(const JointArgs a, JointRec *recs)
 {
-    const long t = (long)blockIdx.x * JT + threadIdx.x;
+    const long t = (long)blockIdx.x * JIT + threadIdx.x;
     if (t >= (long)a.nprob * a.niter) return;
     const int prob = (int)(t / a.niter), h = (int)(t - (long)prob * a.niter);
     int pa, pb;
     joint_parts(prob, a.K, pa, pb);
     const int n0 = a.part_count[pa], n1 = a.part_count[pb];
-    if (n0 <= 0 || n1 <= 0) { a.nfev[t] = 0; return; }
+    JointRec &r = recs[t];
+    if (n0 <= 0 || n1 <= 0) { r.valid = 0; a.nfev[t] = 0; return; }
     double S0[9], T0[9], S1[9], T1[9];
     gather_joint_samples(a, prob, h, pa, pb, n0, n1, S0, T0, S1, T1);
-    pm::JointModel m;
-    pm::LmState st;
-    st.iter = 0;
-    const pm::LmResult lr = pm::joint_estimate3(S0, T0, S1, T1, a.axis_med + (size_t)prob * 3, m, &st, LM_BUDGET1);
-    if (lr.info == pm::LM_SUSPENDED) {
-        const int slot = atomicAdd(a.tail_count, 1);          // work list of round 0
-        a.tail_items[slot].t = (int)t;
-        a.tail_items[slot].st = st;
-    } else {
-        a.nfev[t] = lr.nfev;
-        a.models[t] = m;
+    double S0c[9], T0c[9], S1c[9], T1c[9], s0, s1, R[9], x[6];
+    pm::centre_scale3(S0, T0, S0c, T0c, &s0);
+    pm::centre_scale3(S1, T1, S1c, T1c, &s1);
+    pm::kabsch_points(S0c, T0c, 3, R);                         // :138-139
+    pm::matrix_to_rotvec(R, x);                                // :147-148
+    pm::kabsch_points(S1c, T1c, 3, R);
+    pm::matrix_to_rotvec(R, x + 3);
+    pm::SerialProb P;
+    P.x0 = S0c; P.y0 = T0c; P.n0 = 3; P.x1 = S1c; P.y1 = T1c; P.n1 = 3;
+    const double *u = a.axis_med + (size_t)prob * 3;
+    P.u[0] = u[0]; P.u[1] = u[1]; P.u[2] = u[2];
+    P.nj = 3.0;                                                // min(n0,n1) copies of the joint direction, :134
+    r.fnorm0 = sqrt(P.cost(x));
+    for (int i = 0; i < 9; ++i) { r.pts[i] = S0c[i]; r.pts[9 + i] = T0c[i]; r.pts[18 + i] = S1c[i]; r.pts[27 + i] = T1c[i]; }
+    for (int i = 0; i < 6; ++i) r.x[i] = x[i];
+    r.s0 = s0; r.s1 = s1;
+    for (int c = 0; c < 3; ++c) {
+        r.mS0[c] = (S0[c] + S0[3 + c] + S0[6 + c]) / 3.0; r.mT0[c] = (T0[c] + T0[3 + c] + T0[6 + c]) / 3.0;
+        r.mS1[c] = (S1[c] + S1[3 + c] + S1[6 + c]) / 3.0; r.mT1[c] = (T1[c] + T1[3 + c] + T1[6 + c]) / 3.0;
+    }
+    r.valid = 1;
+}
+
+constexpr int LMT = 64;          // threads per block of joint_lm_kernel
+constexpr int LM_SOLVES_PER_LANE = 3;
+constexpr int LM_BLOCKS_PER_SM = 6;   // 168 registers x 64 threads
+constexpr int LM_SLOTS = 39;     // doubles per lane in shared memory: 36 point coordinates + joint direction
+
+// objective_eval over one lane's 3+3 points; element e of the lane lives at pts[e * LMT] (conflict-free)
+struct LaneProb {
+    const double *pts;
+    __device__ __forceinline__ void load3(int e, double *v) const
+    {
+        v[0] = pts[e * LMT]; v[1] = pts[(e + 1) * LMT]; v[2] = pts[(e + 2) * LMT];
+    }
+    __device__ __forceinline__ double cost(const double *p) const
+    {
+        pm::RotVec r0, r1;
+        r0.set(p);
+        r1.set(p + 3);
+        double fsq = 0.0, x[3], y[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { load3(3 * i, x); load3(9 + 3 * i, y); pm::accum_part(r0, 0, x, y, nullptr, fsq); }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { load3(18 + 3 * i, x); load3(27 + 3 * i, y); pm::accum_part(r1, 1, x, y, nullptr, fsq); }
+        load3(36, x);
+        pm::accum_joint(r0, r1, x, 3.0, nullptr, fsq);
+        return fsq;
+    }
+    __device__ __forceinline__ void normal(const double *p, pm::Normal6 &N) const
+    {
+        pm::RotVec r0, r1;
+        r0.set(p);
+        r1.set(p + 3);
+        N.zero();
+        double fsq = 0.0, x[3], y[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { load3(3 * i, x); load3(9 + 3 * i, y); pm::accum_part(r0, 0, x, y, &N, fsq); }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { load3(18 + 3 * i, x); load3(27 + 3 * i, y); pm::accum_part(r1, 1, x, y, &N, fsq); }
+        load3(36, x);
+        pm::accum_joint(r0, r1, x, 3.0, &N, fsq);
+        N.fsq = fsq;
+    }
+};
+
+__global__ void __launch_bounds__(LMT, LM_BLOCKS_PER_SM) joint_lm_kernel(const JointArgs a, JointRec *recs, int total)
+{
+    __shared__ double s_pts[LM_SLOTS * LMT];
+    double *my = s_pts + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    LaneProb P;
+    P.pts = my;
+    pm::LmTick s;
+    int t = -1;             // record this lane is solving
+    bool more = true;       // unclaimed records may remain
+    for (;;) {
+        const bool want = t < 0 && more;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, want);
+        if (m) {                                              // warp-aggregated claim of the next records
+            const int leader = __ffs(m) - 1;
+            int base = 0;
+            if ((int)lane == leader) base = atomicAdd(a.tail_count, __popc(m));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (want) {
+                const int mine = base + __popc(m & ((1u << lane) - 1u));
+                if (mine >= total) {
+                    more = false;
+                } else if (recs[mine].valid) {
+                    const JointRec &r = recs[mine];
+                    t = mine;
+#pragma unroll 4
+                    for (int e = 0; e < 36; ++e) my[e * LMT] = r.pts[e];
+                    const double *u = a.axis_med + (size_t)(mine / a.niter) * 3;
+                    my[36 * LMT] = u[0]; my[37 * LMT] = u[1]; my[38 * LMT] = u[2];
+                    pm::lm_tick_init(s, r.x, r.fnorm0);
+                }
+            }
+        }
+        if (!__any_sync(0xFFFFFFFFu, t >= 0)) {
+            if (!__any_sync(0xFFFFFFFFu, more)) break;
+            continue;
+        }
+        if (t >= 0) {
+            pm::lm_tick(P, s, 1e-4, 1e-8, 1e-8, 600, 100.0);  // ftol=1e-4 (:155), xtol=gtol=1e-8, max_nfev=100 n, factor=100
+            if (s.info != 0) {
+                JointRec &r = recs[t];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) r.x[j] = s.x[j];
+                a.nfev[t] = s.nfev;
+                t = -1;
+            }
+        }
     }
 }
 
-// Round r of the tail: every suspended solve gets LM_BUDGET_ROUND more evaluations (all lanes of a warp start their
-// items together, so the warp stays convergent); still-unfinished solves are re-queued, densely packed, for the next
-// round.  The last round runs to completion (MINPACK's own maxfev = 600 bounds it).
-constexpr int LM_BUDGET_ROUND = 64;
-constexpr int LM_TAIL_ROUNDS = 9;     // 24 + 8*64 = 536 evaluations, then one unbounded round
-
-__global__ void __launch_bounds__(JT, 9) joint_estimate_round_kernel(const JointArgs a, int round, int last)
+__global__ void __launch_bounds__(JIT) joint_model_kernel(const JointArgs a, const JointRec *recs)
 {
-    const int count = a.tail_count[round];
-    const TailItem *in = a.tail_items + (size_t)(round & 1) * a.nprob * a.niter;
-    TailItem *out = a.tail_items + (size_t)((round + 1) & 1) * a.nprob * a.niter;
-    for (int w = blockIdx.x * JT + threadIdx.x; w < count; w += gridDim.x * JT) {
-        const int t = in[w].t;
-        pm::LmState st = in[w].st;
-        const int prob = t / a.niter, h = t - prob * a.niter;
-        int pa, pb;
-        joint_parts(prob, a.K, pa, pb);
-        const int n0 = a.part_count[pa], n1 = a.part_count[pb];
-        double S0[9], T0[9], S1[9], T1[9];
-        gather_joint_samples(a, prob, h, pa, pb, n0, n1, S0, T0, S1, T1);
-        pm::JointModel m;
-        const int budget = last ? 0x7fffffff : st.nfev + LM_BUDGET_ROUND;
-        const pm::LmResult lr = pm::joint_estimate3(S0, T0, S1, T1, a.axis_med + (size_t)prob * 3, m, &st, budget);
-        if (lr.info == pm::LM_SUSPENDED) {
-            const int slot = atomicAdd(a.tail_count + round + 1, 1);
-            out[slot].t = t;
-            out[slot].st = st;
-        } else {
-            a.nfev[t] = lr.nfev;
-            a.models[t] = m;
-        }
-    }
+    const long t = (long)blockIdx.x * JIT + threadIdx.x;
+    if (t >= (long)a.nprob * a.niter) return;
+    const JointRec &r = recs[t];
+    if (!r.valid) return;
+    pm::JointModel m;
+    pm::rotvec_to_matrix(r.x, m.R0);                           // :156-157
+    pm::rotvec_to_matrix(r.x + 3, m.R1);
+    m.s0 = r.s0; m.s1 = r.s1;
+    double rs[3];
+    pm::matvec3(m.R0, r.mS0, rs);
+    for (int c = 0; c < 3; ++c) m.t0[c] = r.mT0[c] - m.s0 * rs[c];   // mean(T - s R S), :174-175 (un-refined scale)
+    pm::matvec3(m.R1, r.mS1, rs);
+    for (int c = 0; c < 3; ++c) m.t1[c] = r.mT1[c] - m.s1 * rs[c];
+    a.models[t] = m;
 }
 
 // joint_transformation_verifier (:186-194): one block per problem, points staged in shared memory as f64, one
@@ -636,7 +722,7 @@ __global__ void __launch_bounds__(RT) joint_refit_kernel(const JointArgs a)
     const double *axis = a.axis_med + (size_t)prob * 3;
     const int hbest = block_first_argmax_f64(a.scores + (size_t)prob * a.niter, a.niter, s_val, s_idx);   // syncs
     if (tid == 0) {
-        s_model = a.models[(size_t)prob * a.niter + hbest];       // the winning hypothesis' model (joint_estimate_kernel)
+        s_model = a.models[(size_t)prob * a.niter + hbest];       // the winning hypothesis' model (joint_model_kernel)
         a.best[prob] = hbest;
         a.score_out[prob] = a.scores[(size_t)prob * a.niter + hbest];
     }
@@ -724,7 +810,7 @@ __global__ void __launch_bounds__(RT) joint_refit_kernel(const JointArgs a)
     P.s_cmd = &s_cmd;
     P.s_x = s_x;
     if (tid < 32) {
-        pm::lm_solve_fast(P, x, 1e-4, 1e-8, 1e-8, 600, 100.0);   // warp 0: LM control; all its lanes see the same sums
+        pm::lm_solve_tick(P, x, 1e-4, 1e-8, 1e-8, 600, 100.0);   // warp 0: LM control; all its lanes see the same sums
         P.finish();
     } else {
         P.serve();
@@ -829,7 +915,7 @@ extern "C" int ancsh_pose_plan(const ancsh_pose_cfg_t *cfg, int B, int N, ancsh_
     L->joint_best = take(b * (K > 1 ? K - 1 : 1) * 4);
     L->joint_nfev = take(b * (K > 1 ? K - 1 : 1) * (size_t)cfg->niter_joint * 4);
     L->joint_models = take(b * (K > 1 ? K - 1 : 1) * (size_t)cfg->niter_joint * sizeof(pm::JointModel));
-    L->joint_tail = take(256 + 2 * b * (K > 1 ? K - 1 : 1) * (size_t)cfg->niter_joint * 112);   /* counters + 2 x TailItem[] */
+    L->joint_tail = take(256 + b * (K > 1 ? K - 1 : 1) * (size_t)cfg->niter_joint * 464);   /* work counter + JointRec[] */
     L->total_bytes = off;
     return ANCSH_OK;
 }
@@ -906,20 +992,32 @@ extern "C" int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in
         a.models = (pm::JointModel *)(ws + L.joint_models);
         a.nprob = B * (K - 1);
         a.tail_count = (int *)(ws + L.joint_tail);
-        a.tail_items = (TailItem *)(ws + L.joint_tail + 256);
+        JointRec *recs = (JointRec *)(ws + L.joint_tail + 256);
         ANCSH_CUDA(cudaMemsetAsync(a.tail_count, 0, 64 * sizeof(int), st));
         a.N = N; a.K = K; a.niter = cfg->niter_joint; a.th2 = th2; a.seed = cfg->seed;
         a.R0 = out->joint_R0; a.s0 = out->joint_s0; a.t0 = out->joint_t0;
         a.R1 = out->joint_R1; a.s1 = out->joint_s1; a.t1 = out->joint_t1; a.score_out = out->joint_score;
         a.inl0 = out->joint_inliers0; a.inl1 = out->joint_inliers1; a.status = out->status;
         size_t smem = (size_t)N * 6 * sizeof(double);          // n0 + n1 <= N
-        const long nthreads = (long)a.nprob * cfg->niter_joint;
-        joint_estimate_kernel<<<(unsigned)((nthreads + JT - 1) / JT), JT, 0, st>>>(a);
+        const long nsolves = (long)a.nprob * cfg->niter_joint;
+        if (nsolves > 0x7fffffffL) return ANCSH_ERR_UNSUPPORTED;
+        const unsigned gsolve = (unsigned)((nsolves + JIT - 1) / JIT);
+        joint_init_kernel<<<gsolve, JIT, 0, st>>>(a, recs);
         ANCSH_CHECK_LAUNCH();
-        for (int r = 0; r < LM_TAIL_ROUNDS; ++r) {
-            joint_estimate_round_kernel<<<296, JT, 0, st>>>(a, r, r == LM_TAIL_ROUNDS - 1 ? 1 : 0);
+        {
+            // persistent lanes: about one lane per LM_SOLVES_PER_LANE hypotheses, so that refilling finished lanes evens
+            // out the very uneven solve lengths; never more blocks than can be resident (SM count x LM_BLOCKS_PER_SM)
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            long blocks = (nsolves + (long)LMT * LM_SOLVES_PER_LANE - 1) / ((long)LMT * LM_SOLVES_PER_LANE);
+            const long cap = (long)sms * LM_BLOCKS_PER_SM;
+            blocks = blocks < 1 ? 1 : (blocks > cap ? cap : blocks);
+            joint_lm_kernel<<<(unsigned)blocks, LMT, 0, st>>>(a, recs, (int)nsolves);
             ANCSH_CHECK_LAUNCH();
         }
+        joint_model_kernel<<<gsolve, JIT, 0, st>>>(a, recs);
+        ANCSH_CHECK_LAUNCH();
         ANCSH_CUDA(cudaFuncSetAttribute(joint_verify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ANCSH_CUDA(cudaFuncSetAttribute(joint_verify_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         joint_verify_kernel<<<a.nprob, RT, smem, st>>>(a);

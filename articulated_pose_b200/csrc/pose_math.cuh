@@ -660,6 +660,7 @@ PM_HDN inline LmResult lm_solve(const Prob &prob, double *x, double ftol, double
 }
 
 #include "lm_fast.cuh"
+#include "lm_tick.cuh"
 
 // ---------------------------------------------------------------------------------------------------
 // scale_pts (d3_utils.py:237-246) for a handful of points (all ordered pairs; i==j pairs contribute 0)

@@ -385,7 +385,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": world * B * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
-            "gpu_launches": (11 * n_fwd + (5 if full else 0)) * args.steps,
+            "gpu_launches": (16 * n_fwd + (8 if full else 0)) * args.steps,   # kernels per forward / per pose stage (profiles/*launches*)
             "roofline": roofline}
 
     if not args.no_cpu_baseline:

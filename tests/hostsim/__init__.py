@@ -9,8 +9,9 @@ SO = os.path.join(HERE, "libpose_math_host.so")
 
 def load():
     src = os.path.join(HERE, "pose_math_host.cpp")
-    hdr = os.path.join(HERE, "..", "..", "articulated_pose_b200", "csrc", "pose_math.cuh")
-    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    csrc = os.path.join(HERE, "..", "..", "articulated_pose_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, h) for h in ("pose_math.cuh", "lm_fast.cuh", "lm_tick.cuh")]
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(d) for d in deps):
         # -ffp-contract=off: keep host rounding comparable with the device build's explicit operations
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", src,
                                "-o", SO])

@@ -41,6 +41,18 @@ int hs_lm_fast(const double *x0, const double *y0, int n0, const double *x1, con
     out[0] = r.nfev; out[1] = r.njev; out[2] = r.fnorm;
     return r.info;
 }
+// the SIMT state-machine variant (lm_tick.cuh) the joint estimation kernels run
+int hs_lm_tick(const double *x0, const double *y0, int n0, const double *x1, const double *y1, int n1, const double *u,
+               double nj, double *x, double ftol, double xtol, double gtol, int maxfev, double factor, double *out)
+{
+    pm::SerialProb P;
+    P.x0 = x0; P.y0 = y0; P.n0 = n0; P.x1 = x1; P.y1 = y1; P.n1 = n1;
+    P.u[0] = u[0]; P.u[1] = u[1]; P.u[2] = u[2];
+    P.nj = nj;
+    pm::LmResult r = pm::lm_solve_tick(P, x, ftol, xtol, gtol, maxfev, factor);
+    out[0] = r.nfev; out[1] = r.njev; out[2] = r.fnorm;
+    return r.info;
+}
 int hs_joint_estimate3(const double *S0, const double *T0, const double *S1, const double *T1, const double *u,
                        double *model26, double *out)
 {

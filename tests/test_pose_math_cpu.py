@@ -115,10 +115,10 @@ def _problem(rng, n0, n1, noise, garbage=False):
     return x0, y0, x1, y1, u, init
 
 
-def _run_ours(lib, x0, y0, x1, y1, u, init, ftol=1e-4, fast=True):
+def _run_ours(lib, x0, y0, x1, y1, u, init, ftol=1e-4, fast=True, tick=False):
     x = init.copy(); out = np.zeros(3)
     c = np.ascontiguousarray
-    info = (lib.hs_lm_fast if fast else lib.hs_lm)(dp(c(x0)), dp(c(y0)), len(x0), dp(c(x1)), dp(c(y1)), len(x1), dp(c(u)), ctypes.c_double(min(len(x0), len(x1))),
+    info = (lib.hs_lm_tick if tick else lib.hs_lm_fast if fast else lib.hs_lm)(dp(c(x0)), dp(c(y0)), len(x0), dp(c(x1)), dp(c(y1)), len(x1), dp(c(u)), ctypes.c_double(min(len(x0), len(x1))),
                      dp(x), ctypes.c_double(ftol), ctypes.c_double(1e-8), ctypes.c_double(1e-8), 600, ctypes.c_double(100.0), dp(out))
     return x, info, int(out[0]), int(out[1])
 
@@ -234,6 +234,41 @@ def test_fast_lm_equals_literal_minpack_port(lib):
             worst = max(worst, np.abs(xa - xb).max())
     assert same_nfev >= 0.97 * n, same_nfev
     assert worst < 1e-8, worst
+
+
+def test_tick_lm_equals_literal_minpack_port(lib):
+    """lm_tick.cuh (unpivoted state machine the joint kernels run) vs the literal qrfac/qrsolv port: same iterates,
+    same nfev, on well-posed and on garbage problems."""
+    rng = np.random.default_rng(22)
+    same_nfev, worst = 0, 0.0
+    n = 600
+    for t in range(n):
+        prob = _problem(rng, 3, 3, 0.02, garbage=(t % 3 == 0))
+        xa, ia, na, _ = _run_ours(lib, *prob, tick=True)
+        xb, ib, nb, _ = _run_ours(lib, *prob, fast=False)
+        same_nfev += int(na == nb and ia == ib)
+        if na == nb:
+            worst = max(worst, np.abs(xa - xb).max())
+    assert same_nfev >= 0.97 * n, same_nfev
+    assert worst < 1e-8, worst
+
+
+def test_tick_lm_rank_deficient_samples(lib):
+    """Repeated sample indices (collinear / coincident points) make J^T J singular: the tick solver must take the
+    pivoted fallback and still agree with the literal port."""
+    rng = np.random.default_rng(23)
+    agree = 0
+    n = 100
+    for t in range(n):
+        x0, y0, x1, y1, u, init = _problem(rng, 3, 3, 0.02)
+        x0[1] = x0[0]; y0[1] = y0[0]                     # duplicated sample in part 0
+        if t % 2:
+            x1[2] = x1[0]; y1[2] = y1[0]
+        xa, ia, na, _ = _run_ours(lib, x0, y0, x1, y1, u, init, tick=True)
+        xb, ib, nb, _ = _run_ours(lib, x0, y0, x1, y1, u, init, fast=False)
+        assert np.isfinite(xa).all() and ia != 0
+        agree += int(na == nb and np.abs(xa - xb).max() < 1e-6)
+    assert agree >= 0.9 * n, agree
 
 
 def test_suspend_resume_is_bit_identical(lib):
