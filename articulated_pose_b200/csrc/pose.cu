@@ -18,13 +18,17 @@
 namespace {
 
 constexpr int RT = 256;   // threads of the cooperative kernels
+constexpr int RJ = 128;   // threads of joint_refit_kernel: ~240 registers (LM control code) -> two blocks per SM
 
 // ------------------------------------------------------------------------------------------------
-// block reduction of NV doubles per thread (fixed order -> deterministic); result broadcast to all threads
+// block reduction of NV doubles per thread (fixed order -> deterministic); result broadcast to all threads.
+// s_red: (NTH/32 + 1) * NV doubles.  Warp shuffles -> one partial per warp -> thread k adds the partials of value k ->
+// everybody reads the NV totals (two barriers; the totals live in their own slice, so the next call may start at once).
 // ------------------------------------------------------------------------------------------------
 template <int NV, int NTH>
 __device__ void block_sum(double *v, double *s_red)
 {
+    constexpr int NW = NTH / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll 1
     for (int k = 0; k < NV; ++k) {
@@ -33,13 +37,71 @@ __device__ void block_sum(double *v, double *s_red)
         if (lane == 0) s_red[warp * NV + k] = x;
     }
     __syncthreads();
-#pragma unroll 1
-    for (int k = 0; k < NV; ++k) {
+    if (threadIdx.x < NV) {
         double x = 0.0;
-        for (int w = 0; w < NTH / 32; ++w) x += s_red[w * NV + k];
-        v[k] = x;
+        for (int w = 0; w < NW; ++w) x += s_red[w * NV + threadIdx.x];
+        s_red[NW * NV + threadIdx.x] = x;
     }
     __syncthreads();
+#pragma unroll 1
+    for (int k = 0; k < NV; ++k) v[k] = s_red[NW * NV + k];
+}
+
+// ordered list of the indices i < n with mask[i] != 0 -> list[0 .. count); returns count (same in every thread).
+// s_scan: NTH/32 ints.  Ends with a barrier.
+template <int NTH>
+__device__ int block_compact_indices(const unsigned char *mask, int n, int *list, int *s_scan)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int chunk = (n + NTH - 1) / NTH, i0 = min(n, tid * chunk), i1 = min(n, i0 + chunk);
+    int c = 0;
+    for (int i = i0; i < i1; ++i) c += mask[i] ? 1 : 0;
+    int incl = c;
+    for (int off = 1; off < 32; off <<= 1) {
+        const int o = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+        if (lane >= off) incl += o;
+    }
+    if (lane == 31) s_scan[warp] = incl;
+    __syncthreads();
+    int base = 0, total = 0;
+    for (int w = 0; w < NTH / 32; ++w) {
+        const int x = s_scan[w];
+        if (w < warp) base += x;
+        total += x;
+    }
+    int pos = base + incl - c;
+    for (int i = i0; i < i1; ++i)
+        if (mask[i]) list[pos++] = i;
+    __syncthreads();
+    return total;
+}
+
+// Per-thread partial sums over the unordered pairs {i, j} of the listed points (scale_pts, d3_utils.py:237-246):
+// ab += |s_i - s_j| |t_i - t_j|, aa += |s_i - s_j|^2, bb += |t_i - t_j|^2.  Row r is paired with row n-1-r so that every
+// thread walks the same number of pairs; |a||b| is evaluated as sqrt(|a|^2 |b|^2) (one f64 square root per pair).
+__device__ __forceinline__ void pair_row(const double *S, const double *T, const int *list, int n, int r, double &ab, double &aa,
+                                         double &bb)
+{
+    const double *si = S + 3 * list[r], *ti = T + 3 * list[r];
+    const double s0 = si[0], s1 = si[1], s2 = si[2], t0 = ti[0], t1 = ti[1], t2 = ti[2];
+    for (int c = r + 1; c < n; ++c) {
+        const double *sj = S + 3 * list[c], *tj = T + 3 * list[c];
+        const double d0 = s0 - sj[0], d1 = s1 - sj[1], d2 = s2 - sj[2];
+        const double e0 = t0 - tj[0], e1 = t1 - tj[1], e2 = t2 - tj[2];
+        const double A2 = d0 * d0 + d1 * d1 + d2 * d2, B2 = e0 * e0 + e1 * e1 + e2 * e2;
+        ab += sqrt(A2 * B2); aa += A2; bb += B2;
+    }
+}
+template <int NTH>
+__device__ void pair_sums(const double *S, const double *T, const int *list, int n, double &ab, double &aa, double &bb)
+{
+    ab = 0.0; aa = 0.0; bb = 0.0;
+    const int half = (n + 1) / 2;
+    for (int r = threadIdx.x; r < half; r += NTH) {
+        pair_row(S, T, list, n, r, ab, aa, bb);
+        const int r2 = n - 1 - r;
+        if (r2 != r) pair_row(S, T, list, n, r2, ab, aa, bb);
+    }
 }
 
 __device__ __forceinline__ bool is_inlier(const double *R, double s, const double *t, const double *src, const double *tgt,
@@ -237,13 +299,15 @@ __device__ int block_first_argmax_int(const int *scores, int n, unsigned long lo
 __global__ void __launch_bounds__(RT) single_refit_kernel(const SingleArgs a)
 {
     extern __shared__ double s_pts[];
-    __shared__ double s_red[(RT / 32) * 16];
+    __shared__ double s_red[(RT / 32 + 1) * 11];
     __shared__ unsigned long long s_key[RT / 32];
     __shared__ double s_model[13];
+    __shared__ int s_scan[RT / 32];
     const int prob = blockIdx.x, tid = threadIdx.x;
     const int n = a.part_count[prob];
     double *s_src = s_pts, *s_tgt = s_pts + (size_t)a.N * 3;
-    unsigned char *s_inl = reinterpret_cast<unsigned char *>(s_pts + (size_t)a.N * 6);
+    int *s_list = reinterpret_cast<int *>(s_pts + (size_t)a.N * 6);                 // indices of the inliers, ascending
+    unsigned char *s_inl = reinterpret_cast<unsigned char *>(s_list + a.N);
     unsigned char *g_inl = a.inliers + (size_t)prob * a.N;
     double *oR = a.R + (size_t)prob * 9, *ot = a.t + (size_t)prob * 3;
     if (n <= 0) {
@@ -303,22 +367,17 @@ __global__ void __launch_bounds__(RT) single_refit_kernel(const SingleArgs a)
         for (int c = 0; c < 3; ++c) { s_src[3 * i + c] -= ms[c]; s_tgt[3 * i + c] -= mt[c]; }
     __syncthreads();
     // M = target_c^T source_c (9) and the pairwise sums of scale_pts over unordered inlier pairs (2)
+    block_compact_indices<RT>(s_inl, n, s_list, s_scan);
     double v[11];
-    for (int k = 0; k < 11; ++k) v[k] = 0.0;
-    for (int i = tid; i < n; i += RT) {
-        if (!s_inl[i]) continue;
-        const double *si = s_src + 3 * i, *ti = s_tgt + 3 * i;
+    for (int k = 0; k < 9; ++k) v[k] = 0.0;
+    for (int c = tid; c < nin; c += RT) {
+        const double *si = s_src + 3 * s_list[c], *ti = s_tgt + 3 * s_list[c];
         for (int p = 0; p < 3; ++p)
             for (int q = 0; q < 3; ++q) v[3 * p + q] += ti[p] * si[q];
-        for (int j = i + 1; j < n; ++j) {
-            if (!s_inl[j]) continue;
-            const double *sj = s_src + 3 * j, *tj = s_tgt + 3 * j;
-            const double d0 = si[0] - sj[0], d1 = si[1] - sj[1], d2 = si[2] - sj[2];
-            const double e0 = ti[0] - tj[0], e1 = ti[1] - tj[1], e2 = ti[2] - tj[2];
-            const double A2 = d0 * d0 + d1 * d1 + d2 * d2, B2 = e0 * e0 + e1 * e1 + e2 * e2;
-            v[9] += sqrt(A2) * sqrt(B2);
-            v[10] += A2;
-        }
+    }
+    {
+        double bb;
+        pair_sums<RT>(s_src, s_tgt, s_list, nin, v[9], v[10], bb);
     }
     block_sum<11, RT>(v, s_red);
     if (tid == 0) {
@@ -390,12 +449,15 @@ __device__ __forceinline__ void gather_joint_samples(const JointArgs &a, int pro
 struct JointRec {
     double pts[36];                            // x0[9] y0[9] x1[9] y1[9]: centred sources, pre-scaled centred targets
     double x[6];                               // rotation vectors: Kabsch start, overwritten with the LM solution
-    double fnorm0;                             // |f(x)| at the start
+    double fnorm;                              // |f(x)|
     double s0, s1;                             // scale_pts of each part (:121; never refined, :174)
     double mS0[3], mT0[3], mS1[3], mT1[3];     // sample means: t = mean(T - s R S) = mean(T) - s R mean(S)
-    int valid, pad;
+    double par, delta, xnorm;                  // lmder state of a suspended solve (valid when iter > 1)
+    int iter, nfev, njev;                      // iter == 1: fresh record
+    int valid;
+    double pad[2];
 };
-static_assert(sizeof(JointRec) == 464, "ancsh_pose_plan reserves 464 bytes per joint hypothesis");
+static_assert(sizeof(JointRec) == 512, "ancsh_pose_plan reserves 512 bytes per joint hypothesis");
 
 constexpr int JIT = 128;   // threads per block of the init / model kernels
 
@@ -423,7 +485,9 @@ __global__ void __launch_bounds__(JIT) joint_init_kernel(const JointArgs a, Join
     const double *u = a.axis_med + (size_t)prob * 3;
     P.u[0] = u[0]; P.u[1] = u[1]; P.u[2] = u[2];
     P.nj = 3.0;                                                // min(n0,n1) copies of the joint direction, :134
-    r.fnorm0 = sqrt(P.cost(x));
+    r.fnorm = sqrt(P.cost(x));
+    r.par = 0.0; r.delta = 0.0; r.xnorm = 0.0;
+    r.iter = 1; r.nfev = 1; r.njev = 0;
     for (int i = 0; i < 9; ++i) { r.pts[i] = S0c[i]; r.pts[9 + i] = T0c[i]; r.pts[18 + i] = S1c[i]; r.pts[27 + i] = T1c[i]; }
     for (int i = 0; i < 6; ++i) r.x[i] = x[i];
     r.s0 = s0; r.s1 = s1;
@@ -436,6 +500,9 @@ __global__ void __launch_bounds__(JIT) joint_init_kernel(const JointArgs a, Join
 
 constexpr int LMT = 64;          // threads per block of joint_lm_kernel
 constexpr int LM_SOLVES_PER_LANE = 3;
+constexpr int LM_PHASES = 3;
+constexpr int LM_BUDGET[LM_PHASES] = {32, 160, 0x7fffffff};   // evaluations after which a solve moves to the next phase
+constexpr int LM_PHASE_SHARE[LM_PHASES] = {1, 4, 32};         // phase p is sized for 1/share of the solves
 constexpr int LM_BLOCKS_PER_SM = 6;   // 168 registers x 64 threads
 constexpr int LM_SLOTS = 39;     // doubles per lane in shared memory: 36 point coordinates + joint direction
 
@@ -477,36 +544,52 @@ struct LaneProb {
     }
 };
 
-__global__ void __launch_bounds__(LMT, LM_BLOCKS_PER_SM) joint_lm_kernel(const JointArgs a, JointRec *recs, int total)
+// Phase `ph` of the solves.  Phase 0 claims the fresh records 0..total-1; a solve that has used LM_BUDGET[ph]
+// evaluations without terminating is suspended at its next outer-iteration boundary (its lmder state goes back into the
+// record -- 3 doubles + 3 counters, the Jacobian products are recomputed) and its index is appended to the work list of
+// phase ph+1.  Later phases claim from the list the previous phase wrote.  Re-packing keeps the lanes of a warp busy:
+// without it the few solves that run to MINPACK's maxfev = 600 each pin a warp at 1/32 utilisation (measured: 9.8 of 32
+// lanes active on average, 8.3 ms per 256 clouds; the median solve needs 12 evaluations).
+__global__ void __launch_bounds__(LMT, LM_BLOCKS_PER_SM) joint_lm_kernel(const JointArgs a, JointRec *recs, int total, int ph,
+                                                                         int budget, const int *in_list, int *out_list)
 {
     __shared__ double s_pts[LM_SLOTS * LMT];
     double *my = s_pts + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
+    int *claim = a.tail_count + 2 * ph;          // [2 ph] claim counter of this phase, [2 ph + 1] length of its work list
+    const int avail = in_list ? a.tail_count[2 * ph + 1] : total;
     LaneProb P;
     P.pts = my;
     pm::LmTick s;
     int t = -1;             // record this lane is solving
-    bool more = true;       // unclaimed records may remain
+    bool more = true;       // unclaimed work may remain
     for (;;) {
         const bool want = t < 0 && more;
         const unsigned m = __ballot_sync(0xFFFFFFFFu, want);
-        if (m) {                                              // warp-aggregated claim of the next records
+        if (m) {                                              // warp-aggregated claim of the next items
             const int leader = __ffs(m) - 1;
             int base = 0;
-            if ((int)lane == leader) base = atomicAdd(a.tail_count, __popc(m));
+            if ((int)lane == leader) base = atomicAdd(claim, __popc(m));
             base = __shfl_sync(0xFFFFFFFFu, base, leader);
             if (want) {
-                const int mine = base + __popc(m & ((1u << lane) - 1u));
-                if (mine >= total) {
+                const int item = base + __popc(m & ((1u << lane) - 1u));
+                if (item >= avail) {
                     more = false;
-                } else if (recs[mine].valid) {
+                } else {
+                    const int mine = in_list ? in_list[item] : item;
                     const JointRec &r = recs[mine];
-                    t = mine;
+                    if (r.valid) {
+                        t = mine;
 #pragma unroll 4
-                    for (int e = 0; e < 36; ++e) my[e * LMT] = r.pts[e];
-                    const double *u = a.axis_med + (size_t)(mine / a.niter) * 3;
-                    my[36 * LMT] = u[0]; my[37 * LMT] = u[1]; my[38 * LMT] = u[2];
-                    pm::lm_tick_init(s, r.x, r.fnorm0);
+                        for (int e = 0; e < 36; ++e) my[e * LMT] = r.pts[e];
+                        const double *u = a.axis_med + (size_t)(mine / a.niter) * 3;
+                        my[36 * LMT] = u[0]; my[37 * LMT] = u[1]; my[38 * LMT] = u[2];
+                        pm::lm_tick_init(s, r.x, r.fnorm);
+                        if (r.iter > 1) {                     // resume a suspended solve
+                            s.par = r.par; s.delta = r.delta; s.xnorm = r.xnorm;
+                            s.iter = r.iter; s.nfev = r.nfev; s.njev = r.njev;
+                        }
+                    }
                 }
             }
         }
@@ -521,6 +604,14 @@ __global__ void __launch_bounds__(LMT, LM_BLOCKS_PER_SM) joint_lm_kernel(const J
 #pragma unroll
                 for (int j = 0; j < 6; ++j) r.x[j] = s.x[j];
                 a.nfev[t] = s.nfev;
+                t = -1;
+            } else if (s.need_jac && s.nfev >= budget) {      // out of budget: hand the solve to the next phase
+                JointRec &r = recs[t];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) r.x[j] = s.x[j];
+                r.fnorm = s.fnorm; r.par = s.par; r.delta = s.delta; r.xnorm = s.xnorm;
+                r.iter = s.iter; r.nfev = s.nfev; r.njev = s.njev;
+                out_list[atomicAdd(a.tail_count + 2 * (ph + 1) + 1, 1)] = t;
                 t = -1;
             }
         }
@@ -581,11 +672,12 @@ __global__ void __launch_bounds__(RT) joint_verify_kernel(const JointArgs a)
 // __syncthreads publishing (cmd, x), then block_sum's two.
 struct BlockProb {
     const double *x0, *y0, *x1, *y1;
-    const unsigned char *m0, *m1;
-    int n0, n1;
+    const int *l0, *l1;          // ascending indices of the inliers of each part
+    int n0, n1;                  // list lengths
     double u[3];
     double nj;
     double *s_red;
+    double *s_cross;   // [9] joint-row cross block of J^T J (only thread 0 contributes)
     int *s_cmd;        // 0 = exit, 1 = cost, 2 = normal equations
     double *s_x;       // [6] evaluation point
 
@@ -595,14 +687,14 @@ struct BlockProb {
         r0.set(p);
         r1.set(p + 3);
         double fsq[1] = {0.0};
-        for (int i = threadIdx.x; i < n0; i += RT)
-            if (m0[i]) pm::accum_part(r0, 0, x0 + 3 * i, y0 + 3 * i, nullptr, fsq[0]);
-        for (int i = threadIdx.x; i < n1; i += RT)
-            if (m1[i]) pm::accum_part(r1, 1, x1 + 3 * i, y1 + 3 * i, nullptr, fsq[0]);
+        for (int c = threadIdx.x; c < n0; c += RJ) pm::accum_part(r0, 0, x0 + 3 * l0[c], y0 + 3 * l0[c], nullptr, fsq[0]);
+        for (int c = threadIdx.x; c < n1; c += RJ) pm::accum_part(r1, 1, x1 + 3 * l1[c], y1 + 3 * l1[c], nullptr, fsq[0]);
         if (threadIdx.x == 0) pm::accum_joint(r0, r1, u, nj, nullptr, fsq[0]);
-        block_sum<1, RT>(fsq, s_red);
+        block_sum<1, RJ>(fsq, s_red);
         s_result = fsq[0];
     }
+    // The point rows of part k only touch the diagonal block (k,k) of J^T J; the off-diagonal block comes from the joint
+    // rows alone (thread 0).  So 6 + 6 + 6 + 1 = 19 values are reduced over the block instead of all 43.
     __device__ void part_normal(const double *p, pm::Normal6 &N) const
     {
         pm::RotVec r0, r1;
@@ -610,16 +702,44 @@ struct BlockProb {
         r1.set(p + 3);
         N.zero();
         double fsq = 0.0;
-        for (int i = threadIdx.x; i < n0; i += RT)
-            if (m0[i]) pm::accum_part(r0, 0, x0 + 3 * i, y0 + 3 * i, &N, fsq);
-        for (int i = threadIdx.x; i < n1; i += RT)
-            if (m1[i]) pm::accum_part(r1, 1, x1 + 3 * i, y1 + 3 * i, &N, fsq);
-        if (threadIdx.x == 0) pm::accum_joint(r0, r1, u, nj, &N, fsq);
-        N.fsq = fsq;
-        block_sum<43, RT>(N.JtJ, s_red);     // JtJ[36], Jtf[6], fsq are contiguous in Normal6
+        for (int c = threadIdx.x; c < n0; c += RJ) pm::accum_part(r0, 0, x0 + 3 * l0[c], y0 + 3 * l0[c], &N, fsq);
+        for (int c = threadIdx.x; c < n1; c += RJ) pm::accum_part(r1, 1, x1 + 3 * l1[c], y1 + 3 * l1[c], &N, fsq);
+        if (threadIdx.x == 0) {
+            pm::accum_joint(r0, r1, u, nj, &N, fsq);
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b) s_cross[3 * a + b] = N.JtJ[a * 6 + 3 + b];
+        }
+        double v[19];
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk)
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = a; b < 3; ++b) v[6 * blk + 3 * a - (a * (a - 1)) / 2 + (b - a)] = N.JtJ[(3 * blk + a) * 6 + 3 * blk + b];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) v[12 + a] = N.Jtf[a];
+        v[18] = fsq;
+        block_sum<19, RJ>(v, s_red);          // its barriers also publish s_cross
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk)
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = a; b < 3; ++b) {
+                    const double x = v[6 * blk + 3 * a - (a * (a - 1)) / 2 + (b - a)];
+                    N.JtJ[(3 * blk + a) * 6 + 3 * blk + b] = x;
+                    N.JtJ[(3 * blk + b) * 6 + 3 * blk + a] = x;
+                }
+#pragma unroll
+        for (int a = 0; a < 6; ++a) N.Jtf[a] = v[12 + a];
+        N.fsq = v[18];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) { N.JtJ[a * 6 + 3 + b] = s_cross[3 * a + b]; N.JtJ[(3 + b) * 6 + a] = s_cross[3 * a + b]; }
     }
     mutable double s_result;
-    // ---- called by warp 0 only (through pm::lm_solve_fast) ----
+    // ---- called by warp 0 only (through pm::lm_solve_tick) ----
     __host__ __device__ double cost(const double *p) const
     {
 #ifdef __CUDA_ARCH__
@@ -668,7 +788,7 @@ __device__ int block_first_argmax_f64(const double *scores, int n, double *s_val
 {
     double bv = -1.0;
     int bi = 0x7FFFFFFF;
-    for (int h = threadIdx.x; h < n; h += RT) {
+    for (int h = threadIdx.x; h < n; h += RJ) {
         const double v = scores[h];
         if (v > bv) { bv = v; bi = h; }       // ascending h per thread: strict '>' keeps the first
     }
@@ -680,21 +800,22 @@ __device__ int block_first_argmax_f64(const double *scores, int n, double *s_val
     if ((threadIdx.x & 31) == 0) { s_val[threadIdx.x >> 5] = bv; s_idx[threadIdx.x >> 5] = bi; }
     __syncthreads();
     bv = -1.0; bi = 0x7FFFFFFF;
-    for (int w = 0; w < RT / 32; ++w)
+    for (int w = 0; w < RJ / 32; ++w)
         if (s_val[w] > bv || (s_val[w] == bv && s_idx[w] < bi)) { bv = s_val[w]; bi = s_idx[w]; }
     __syncthreads();
     return bi;
 }
 
-__global__ void __launch_bounds__(RT) joint_refit_kernel(const JointArgs a)
+__global__ void __launch_bounds__(RJ, 2) joint_refit_kernel(const JointArgs a)
 {
     extern __shared__ double s_pts[];
-    __shared__ double s_red[(RT / 32) * 43];
-    __shared__ double s_val[RT / 32];
-    __shared__ int s_idx[RT / 32];
+    __shared__ double s_red[(RJ / 32 + 1) * 19];
+    __shared__ double s_val[RJ / 32];
+    __shared__ int s_idx[RJ / 32];
     __shared__ pm::JointModel s_model;
     __shared__ int s_cmd;
     __shared__ double s_x[6];
+    __shared__ double s_cross[9];
     const int prob = blockIdx.x, tid = threadIdx.x;
     int pa, pb;
     joint_parts(prob, a.K, pa, pb);
@@ -710,13 +831,14 @@ __global__ void __launch_bounds__(RT) joint_refit_kernel(const JointArgs a)
         }
     };
     if (n0 <= 0 || n1 <= 0) {
-        for (int i = tid; i < a.N; i += RT) { g0[i] = 0; g1[i] = 0; }
+        for (int i = tid; i < a.N; i += RJ) { g0[i] = 0; g1[i] = 0; }
         if (tid == 0) { a.best[prob] = -1; a.score_out[prob] = 0.0; }
         write_nan(ANCSH_POSE_EMPTY_PART);
         return;
     }
     double *s_src0 = s_pts, *s_tgt0 = s_src0 + 3 * n0, *s_src1 = s_tgt0 + 3 * n0, *s_tgt1 = s_src1 + 3 * n1;
-    unsigned char *s_m0 = reinterpret_cast<unsigned char *>(s_tgt1 + 3 * n1), *s_m1 = s_m0 + n0;
+    int *s_l0 = reinterpret_cast<int *>(s_tgt1 + 3 * n1), *s_l1 = s_l0 + n0;           // inlier index lists
+    unsigned char *s_m0 = reinterpret_cast<unsigned char *>(s_l1 + n1), *s_m1 = s_m0 + n0;
     load_part_f64(a.part_src + (size_t)pa * a.N * 3, a.part_tgt + (size_t)pa * a.N * 3, n0, s_src0, s_tgt0);
     load_part_f64(a.part_src + (size_t)pb * a.N * 3, a.part_tgt + (size_t)pb * a.N * 3, n1, s_src1, s_tgt1);
     const double *axis = a.axis_med + (size_t)prob * 3;
@@ -730,7 +852,7 @@ __global__ void __launch_bounds__(RT) joint_refit_kernel(const JointArgs a)
     // masks of the best hypothesis and the sums needed for centring: sum S, sum T, count per part
     double acc[14];
     for (int k = 0; k < 14; ++k) acc[k] = 0.0;
-    for (int i = tid; i < a.N; i += RT) {
+    for (int i = tid; i < a.N; i += RJ) {
         unsigned char in = 0;
         if (i < n0) {
             in = is_inlier(s_model.R0, s_model.s0, s_model.t0, s_src0 + 3 * i, s_tgt0 + 3 * i, a.th2) ? 1 : 0;
@@ -746,7 +868,7 @@ __global__ void __launch_bounds__(RT) joint_refit_kernel(const JointArgs a)
         }
         g1[i] = in;
     }
-    block_sum<14, RT>(acc, s_red);
+    block_sum<14, RJ>(acc, s_red);
     const int nin0 = (int)acc[6], nin1 = (int)acc[13];
     if (nin0 == 0 || nin1 == 0) { write_nan(ANCSH_POSE_NO_INLIERS); return; }
     double mS0[3], mT0[3], mS1[3], mT1[3];
@@ -755,61 +877,48 @@ __global__ void __launch_bounds__(RT) joint_refit_kernel(const JointArgs a)
         mS1[c] = acc[7 + c] / nin1; mT1[c] = acc[10 + c] / nin1;
     }
     // scale_pts(S,T) and scale_pts(T,S) over the inliers of each part (:121-124): pairwise sums
+    block_compact_indices<RJ>(s_m0, n0, s_l0, s_idx);
+    block_compact_indices<RJ>(s_m1, n1, s_l1, s_idx);
     double pw[6];
-    for (int k = 0; k < 6; ++k) pw[k] = 0.0;
-    for (int part = 0; part < 2; ++part) {
-        const double *S = part ? s_src1 : s_src0, *T = part ? s_tgt1 : s_tgt0;
-        const unsigned char *mk = part ? s_m1 : s_m0;
-        const int n = part ? n1 : n0;
-        double ab = 0.0, aa = 0.0, bb = 0.0;
-        for (int i = tid; i < n; i += RT) {
-            if (!mk[i]) continue;
-            const double *si = S + 3 * i, *ti = T + 3 * i;
-            for (int j = i + 1; j < n; ++j) {
-                if (!mk[j]) continue;
-                const double *sj = S + 3 * j, *tj = T + 3 * j;
-                const double d0 = si[0] - sj[0], d1 = si[1] - sj[1], d2 = si[2] - sj[2];
-                const double e0 = ti[0] - tj[0], e1 = ti[1] - tj[1], e2 = ti[2] - tj[2];
-                const double A2 = d0 * d0 + d1 * d1 + d2 * d2, B2 = e0 * e0 + e1 * e1 + e2 * e2;
-                ab += sqrt(A2) * sqrt(B2); aa += A2; bb += B2;
-            }
-        }
-        pw[3 * part] = ab; pw[3 * part + 1] = aa; pw[3 * part + 2] = bb;
-    }
-    block_sum<6, RT>(pw, s_red);
+    pair_sums<RJ>(s_src0, s_tgt0, s_l0, nin0, pw[0], pw[1], pw[2]);
+    pair_sums<RJ>(s_src1, s_tgt1, s_l1, nin1, pw[3], pw[4], pw[5]);
+    block_sum<6, RJ>(pw, s_red);
     const double sc0 = 2.0 * pw[0] / (2.0 * pw[1] + 1e-6), sinv0 = 2.0 * pw[0] / (2.0 * pw[2] + 1e-6);
     const double sc1 = 2.0 * pw[3] / (2.0 * pw[4] + 1e-6), sinv1 = 2.0 * pw[3] / (2.0 * pw[5] + 1e-6);
     // centre / pre-scale in place (:126-132): x = S - mean(S); y = sinv*T - mean(sinv*T)
-    for (int i = tid; i < n0; i += RT)
+    for (int i = tid; i < n0; i += RJ)
         for (int c = 0; c < 3; ++c) { s_src0[3 * i + c] -= mS0[c]; s_tgt0[3 * i + c] = sinv0 * s_tgt0[3 * i + c] - sinv0 * mT0[c]; }
-    for (int i = tid; i < n1; i += RT)
+    for (int i = tid; i < n1; i += RJ)
         for (int c = 0; c < 3; ++c) { s_src1[3 * i + c] -= mS1[c]; s_tgt1[3 * i + c] = sinv1 * s_tgt1[3 * i + c] - sinv1 * mT1[c]; }
     __syncthreads();
     // Kabsch initialisation (:138-139)
     double M[18];
     for (int k = 0; k < 18; ++k) M[k] = 0.0;
-    for (int i = tid; i < n0; i += RT)
-        if (s_m0[i])
-            for (int p = 0; p < 3; ++p)
-                for (int q = 0; q < 3; ++q) M[3 * p + q] += s_tgt0[3 * i + p] * s_src0[3 * i + q];
-    for (int i = tid; i < n1; i += RT)
-        if (s_m1[i])
-            for (int p = 0; p < 3; ++p)
-                for (int q = 0; q < 3; ++q) M[9 + 3 * p + q] += s_tgt1[3 * i + p] * s_src1[3 * i + q];
-    block_sum<18, RT>(M, s_red);
+    for (int c = tid; c < nin0; c += RJ) {
+        const int i = s_l0[c];
+        for (int p = 0; p < 3; ++p)
+            for (int q = 0; q < 3; ++q) M[3 * p + q] += s_tgt0[3 * i + p] * s_src0[3 * i + q];
+    }
+    for (int c = tid; c < nin1; c += RJ) {
+        const int i = s_l1[c];
+        for (int p = 0; p < 3; ++p)
+            for (int q = 0; q < 3; ++q) M[9 + 3 * p + q] += s_tgt1[3 * i + p] * s_src1[3 * i + q];
+    }
+    block_sum<18, RJ>(M, s_red);
     double R0[9], R1[9], x[6];
-    pm::kabsch_rotation(M, R0);
-    pm::kabsch_rotation(M + 9, R1);
-    pm::matrix_to_rotvec(R0, x);
-    pm::matrix_to_rotvec(R1, x + 3);
     BlockProb P;
-    P.x0 = s_src0; P.y0 = s_tgt0; P.x1 = s_src1; P.y1 = s_tgt1; P.m0 = s_m0; P.m1 = s_m1; P.n0 = n0; P.n1 = n1;
+    P.x0 = s_src0; P.y0 = s_tgt0; P.x1 = s_src1; P.y1 = s_tgt1; P.l0 = s_l0; P.l1 = s_l1; P.n0 = nin0; P.n1 = nin1;
     P.u[0] = axis[0]; P.u[1] = axis[1]; P.u[2] = axis[2];
     P.nj = (double)min(nin0, nin1);
     P.s_red = s_red;
     P.s_cmd = &s_cmd;
     P.s_x = s_x;
+    P.s_cross = s_cross;
     if (tid < 32) {
+        pm::kabsch_rotation(M, R0);
+        pm::kabsch_rotation(M + 9, R1);
+        pm::matrix_to_rotvec(R0, x);
+        pm::matrix_to_rotvec(R1, x + 3);
         pm::lm_solve_tick(P, x, 1e-4, 1e-8, 1e-8, 600, 100.0);   // warp 0: LM control; all its lanes see the same sums
         P.finish();
     } else {
@@ -915,7 +1024,7 @@ extern "C" int ancsh_pose_plan(const ancsh_pose_cfg_t *cfg, int B, int N, ancsh_
     L->joint_best = take(b * (K > 1 ? K - 1 : 1) * 4);
     L->joint_nfev = take(b * (K > 1 ? K - 1 : 1) * (size_t)cfg->niter_joint * 4);
     L->joint_models = take(b * (K > 1 ? K - 1 : 1) * (size_t)cfg->niter_joint * sizeof(pm::JointModel));
-    L->joint_tail = take(256 + b * (K > 1 ? K - 1 : 1) * (size_t)cfg->niter_joint * 464);   /* work counter + JointRec[] */
+    L->joint_tail = take(256 + b * (K > 1 ? K - 1 : 1) * (size_t)cfg->niter_joint * (512 + 8));   /* counters + JointRec[] + 2 work lists */
     L->total_bytes = off;
     return ANCSH_OK;
 }
@@ -977,7 +1086,7 @@ extern "C" int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in
         single_score_kernel<<<grid, RT, smem, st>>>(a);
         ANCSH_CHECK_LAUNCH();
         STAGE_MARK();
-        size_t smem2 = smem + N;
+        size_t smem2 = smem + (size_t)5 * N;           // + inlier index list (int) + mask (byte)
         ANCSH_CUDA(cudaFuncSetAttribute(single_refit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         ANCSH_CUDA(cudaFuncSetAttribute(single_refit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         single_refit_kernel<<<B * K, RT, smem2, st>>>(a);
@@ -1005,16 +1114,24 @@ extern "C" int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in
         joint_init_kernel<<<gsolve, JIT, 0, st>>>(a, recs);
         ANCSH_CHECK_LAUNCH();
         {
-            // persistent lanes: about one lane per LM_SOLVES_PER_LANE hypotheses, so that refilling finished lanes evens
-            // out the very uneven solve lengths; never more blocks than can be resident (SM count x LM_BLOCKS_PER_SM)
+            // persistent lanes: about one lane per LM_SOLVES_PER_LANE items, so that refilling finished lanes evens out
+            // the uneven solve lengths; never more blocks than can be resident (SM count x LM_BLOCKS_PER_SM).  Later
+            // phases see a fraction of the solves (LM_PHASE_SHARE: generous upper estimates; the claim loop copes with
+            // any list length, surplus blocks exit at once).
             int dev = 0, sms = 148;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            long blocks = (nsolves + (long)LMT * LM_SOLVES_PER_LANE - 1) / ((long)LMT * LM_SOLVES_PER_LANE);
             const long cap = (long)sms * LM_BLOCKS_PER_SM;
-            blocks = blocks < 1 ? 1 : (blocks > cap ? cap : blocks);
-            joint_lm_kernel<<<(unsigned)blocks, LMT, 0, st>>>(a, recs, (int)nsolves);
-            ANCSH_CHECK_LAUNCH();
+            int *lists = (int *)(recs + nsolves);              // 2 x nsolves work-list entries behind the records
+            for (int ph = 0; ph < LM_PHASES; ++ph) {
+                const long items = ph == 0 ? nsolves : nsolves / LM_PHASE_SHARE[ph] + 1;
+                long blocks = (items + (long)LMT * LM_SOLVES_PER_LANE - 1) / ((long)LMT * LM_SOLVES_PER_LANE);
+                blocks = blocks < 1 ? 1 : (blocks > cap ? cap : blocks);
+                joint_lm_kernel<<<(unsigned)blocks, LMT, 0, st>>>(a, recs, (int)nsolves, ph, LM_BUDGET[ph],
+                                                                 ph == 0 ? nullptr : lists + (size_t)((ph - 1) & 1) * nsolves,
+                                                                 lists + (size_t)(ph & 1) * nsolves);
+                ANCSH_CHECK_LAUNCH();
+            }
         }
         joint_model_kernel<<<gsolve, JIT, 0, st>>>(a, recs);
         ANCSH_CHECK_LAUNCH();
@@ -1023,10 +1140,10 @@ extern "C" int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in
         joint_verify_kernel<<<a.nprob, RT, smem, st>>>(a);
         ANCSH_CHECK_LAUNCH();
         STAGE_MARK();
-        size_t smem2 = smem + N + 16;
+        size_t smem2 = smem + (size_t)5 * N + 16;      // + inlier index lists (int) + masks (byte)
         ANCSH_CUDA(cudaFuncSetAttribute(joint_refit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         ANCSH_CUDA(cudaFuncSetAttribute(joint_refit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        joint_refit_kernel<<<B * (K - 1), RT, smem2, st>>>(a);
+        joint_refit_kernel<<<B * (K - 1), RJ, smem2, st>>>(a);
         ANCSH_CHECK_LAUNCH();
     } else {
         STAGE_MARK();
