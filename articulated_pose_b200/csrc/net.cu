@@ -8,6 +8,7 @@
 //                 (architectures.py:89-93, lib/architecture.py:98-159, 195-208)
 //
 // Arithmetic: f32 FMA accumulation in natural k order on the CUDA cores (this file is the exact-f32 path).
+#include <stdlib.h>
 #include "common.cuh"
 #include "ops.cuh"
 #include "mlp_simt.cuh"
@@ -120,6 +121,13 @@ static int sa_launch(const SaArgs &a0, int B, cudaStream_t st)
     return ANCSH_OK;
 }
 
+// TEMPORARY development switch: ANCSH_TC_V1=1 selects the first-generation tensor-core kernels (net_tc.cu)
+static bool tc_v1()
+{
+    static const bool v = getenv("ANCSH_TC_V1") != nullptr;
+    return v;
+}
+
 // tensor-core variant of a set-abstraction stage (net_tc.cu); falls back to nothing: errors propagate
 static int sa_tc_from(const SaArgs &s, int B, cudaStream_t st)
 {
@@ -131,7 +139,7 @@ static int sa_tc_from(const SaArgs &s, int B, cudaStream_t st)
         t.L[l].bias = s.L[l].b; t.L[l].K = s.L[l].cin_pad; t.L[l].N = s.L[l].cout_pad; t.L[l].relu = s.L[l].relu;
     }
     if (s.L[2].cout != s.L[2].cout_pad) return ANCSH_ERR_INVALID_ARG;
-    return sa_tc_launch(t, B, st);
+    return tc_v1() ? sa_tc_launch(t, B, st) : sa_tc2_launch(t, B, st);
 }
 
 // ================================================================================================
@@ -608,7 +616,7 @@ extern "C" int ancsh_net_forward(const ancsh_net_t *net, int B, int N, const flo
             c.S[1].L = tc_layer(net->fp1[1]); c.S[1].dst = TC_DST_GLOBAL; c.S[1].out = l2_fp; c.S[1].ldo = net->fp1[1].cout;
             c.nsteps = 2;
             if (net->fp1[1].cout != net->fp1[1].cout_pad) return ANCSH_ERR_INVALID_ARG;
-            if ((rc = chain_tc_launch(c, (long)B * m2, st))) return rc;
+            if ((rc = (tc_v1() ? chain_tc_launch : chain_tc2_launch)(c, (long)B * m2, st))) return rc;
         } else if ((rc = fp_launch<64, false>(a, B, st))) return rc;
     }
     // fa_layer2
@@ -634,7 +642,7 @@ extern "C" int ancsh_net_forward(const ancsh_net_t *net, int B, int N, const flo
             c.S[1].L = tc_layer(net->fp2[1]); c.S[1].dst = TC_DST_GLOBAL; c.S[1].out = l1_fp; c.S[1].ldo = net->fp2[1].cout;
             c.nsteps = 2;
             if (net->fp2[1].cout != net->fp2[1].cout_pad) return ANCSH_ERR_INVALID_ARG;
-            if ((rc = chain_tc_launch(c, (long)B * m1, st))) return rc;
+            if ((rc = (tc_v1() ? chain_tc_launch : chain_tc2_launch)(c, (long)B * m1, st))) return rc;
         } else if ((rc = fp_launch<64, false>(a, B, st))) return rc;
     }
     // fa_layer3 + fc1 + heads
@@ -669,7 +677,7 @@ extern "C" int ancsh_net_forward(const ancsh_net_t *net, int B, int N, const flo
             c.S[4].dst = TC_DST_GLOBAL; c.S[4].out = raw1; c.S[4].ldo = 64;           // raw nocs_net outputs (net kept)
             c.S[7].dst = TC_DST_GLOBAL; c.S[7].out = raw2; c.S[7].ldo = 64;           // raw joint_net outputs
             c.nsteps = 8;
-            if ((rc = chain_tc_launch(c, (long)B * N, st))) return rc;
+            if ((rc = (tc_v1() ? chain_tc_launch : chain_tc2_launch)(c, (long)B * N, st))) return rc;
             const long rows = (long)B * N;
             heads_act_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(raw1, raw2, rows, net->n_parts, net->mixed_pred, *pred);
             ANCSH_CHECK_LAUNCH();

@@ -20,6 +20,7 @@ struct SaTcArgs {
 };
 
 int sa_tc_launch(const SaTcArgs &a, int B, cudaStream_t st);
+int sa_tc2_launch(const SaTcArgs &a, int B, cudaStream_t st);    // warp-specialised version (net_tc2.cu)
 
 // ---- generic row-tile chain (feature propagation / heads) ------------------------------------------------------
 enum { TC_DST_INPLACE = 0, TC_DST_GLOBAL = 1 };
@@ -52,6 +53,7 @@ __host__ __device__ inline int tc_num_acc(int K, int max_acc)
 }
 
 int chain_tc_launch(const ChainTcArgs &a, long rows_total, cudaStream_t st);
+int chain_tc2_launch(const ChainTcArgs &a, long rows_total, cudaStream_t st);   // warp-specialised version (net_tc2.cu)
 
 // ---- streaming GEMM (layers whose K or N do not fit the operand-resident chain: layer3 / group_all) -------------
 struct GemmTcArgs {

@@ -1,0 +1,468 @@
+// net_tc2.cu -- warp-specialised tcgen05 kernel for the operand-resident layer chains of the network:
+//   set abstraction (layer1 / layer2): ball-query indices -> gather(features, xyz - centroid) -> 3 x (1x1 conv + folded
+//                    BN + ReLU) -> max over nsample                                  (pointnet_util.py:94-161)
+//   point-wise chains (fa_layer1/2/3, fc1, all heads): rows from global memory, a chain of layers (:206-236,
+//                    architectures.py:89-93, architecture.py:98-159, 195-208)
+//
+// One CTA = 128 rows = 10 warps:
+//   warps 0..7  workers: gather the rows into the fp16 hi/lo operand images (tc_common.cuh), run every epilogue
+//               (TMEM -> bias + ReLU -> next operand in place / rows to HBM / max-pool).  Warps w and w+4 own the same
+//               32 TMEM lanes (rows) and split the columns in 32-wide groups.
+//   warp 8      MMA: one elected lane issues the tcgen05.mma chain of each layer as soon as the weight stage it needs has
+//               landed and releases the stage with tcgen05.commit.
+//   warp 9      producer: one elected lane streams the pre-tiled weight images from L2 into a ring of 8 KB stages with
+//               1-D bulk copies (cp.async.bulk + mbarrier complete_tx); it runs ahead across layer boundaries, so the
+//               next layer's first stages arrive while the workers are still in the epilogue.
+// The first version of these kernels (net_tc.cu) staged every 32-wide weight slice with cp.async from all threads and
+// waited for it before the MMAs (ncu: tensor pipe 17% active, the load latency of each slice fully exposed).
+//
+// "Unit" = the MMAs whose accumulators are live together followed by one epilogue: a whole in-place layer (all its
+// 128-column chunks must have read the operand before it is overwritten) or one chunk of an output layer.
+// Numerics as in net_tc.cu: hi*hi products and the cross terms hi*lo + lo*hi go to separate f32 accumulators (the tensor
+// core accumulates with truncation), long k ranges are split over several hi*hi accumulators, the epilogue adds them in
+// round-to-nearest f32.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "net_tc.cuh"
+
+namespace {
+
+constexpr int TM = 128;                 // rows per CTA
+constexpr int NWORK = 256;              // worker threads
+constexpr int NTHR = NWORK + 64;        // + MMA warp + producer warp
+constexpr int STAGE_BYTES = 8192;       // one ring stage of weights
+constexpr int MAX_STAGES = 4;
+constexpr int MAX_UNITS = 16;
+
+struct Unit {
+    const __half *Wimg;    // [K/8][hi|lo][Nfull][8] fp16
+    const float *bias;     // [Nfull], or [clouds][bias_stride] when bias_stride > 0
+    float *out;            // rows [R][ldo] (pool == 0) or pooled [groups][Nfull] (pool == 1), or NULL
+    long bias_stride;
+    int K, Nfull;
+    int n0;                // first column of chunk 0
+    int nc;                // chunk width == accumulator stride in TMEM columns (32 / 64 / 128)
+    int nchunks;
+    int G;                 // hi*hi accumulators per chunk
+    int ksl;               // k16 steps per ring stage
+    int nsl;               // ring stages (slices) per chunk
+    int relu, inplace, pool, ldo;
+};
+
+struct Chain2Args {
+    // rows from global memory: [X1 | X2]
+    const float *X1, *X2;
+    int C1, C2;
+    long rows_per_cloud;
+    // set-abstraction gather
+    const float *xyz, *points, *new_xyz;
+    const int *idx;
+    int n, m, S, C;
+    int K0;                // operand width of the first layer (multiple of 16)
+    int kmax8;             // operand image width / 8
+    int nst;               // ring stages
+    int nunits;
+    uint32_t tmem_cols;
+    Unit U[MAX_UNITS];
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(tc::smem_u32(bar))
+                 : "memory");
+}
+
+// one lane of a converged warp (ptxas then knows that the tcgen05 / bulk-copy operands below are warp-uniform)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// barrier of the workers and the MMA warp (the producer warp runs free of it)
+__device__ __forceinline__ void work_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NWORK + 32) : "memory"); }
+
+// 32 accumulator columns of this thread's row: sum of the hi*hi accumulators and the cross-term accumulator
+__device__ __forceinline__ void load_acc2(uint32_t trow, int G, int c0, float (&v)[32], int stride)
+{
+    if (G == 1) {
+        uint32_t ra[32], rb[32];
+        tc::tmem_ld32_issue(trow + c0, ra);
+        tc::tmem_ld32_issue(trow + (uint32_t)stride + c0, rb);
+        tc::tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ra[i]) + __uint_as_float(rb[i]);
+        return;
+    }
+    tc::tmem_ld32(trow + c0, v);
+    for (int g = 1; g <= G; ++g) {
+        float u[32];
+        tc::tmem_ld32(trow + (uint32_t)(g * stride) + c0, u);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += u[i];
+    }
+}
+
+// 8 consecutive k of one row -> one 16-byte piece each for the hi and lo operand images, packed conversions
+__device__ __forceinline__ void split8(const float (&v)[8], uint4 *dst_hi, uint4 *dst_lo)
+{
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 hi = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        const float2 back = __half22float2(hi);
+        const __half2 lo = __floats2half2_rn(v[2 * i] - back.x, v[2 * i + 1] - back.y);
+        h[i] = *reinterpret_cast<const uint32_t *>(&hi);
+        l[i] = *reinterpret_cast<const uint32_t *>(&lo);
+    }
+    *dst_hi = make_uint4(h[0], h[1], h[2], h[3]);
+    *dst_lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__device__ __forceinline__ void store_operand2(uint8_t *A_hi, uint8_t *A_lo, int row, int col0, const float (&v)[32])
+{
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = v[q * 8 + i];
+        const int kc = (col0 >> 3) + q;
+        split8(w, reinterpret_cast<uint4 *>(A_hi + (size_t)kc * 2048 + row * 16), reinterpret_cast<uint4 *>(A_lo + (size_t)kc * 2048 + row * 16));
+    }
+}
+
+// max over the 32 rows of a warp (values >= 0 after ReLU: unsigned order of the bit patterns == float order)
+__device__ __forceinline__ void pool_store2(float *orow, int S, int lane, const float (&v)[32])
+{
+    uint32_t keep = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const uint32_t mx = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(v[i]));
+        if (lane == i) keep = mx;
+    }
+    if (S == 32) orow[lane] = __uint_as_float(keep);
+    else atomicMax(reinterpret_cast<int *>(orow + lane), (int)keep);
+}
+
+template <bool SA>
+__global__ void __launch_bounds__(NTHR, 2) chain2_kernel(const __grid_constant__ Chain2Args a)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *A_hi = smem;
+    uint8_t *A_lo = A_hi + (size_t)a.kmax8 * 2048;
+    uint8_t *ring = A_lo + (size_t)a.kmax8 * 2048;
+    uint64_t *bar_full = reinterpret_cast<uint64_t *>(ring + (size_t)a.nst * STAGE_BYTES);
+    uint64_t *bar_empty = bar_full + MAX_STAGES;
+    uint64_t *bar_acc = bar_empty + MAX_STAGES;
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bar_acc + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) tc::tmem_alloc(s_tmem, a.tmem_cols);
+    if (tid == NWORK) {
+        for (int s = 0; s < MAX_STAGES; ++s) { tc::mbar_init(bar_full + s, 1); tc::mbar_init(bar_empty + s, 1); }
+        tc::mbar_init(bar_acc, 1);
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *s_tmem;
+    const uint32_t a_hi0 = tc::smem_u32(A_hi), a_lo0 = tc::smem_u32(A_lo), ring0 = tc::smem_u32(ring);
+
+    if (warp == NWORK / 32 + 1) {
+        // =========================== producer warp: weight slices -> ring ===========================
+        int slot = 0, round = 0;
+        for (int u = 0; u < a.nunits; ++u) {
+            const Unit &U = a.U[u];
+            const int nk16 = U.K / 16;
+            const uint32_t piece = (uint32_t)U.nc * 16u;                               // one (kc, hi|lo) block of the chunk
+            const uint8_t *src = reinterpret_cast<const uint8_t *>(U.Wimg);
+            for (int j = 0; j < U.nchunks; ++j) {
+                const int ncol0 = U.n0 + j * U.nc;
+                for (int i = 0; i < U.nsl; ++i) {
+                    if (round > 0) tc::mbar_wait(bar_empty + slot, (uint32_t)((round - 1) & 1));
+                    if (elect_one()) {
+                        const int k0 = i * U.ksl, steps = min(U.ksl, nk16 - k0);
+                        mbar_expect_tx(bar_full + slot, (uint32_t)steps * 4u * piece);
+                        const uint32_t dst = ring0 + (uint32_t)slot * STAGE_BYTES;
+                        if (U.nc == U.Nfull) {                                         // contiguous slice
+                            bulk_g2s(dst, src + (size_t)(2 * k0) * 2 * U.Nfull * 16, (uint32_t)steps * 4u * piece, bar_full + slot);
+                        } else {
+                            for (int p = 0; p < steps * 4; ++p)                        // p = kc_local * 2 + (hi|lo)
+                                bulk_g2s(dst + (uint32_t)p * piece,
+                                         src + ((size_t)(2 * k0) * 2 + p) * U.Nfull * 16 + (size_t)ncol0 * 16, piece, bar_full + slot);
+                        }
+                    }
+                    __syncwarp();
+                    if (++slot == a.nst) { slot = 0; ++round; }
+                }
+            }
+        }
+    } else if (warp == NWORK / 32) {
+        // =========================== MMA warp ===========================
+        int slot = 0, round = 0;
+        work_sync();                                          // operand of unit 0 gathered
+        for (int u = 0; u < a.nunits; ++u) {
+            const Unit &U = a.U[u];
+            const int nk16 = U.K / 16;
+            const uint32_t idesc = tc::instr_desc_f16(TM, U.nc);
+            const uint32_t sslab = 2u * (uint32_t)U.nc * 16u;
+            const uint64_t ah0 = tc::smem_desc(a_hi0, 2048u, 128u), al0 = tc::smem_desc(a_lo0, 2048u, 128u);
+            tc::fence_after_sync();
+            for (int j = 0; j < U.nchunks; ++j) {
+                const uint32_t tbase = tmem + (uint32_t)(j * (U.G + 1) * U.nc);
+                uint32_t startedA = 0, startedB = 0;
+                for (int i = 0; i < U.nsl; ++i) {
+                    tc::mbar_wait(bar_full + slot, (uint32_t)(round & 1));
+                    if (elect_one()) {
+                        const int k0 = i * U.ksl, steps = min(U.ksl, nk16 - k0);
+                        // descriptors differ only in the start-address field (address >> 4): add offsets to a base
+                        const uint64_t bh0 = tc::smem_desc(ring0 + (uint32_t)slot * STAGE_BYTES, sslab, 128u);
+                        for (int s = 0; s < steps; ++s) {
+                            const int kk = k0 + s;
+                            const uint64_t ah = ah0 + (uint64_t)(kk * 256), al = al0 + (uint64_t)(kk * 256);   // 2 * 2048 / 16
+                            const uint64_t bh = bh0 + (uint64_t)(s * (int)(sslab >> 3)), bl = bh + (uint64_t)U.nc;
+                            const int g = U.G == 1 ? 0 : kk * U.G / nk16;
+                            tc::mma_f16(tbase + (uint32_t)(g * U.nc), ah, bh, idesc, (startedA >> g) & 1u);
+                            startedA |= 1u << g;
+                            tc::mma_f16(tbase + (uint32_t)(U.G * U.nc), ah, bl, idesc, startedB);
+                            startedB = 1u;
+                            tc::mma_f16(tbase + (uint32_t)(U.G * U.nc), al, bh, idesc, 1u);
+                        }
+                        tc::mma_commit(bar_empty + slot);     // the stage may be refilled once these MMAs have read it
+                    }
+                    __syncwarp();
+                    if (++slot == a.nst) { slot = 0; ++round; }
+                }
+            }
+            if (elect_one()) tc::mma_commit(bar_acc);         // accumulators of the unit complete
+            __syncwarp();
+            tc::fence_before_sync();
+            work_sync();                                      // epilogue done: operand rewritten, TMEM drained
+        }
+    } else {
+        // =========================== workers ===========================
+        const int r = tid & (TM - 1), h = tid >> 7, wq = warp & 3;
+        long R;                 // global row (rows mode) / row inside the cloud (SA mode)
+        int b = 0;
+        if (SA) {
+            b = blockIdx.y;
+            R = (long)blockIdx.x * TM + r;
+            const int g = (int)(R / a.S);
+            const int id = a.idx ? __ldg(a.idx + (size_t)b * a.m * a.S + R) : (int)R;
+            const float *prow = a.points ? a.points + ((size_t)b * a.n + id) * a.C : nullptr;
+            float rel[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float v = __ldg(a.xyz + ((size_t)b * a.n + id) * 3 + c);
+                if (a.new_xyz) v = __fsub_rn(v, __ldg(a.new_xyz + ((size_t)b * a.m + g) * 3 + c));
+                rel[c] = v;
+            }
+            // channel order [features(C), xyz(3), zero pad] (pointnet_util.py:52-57)
+            for (int kc = h; kc < a.K0 / 8; kc += 2) {
+                float v[8];
+                if (kc * 8 + 8 <= a.C) {
+                    const float4 p0 = ldg4(prow + kc * 8), p1 = ldg4(prow + kc * 8 + 4);
+                    v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int c = kc * 8 + i;
+                        v[i] = c < a.C ? __ldg(prow + c) : (c < a.C + 3 ? rel[c - a.C] : 0.f);
+                    }
+                }
+                split8(v, reinterpret_cast<uint4 *>(A_hi + (size_t)kc * 2048 + r * 16), reinterpret_cast<uint4 *>(A_lo + (size_t)kc * 2048 + r * 16));
+            }
+        } else {
+            R = (long)blockIdx.x * TM + r;
+            const float *r1 = a.X1 + (size_t)R * a.C1;
+            const float *r2 = a.X2 ? a.X2 + (size_t)R * a.C2 : nullptr;
+            for (int kc = h; kc < a.K0 / 8; kc += 2) {
+                float v[8];
+                if (kc * 8 + 8 <= a.C1) {
+                    const float4 p0 = ldg4(r1 + kc * 8), p1 = ldg4(r1 + kc * 8 + 4);
+                    v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
+                } else if (r2 && (a.C2 & 7) == 0 && (a.C1 & 7) == 0 && kc * 8 >= a.C1 && kc * 8 + 8 <= a.C1 + a.C2) {
+                    const float4 p0 = ldg4(r2 + (kc * 8 - a.C1)), p1 = ldg4(r2 + (kc * 8 - a.C1) + 4);
+                    v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int c = kc * 8 + i;
+                        v[i] = c < a.C1 ? __ldg(r1 + c) : (r2 && c < a.C1 + a.C2 ? __ldg(r2 + (c - a.C1)) : 0.f);
+                    }
+                }
+                split8(v, reinterpret_cast<uint4 *>(A_hi + (size_t)kc * 2048 + r * 16), reinterpret_cast<uint4 *>(A_lo + (size_t)kc * 2048 + r * 16));
+            }
+        }
+        tc::fence_proxy_async();
+        work_sync();                                          // operand of unit 0 gathered
+        const uint32_t trow = tmem + ((uint32_t)(wq * 32) << 16);
+        for (int u = 0; u < a.nunits; ++u) {
+            const Unit &U = a.U[u];
+            tc::mbar_wait(bar_acc, (uint32_t)(u & 1));
+            tc::fence_after_sync();
+            const float *bias = U.bias_stride ? U.bias + (size_t)(R / a.rows_per_cloud) * U.bias_stride : U.bias;
+            const int groups = U.nc >> 5;                     // 32-column groups per chunk
+            for (int j = 0; j < U.nchunks; ++j) {
+                for (int q = 0; q < groups; ++q) {
+                    if (((j * groups + q) & 1) != h) continue;        // the two halves alternate 32-column groups
+                    const int c0 = q * 32;
+                    float v[32];
+                    load_acc2(trow + (uint32_t)(j * (U.G + 1) * U.nc), U.G, c0, v, U.nc);
+                    const int col = U.n0 + j * U.nc + c0;
+                    const float4 *b4 = reinterpret_cast<const float4 *>(bias + col);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 bb = __ldg(b4 + i);
+                        v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+                    }
+                    if (U.relu) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                    }
+                    if (U.pool) {
+                        const long g = ((long)blockIdx.x * TM + wq * 32) / a.S;
+                        pool_store2(U.out + ((size_t)b * a.m + g) * U.Nfull + col, a.S, lane, v);
+                    } else if (U.out) {
+                        float4 *o = reinterpret_cast<float4 *>(U.out + (size_t)R * U.ldo + col);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    }
+                    if (U.inplace) store_operand2(A_hi, A_lo, r, col, v);
+                }
+            }
+            tc::fence_proxy_async();
+            tc::fence_before_sync();
+            work_sync();
+        }
+        if (warp == 0) tc::tmem_dealloc(tmem, a.tmem_cols);
+    }
+}
+
+// ---- host: unit list + launch ------------------------------------------------------------------------------------
+struct LayerSpec {
+    TcLayer L;
+    int inplace;       // output becomes the next operand
+    int pool;          // max-pool over the group (set abstraction's last layer)
+    float *out;
+    int ldo;
+    const float *bias_override;
+    long bias_stride;
+};
+
+int build_units(Chain2Args &a, const LayerSpec *spec, int nspec, size_t *smem_out)
+{
+    int kmax = a.K0;
+    for (int i = 0; i < nspec; ++i) {
+        const TcLayer &L = spec[i].L;
+        if (!L.Wimg || L.K % 16 != 0 || L.N % 32 != 0 || L.N > 256) return ANCSH_ERR_INVALID_ARG;
+        if (i > 0 && spec[i - 1].inplace && L.K != spec[i - 1].L.N) return ANCSH_ERR_INVALID_ARG;
+        kmax = L.K > kmax ? L.K : kmax;
+        if (spec[i].inplace && L.N > kmax) kmax = L.N;
+    }
+    a.kmax8 = kmax / 8;
+    const size_t opbytes = (size_t)2 * a.kmax8 * 2048;
+    const size_t tail = (2 * MAX_STAGES + 1) * sizeof(uint64_t) + 16;
+    size_t limit = 113 * 1024;                                 // two CTAs per SM when the operand is small enough
+    a.tmem_cols = 256;
+    a.nst = MAX_STAGES;
+    if (opbytes + (size_t)MAX_STAGES * STAGE_BYTES + tail > limit) {
+        limit = 227 * 1024;
+        a.tmem_cols = 512;
+        while (a.nst > 2 && opbytes + (size_t)a.nst * STAGE_BYTES + tail > limit) --a.nst;
+    }
+    const size_t smem = opbytes + (size_t)a.nst * STAGE_BYTES + tail;
+    if (smem > limit) return ANCSH_ERR_UNSUPPORTED;
+    a.nunits = 0;
+    for (int i = 0; i < nspec; ++i) {
+        const TcLayer &L = spec[i].L;
+        const int nc = L.N >= 128 ? 128 : L.N;                 // 32 / 64 / 128
+        if (L.N % nc != 0) return ANCSH_ERR_UNSUPPORTED;
+        const int nch = L.N / nc;
+        const int together = spec[i].inplace ? nch : 1;        // chunks whose accumulators are live together
+        if (together * 2 * nc > (int)a.tmem_cols) {            // e.g. a 256-wide in-place layer needs all 512 columns
+            if (limit == 113 * 1024) { a.tmem_cols = 512; }
+            if (together * 2 * nc > (int)a.tmem_cols) return ANCSH_ERR_UNSUPPORTED;
+        }
+        for (int j = 0; j < nch; j += together) {
+            if (a.nunits >= MAX_UNITS) return ANCSH_ERR_UNSUPPORTED;
+            Unit &U = a.U[a.nunits++];
+            U.Wimg = L.Wimg;
+            U.bias = spec[i].bias_override ? spec[i].bias_override : L.bias;
+            U.bias_stride = spec[i].bias_override ? spec[i].bias_stride : 0;
+            U.out = spec[i].out; U.ldo = spec[i].ldo;
+            U.K = L.K; U.Nfull = L.N; U.n0 = j * nc; U.nc = nc; U.nchunks = together;
+            U.G = 1;                                           // filled below (needs the final tmem_cols)
+            U.ksl = STAGE_BYTES / (64 * nc);
+            U.nsl = (L.K / 16 + U.ksl - 1) / U.ksl;
+            U.relu = L.relu; U.inplace = spec[i].inplace; U.pool = spec[i].pool;
+        }
+    }
+    for (int u = 0; u < a.nunits; ++u) {
+        Unit &U = a.U[u];
+        U.G = tc_num_acc(U.K, (int)a.tmem_cols / (U.nc * U.nchunks) - 1);
+    }
+    *smem_out = smem;
+    return ANCSH_OK;
+}
+
+template <bool SA>
+int launch_chain2(const Chain2Args &a, dim3 grid, size_t smem, cudaStream_t st)
+{
+    ANCSH_CUDA(cudaFuncSetAttribute(chain2_kernel<SA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ANCSH_CUDA(cudaFuncSetAttribute(chain2_kernel<SA>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    chain2_kernel<SA><<<grid, NTHR, smem, st>>>(a);
+    ANCSH_CHECK_LAUNCH();
+    return ANCSH_OK;
+}
+
+}  // namespace
+
+int sa_tc2_launch(const SaTcArgs &s, int B, cudaStream_t st)
+{
+    const long rows = (long)s.m * s.S;
+    if (rows % TM != 0 || s.S % 32 != 0 || s.C % 8 != 0) return ANCSH_ERR_UNSUPPORTED;
+    if (s.L[0].K < s.C + 3 || !s.L[2].relu) return ANCSH_ERR_INVALID_ARG;
+    Chain2Args a{};
+    a.xyz = s.xyz; a.points = s.points; a.new_xyz = s.new_xyz; a.idx = s.idx;
+    a.n = s.n; a.m = s.m; a.S = s.S; a.C = s.C;
+    a.K0 = s.L[0].K;
+    a.rows_per_cloud = 1;
+    LayerSpec spec[3] = {};
+    for (int l = 0; l < 3; ++l) { spec[l].L = s.L[l]; spec[l].inplace = l < 2; }
+    spec[2].pool = 1; spec[2].out = s.out;
+    size_t smem = 0;
+    int rc = build_units(a, spec, 3, &smem);
+    if (rc) return rc;
+    if (s.S != 32) ANCSH_CUDA(cudaMemsetAsync(s.out, 0, (size_t)B * s.m * s.L[2].N * sizeof(float), st));
+    return launch_chain2<true>(a, dim3((unsigned)(rows / TM), B), smem, st);
+}
+
+int chain_tc2_launch(const ChainTcArgs &c, long rows_total, cudaStream_t st)
+{
+    if (rows_total % TM != 0 || c.C1 % 8 != 0 || c.nsteps < 1 || c.nsteps > 8) return ANCSH_ERR_UNSUPPORTED;
+    if (c.S[0].L.K < c.C1 + (c.X2 ? c.C2 : 0)) return ANCSH_ERR_INVALID_ARG;
+    Chain2Args a{};
+    a.X1 = c.X1; a.X2 = c.X2; a.C1 = c.C1; a.C2 = c.C2;
+    a.rows_per_cloud = c.rows_per_cloud > 0 ? c.rows_per_cloud : 1;
+    a.K0 = c.S[0].L.K;
+    LayerSpec spec[8] = {};
+    for (int i = 0; i < c.nsteps; ++i) {
+        spec[i].L = c.S[i].L;
+        spec[i].inplace = c.S[i].dst == TC_DST_INPLACE;
+        spec[i].out = c.S[i].out; spec[i].ldo = c.S[i].ldo;
+        if (c.S[i].dst == TC_DST_GLOBAL && !c.S[i].out) return ANCSH_ERR_INVALID_ARG;
+        if (c.S[i].out && (c.S[i].ldo < c.S[i].L.N || c.S[i].ldo % 4 != 0)) return ANCSH_ERR_INVALID_ARG;
+    }
+    if (c.bias0) { spec[0].bias_override = c.bias0; spec[0].bias_stride = c.bias0_stride; }
+    size_t smem = 0;
+    int rc = build_units(a, spec, c.nsteps, &smem);
+    if (rc) return rc;
+    return launch_chain2<false>(a, dim3((unsigned)(rows_total / TM)), smem, st);
+}

@@ -1125,7 +1125,8 @@ extern "C" int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in
             int *lists = (int *)(recs + nsolves);              // 2 x nsolves work-list entries behind the records
             for (int ph = 0; ph < LM_PHASES; ++ph) {
                 const long items = ph == 0 ? nsolves : nsolves / LM_PHASE_SHARE[ph] + 1;
-                long blocks = (items + (long)LMT * LM_SOLVES_PER_LANE - 1) / ((long)LMT * LM_SOLVES_PER_LANE);
+                const long per_lane = ph == 0 ? LM_SOLVES_PER_LANE : 1;     // later phases: few, long solves -> one lane each
+                long blocks = (items + (long)LMT * per_lane - 1) / ((long)LMT * per_lane);
                 blocks = blocks < 1 ? 1 : (blocks > cap ? cap : blocks);
                 joint_lm_kernel<<<(unsigned)blocks, LMT, 0, st>>>(a, recs, (int)nsolves, ph, LM_BUDGET[ph],
                                                                  ph == 0 ? nullptr : lists + (size_t)((ph - 1) & 1) * nsolves,
