@@ -82,6 +82,9 @@ ancsh_three_interpolate = _sig("ancsh_three_interpolate", [c_int, c_int, c_int, 
 ancsh_net_plan = _sig("ancsh_net_plan", [ctypes.POINTER(Net), c_int, c_int, ctypes.POINTER(WsLayout)])
 ancsh_net_forward = _sig("ancsh_net_forward", [ctypes.POINTER(Net), c_int, c_int, vp, vp, c_size_t,
                                                ctypes.POINTER(Pred), ctypes.POINTER(vp), vp])
+ancsh_net_forward_shared = _sig("ancsh_net_forward_shared", [ctypes.POINTER(Net), c_int, c_int, vp, vp, c_size_t,
+                                                             ctypes.POINTER(Net), vp, ctypes.POINTER(Pred),
+                                                             ctypes.POINTER(vp), vp])
 ancsh_event_create = _sig("ancsh_event_create", [ctypes.POINTER(vp)])
 ancsh_event_record = _sig("ancsh_event_record", [vp, vp])
 ancsh_event_elapsed_ms = _sig("ancsh_event_elapsed_ms", [vp, vp, ctypes.POINTER(ctypes.c_float)])

@@ -134,6 +134,7 @@ static int sa_tc_from(const SaArgs &s, int B, cudaStream_t st)
     SaTcArgs t{};
     t.xyz = s.xyz; t.points = s.points; t.new_xyz = s.new_xyz; t.idx = s.idx; t.out = s.out;
     t.n = s.n; t.m = s.m; t.S = s.S; t.C = s.C;
+    t.W0 = s.L[0].W;
     for (int l = 0; l < 3; ++l) {
         t.L[l].Wimg = reinterpret_cast<const __half *>(s.L[l].W_tc);
         t.L[l].bias = s.L[l].b; t.L[l].K = s.L[l].cin_pad; t.L[l].N = s.L[l].cout_pad; t.L[l].relu = s.L[l].relu;
@@ -514,9 +515,11 @@ extern "C" int ancsh_net_plan(const ancsh_net_t *net, int B, int N, ancsh_ws_lay
     return ANCSH_OK;
 }
 
-extern "C" int ancsh_net_forward(const ancsh_net_t *net, int B, int N, const float *P, void *workspace,
-                                 size_t workspace_bytes, const ancsh_pred_t *pred, void *const *stage_events,
-                                 void *stream)
+// geo_net / geo_ws != NULL: sampling and grouping geometry (FPS indices, level xyz, ball-query indices) is read from the
+// workspace of a forward of `geo_net` over the same P instead of being recomputed (ancsh_net_forward_shared).
+static int net_forward_impl(const ancsh_net_t *net, int B, int N, const float *P, void *workspace, size_t workspace_bytes,
+                            const ancsh_net_t *geo_net, const void *geo_ws, const ancsh_pred_t *pred,
+                            void *const *stage_events, void *stream)
 {
     if (!net || !P || !workspace || !pred) return ANCSH_ERR_INVALID_ARG;
     if (B > 65535) return ANCSH_ERR_UNSUPPORTED;
@@ -526,10 +529,20 @@ extern "C" int ancsh_net_forward(const ancsh_net_t *net, int B, int N, const flo
     if (workspace_bytes < L.total_bytes) return ANCSH_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     char *ws = (char *)workspace;
-    int *fps1 = (int *)(ws + L.fps_idx1), *fps2 = (int *)(ws + L.fps_idx2);
-    float *l1_xyz = (float *)(ws + L.l1_xyz), *l2_xyz = (float *)(ws + L.l2_xyz);
-    int *bidx1 = (int *)(ws + L.ball_idx1), *bcnt1 = (int *)(ws + L.ball_cnt1);
-    int *bidx2 = (int *)(ws + L.ball_idx2), *bcnt2 = (int *)(ws + L.ball_cnt2);
+    char *gws = ws;                       // where the geometry lives
+    ancsh_ws_layout_t GL = L;
+    const bool shared = geo_net != nullptr && geo_ws != nullptr;
+    if (shared) {
+        if (geo_net->npoint1 != net->npoint1 || geo_net->npoint2 != net->npoint2 || geo_net->nsample1 != net->nsample1 ||
+            geo_net->nsample2 != net->nsample2 || geo_net->radius1 != net->radius1 || geo_net->radius2 != net->radius2)
+            return ANCSH_ERR_INVALID_ARG;
+        if ((rc = ancsh_net_plan(geo_net, B, N, &GL)) != ANCSH_OK) return rc;
+        gws = (char *)const_cast<void *>(geo_ws);
+    }
+    int *fps1 = (int *)(gws + GL.fps_idx1), *fps2 = (int *)(gws + GL.fps_idx2);
+    float *l1_xyz = (float *)(gws + GL.l1_xyz), *l2_xyz = (float *)(gws + GL.l2_xyz);
+    int *bidx1 = (int *)(gws + GL.ball_idx1), *bcnt1 = (int *)(gws + GL.ball_cnt1);
+    int *bidx2 = (int *)(gws + GL.ball_idx2), *bcnt2 = (int *)(gws + GL.ball_cnt2);
     float *l1_points = (float *)(ws + L.l1_points), *l2_points = (float *)(ws + L.l2_points);
     float *l3_points = (float *)(ws + L.l3_points), *fp1_bias = (float *)(ws + L.fp1_bias);
     float *l2_fp = (float *)(ws + L.l2_points_fp), *l1_fp = (float *)(ws + L.l1_points_fp);
@@ -543,13 +556,13 @@ extern "C" int ancsh_net_forward(const ancsh_net_t *net, int B, int N, const flo
 
     // sampling (pointnet_util.py:47) -- level 2 samples the level-1 centroids
     STAGE_MARK();
-    if ((rc = ancsh_fps_impl(B, N, m1, P, fps1, l1_xyz, st))) return rc;
+    if (!shared && (rc = ancsh_fps_impl(B, N, m1, P, fps1, l1_xyz, st))) return rc;
     STAGE_MARK();
-    if ((rc = ancsh_fps_impl(B, m1, m2, l1_xyz, fps2, l2_xyz, st))) return rc;
+    if (!shared && (rc = ancsh_fps_impl(B, m1, m2, l1_xyz, fps2, l2_xyz, st))) return rc;
     STAGE_MARK();
 
     // layer1
-    if ((rc = ancsh_ball_query_impl(B, N, m1, net->radius1, net->nsample1, P, l1_xyz, bidx1, bcnt1, st))) return rc;
+    if (!shared && (rc = ancsh_ball_query_impl(B, N, m1, net->radius1, net->nsample1, P, l1_xyz, bidx1, bcnt1, st))) return rc;
     STAGE_MARK();
     {
         SaArgs a{};
@@ -560,7 +573,7 @@ extern "C" int ancsh_net_forward(const ancsh_net_t *net, int B, int N, const flo
     }
     // layer2
     STAGE_MARK();
-    if ((rc = ancsh_ball_query_impl(B, m1, m2, net->radius2, net->nsample2, l1_xyz, l2_xyz, bidx2, bcnt2, st))) return rc;
+    if (!shared && (rc = ancsh_ball_query_impl(B, m1, m2, net->radius2, net->nsample2, l1_xyz, l2_xyz, bidx2, bcnt2, st))) return rc;
     STAGE_MARK();
     {
         SaArgs a{};
@@ -686,6 +699,23 @@ extern "C" int ancsh_net_forward(const ancsh_net_t *net, int B, int N, const flo
     STAGE_MARK();
 #undef STAGE_MARK
     return ANCSH_OK;
+}
+
+extern "C" int ancsh_net_forward(const ancsh_net_t *net, int B, int N, const float *P, void *workspace,
+                                 size_t workspace_bytes, const ancsh_pred_t *pred, void *const *stage_events,
+                                 void *stream)
+{
+    return net_forward_impl(net, B, N, P, workspace, workspace_bytes, nullptr, nullptr, pred, stage_events, stream);
+}
+
+extern "C" int ancsh_net_forward_shared(const ancsh_net_t *net, int B, int N, const float *P, void *workspace,
+                                        size_t workspace_bytes, const ancsh_net_t *geometry_net,
+                                        const void *geometry_workspace, const ancsh_pred_t *pred,
+                                        void *const *stage_events, void *stream)
+{
+    if (!geometry_net || !geometry_workspace) return ANCSH_ERR_INVALID_ARG;
+    return net_forward_impl(net, B, N, P, workspace, workspace_bytes, geometry_net, geometry_workspace, pred, stage_events,
+                            stream);
 }
 
 extern "C" int ancsh_event_create(void **event_out)

@@ -15,6 +15,8 @@ struct SaTcArgs {
     float *out;
     TcLayer L[3];
     int n, m, S, C;
+    const float *W0;             // optional f32 [K0][N0] weights of L[0] (ancsh_layer_t::W): with C == 0 (xyz-only input) the
+                                 // warp-specialised kernel evaluates L[0] on the CUDA cores inside the gather
     int kmax8, nch;              // filled by the launcher: operand width / 8, output chunk width
     uint32_t tmem_cols;
 };

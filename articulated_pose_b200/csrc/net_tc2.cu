@@ -58,7 +58,9 @@ struct Chain2Args {
     const float *xyz, *points, *new_xyz;
     const int *idx;
     int n, m, S, C;
-    int K0;                // operand width of the first layer (multiple of 16)
+    const float *W0, *b0;  // xyz-only set abstraction: f32 weights [>=3][N0] / bias of the first conv, evaluated in the gather
+    int N0, relu0;         // (N0 == 0: disabled)
+    int K0;                // operand width of the first tensor-core layer (multiple of 16)
     int kmax8;             // operand image width / 8
     int nst;               // ring stages
     int nunits;
@@ -263,6 +265,29 @@ __global__ void __launch_bounds__(NTHR, 2) chain2_kernel(const __grid_constant__
                 if (a.new_xyz) v = __fsub_rn(v, __ldg(a.new_xyz + ((size_t)b * a.m + g) * 3 + c));
                 rel[c] = v;
             }
+            if (a.N0) {
+                // xyz-only input (layer1): the first conv has 3 input channels -- 3 FMAs per output on the CUDA cores in
+                // exact f32 instead of a 16-deep tensor-core step plus a whole epilogue round trip through TMEM
+                for (int c0 = h * 32; c0 < a.N0; c0 += 64) {
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 bb = __ldg(reinterpret_cast<const float4 *>(a.b0 + c0) + i);
+                        const float4 w0 = __ldg(reinterpret_cast<const float4 *>(a.W0 + c0) + i);
+                        const float4 w1 = __ldg(reinterpret_cast<const float4 *>(a.W0 + a.N0 + c0) + i);
+                        const float4 w2 = __ldg(reinterpret_cast<const float4 *>(a.W0 + 2 * a.N0 + c0) + i);
+                        v[4 * i] = fmaf(rel[2], w2.x, fmaf(rel[1], w1.x, fmaf(rel[0], w0.x, bb.x)));
+                        v[4 * i + 1] = fmaf(rel[2], w2.y, fmaf(rel[1], w1.y, fmaf(rel[0], w0.y, bb.y)));
+                        v[4 * i + 2] = fmaf(rel[2], w2.z, fmaf(rel[1], w1.z, fmaf(rel[0], w0.z, bb.z)));
+                        v[4 * i + 3] = fmaf(rel[2], w2.w, fmaf(rel[1], w1.w, fmaf(rel[0], w0.w, bb.w)));
+                    }
+                    if (a.relu0) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                    }
+                    store_operand2(A_hi, A_lo, r, c0, v);
+                }
+            } else
             // channel order [features(C), xyz(3), zero pad] (pointnet_util.py:52-57)
             for (int kc = h; kc < a.K0 / 8; kc += 2) {
                 float v[8];
@@ -432,13 +457,18 @@ int sa_tc2_launch(const SaTcArgs &s, int B, cudaStream_t st)
     Chain2Args a{};
     a.xyz = s.xyz; a.points = s.points; a.new_xyz = s.new_xyz; a.idx = s.idx;
     a.n = s.n; a.m = s.m; a.S = s.S; a.C = s.C;
-    a.K0 = s.L[0].K;
     a.rows_per_cloud = 1;
     LayerSpec spec[3] = {};
-    for (int l = 0; l < 3; ++l) { spec[l].L = s.L[l]; spec[l].inplace = l < 2; }
-    spec[2].pool = 1; spec[2].out = s.out;
+    int first = 0;
+    if (s.C == 0 && s.W0 && s.L[0].N % 64 == 0 && s.L[1].K == s.L[0].N) {   // xyz-only: first conv in the gather
+        a.W0 = s.W0; a.b0 = s.L[0].bias; a.N0 = s.L[0].N; a.relu0 = s.L[0].relu;
+        first = 1;
+    }
+    a.K0 = first ? s.L[0].N : s.L[0].K;
+    for (int l = first; l < 3; ++l) { spec[l - first].L = s.L[l]; spec[l - first].inplace = l < 2; }
+    spec[2 - first].pool = 1; spec[2 - first].out = s.out;
     size_t smem = 0;
-    int rc = build_units(a, spec, 3, &smem);
+    int rc = build_units(a, spec, 3 - first, &smem);
     if (rc) return rc;
     if (s.S != 32) ANCSH_CUDA(cudaMemsetAsync(s.out, 0, (size_t)B * s.m * s.L[2].N * sizeof(float), st));
     return launch_chain2<true>(a, dim3((unsigned)(rows / TM), B), smem, st);

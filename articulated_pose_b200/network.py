@@ -109,9 +109,11 @@ class AncshNet:
             out[k] = torch.empty((B, N, _PRED_WIDTH[k](K)), dtype=torch.float32, device=self.device)
         return out
 
-    def forward_device(self, P, out=None, stage_events=None, net_out=None):
+    def forward_device(self, P, out=None, stage_events=None, net_out=None, geometry_from=None):
         """P: CUDA f32 (B,N,3).  Launches on torch's current stream; returns dict of CUDA tensors.
-        stage_events: optional _lib.EventList(len(_lib.NET_STAGES)+1) recorded around each stage."""
+        stage_events: optional _lib.EventList(len(_lib.NET_STAGES)+1) recorded around each stage.
+        geometry_from: another AncshNet whose forward over the same P was enqueued before on the same stream: its
+        FPS / ball-query results are reused instead of being recomputed (ancsh_net_forward_shared)."""
         if P.dtype != torch.float32 or P.dim() != 3 or P.shape[2] != 3 or not P.is_cuda:
             raise ValueError("P must be a CUDA float32 tensor of shape (B,N,3)")
         P = P.contiguous()
@@ -123,9 +125,17 @@ class AncshNet:
         for k in _lib.PRED_FIELDS:
             setattr(pred, k, out[k].data_ptr() if k in out else None)
         pred.net = net_out.data_ptr() if net_out is not None else None     # optional (B,N,128) trunk feature
-        rc = _lib.ancsh_net_forward(ctypes.byref(self._net), B, N, P.data_ptr(), ws.data_ptr(), lay.total_bytes,
-                                    ctypes.byref(pred), stage_events.arr if stage_events is not None else None,
-                                    torch.cuda.current_stream().cuda_stream)
+        ev = stage_events.arr if stage_events is not None else None
+        if geometry_from is not None:
+            gws, _, gB = geometry_from.last_workspace
+            if gB != B:
+                raise ValueError("geometry_from ran on a different batch size")
+            rc = _lib.ancsh_net_forward_shared(ctypes.byref(self._net), B, N, P.data_ptr(), ws.data_ptr(), lay.total_bytes,
+                                               ctypes.byref(geometry_from._net), gws.data_ptr(), ctypes.byref(pred), ev,
+                                               torch.cuda.current_stream().cuda_stream)
+        else:
+            rc = _lib.ancsh_net_forward(ctypes.byref(self._net), B, N, P.data_ptr(), ws.data_ptr(), lay.total_bytes,
+                                        ctypes.byref(pred), ev, torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "ancsh_net_forward")
         self.last_workspace = (ws, lay, B)
         return out

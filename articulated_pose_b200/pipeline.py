@@ -55,7 +55,7 @@ class AncshPipeline:
         pred = self.net.forward_device(P, buf["pred"], stage_events=net_events)
         src = pred
         if self.net_npcs is not None:
-            src = self.net_npcs.forward_device(P, buf["pred_b"], stage_events=net_b_events)
+            src = self.net_npcs.forward_device(P, buf["pred_b"], stage_events=net_b_events, geometry_from=self.net)
         return self.pose.solve_device(P, src["nocs_per_point"], src["W"], pred["joint_axis_per_point"], joint_cls,
                                       out=buf["pose"], stage_events=pose_events)
 
@@ -89,7 +89,7 @@ class AncshPipeline:
         pred = self.net.forward_device(P, sl["pred"], stage_events=net_events)
         src = pred
         if self.net_npcs is not None:
-            src = self.net_npcs.forward_device(P, sl["pred_b"], stage_events=net_b_events)
+            src = self.net_npcs.forward_device(P, sl["pred_b"], stage_events=net_b_events, geometry_from=self.net)
         sl["fwd_done"].record(main)
         with torch.cuda.stream(ps):
             ps.wait_event(sl["fwd_done"])

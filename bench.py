@@ -385,7 +385,8 @@ def main():
             "clocks": clocks,
             "e2e": {"value": world * B * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
-            "gpu_launches": (16 * n_fwd + (8 if full else 0)) * args.steps,   # kernels per forward / per pose stage (profiles/*launches*)
+            "gpu_launches": (16 + (12 if n_fwd == 2 else 0) + (8 if full else 0)) * args.steps,   # kernels per forward (the second
+            # network reuses the first one's FPS / ball-query launches) / per pose stage (profiles/*launches*)
             "roofline": roofline}
 
     if not args.no_cpu_baseline:

@@ -161,6 +161,16 @@ int ancsh_net_forward(const ancsh_net_t *net, int B, int N, const float *P, void
                       const ancsh_pred_t *pred, void *const *stage_events, void *stream);
 
 /* Timing-enabled CUDA events for callers that have no CUDA runtime binding of their own. */
+/* Second network over the SAME cloud batch (the reference's pose stage reads NOCS + segmentation from the NPCS baseline
+ * network and the joint axis from the ANCSH network, parallel_ancsh_pose.py:197,232-236; both run
+ * farthest_point_sample / query_ball_point on the same xyz, pointnet_util.py:47-49): the sampling indices, level
+ * coordinates and ball-query indices are read from `geometry_workspace`, the workspace of a completed or enqueued
+ * ancsh_net_forward of `geometry_net` on the same stream, instead of being recomputed.  The two networks must agree
+ * in npoint / radius / nsample (ANCSH_ERR_INVALID_ARG otherwise). */
+int ancsh_net_forward_shared(const ancsh_net_t *net, int B, int N, const float *P, void *workspace, size_t workspace_bytes,
+                             const ancsh_net_t *geometry_net, const void *geometry_workspace, const ancsh_pred_t *pred,
+                             void *const *stage_events, void *stream);
+
 int ancsh_event_create(void **event_out);
 int ancsh_event_record(void *event, void *stream);
 int ancsh_event_elapsed_ms(void *start, void *stop, float *ms_out); /* both events must have completed */

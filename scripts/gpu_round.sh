@@ -19,7 +19,7 @@ echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_launches.log 2>&1
 echo "== ncu full (dominant kernels)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'sa_tc_kernel|chain_tc_kernel|gemm_tc_kernel|single_score|joint_lm_kernel|joint_init_kernel|joint_refit|fps_kernel' -s 30 -c 16 -f -o $OUT/${TAG}_prof \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'chain2_kernel|gemm_tc_kernel|single_score|joint_lm_kernel|joint_init_kernel|joint_refit|fps_kernel' -s 30 -c 16 -f -o $OUT/${TAG}_prof \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --batch 64 > $OUT/${TAG}_ncu_full.log 2>&1
 fi
 ls -la $OUT | tail -20

@@ -66,3 +66,21 @@ def test_pipeline_matches_stagewise_and_oracle():
                 assert abs(res[b]["baseline"][j]["scale"] - ref["baseline"][j]["scale"]) < 5e-3
                 checked += 1
     assert checked >= 3
+
+
+def test_shared_geometry_forward_is_bit_identical():
+    """ancsh_net_forward_shared: the second network reuses the first network's FPS / ball-query results (same xyz,
+    pointnet_util.py:47-49) -- outputs must equal a stand-alone forward bit for bit."""
+    import torch
+    from articulated_pose_b200 import synthetic, weights
+    from articulated_pose_b200.network import AncshNet
+    P, _ = synthetic.make_batch(range(40, 44))
+    a = AncshNet(weights.synthetic_weights(3, True, True, seed=7), 3, nsample=32)
+    b = AncshNet(weights.synthetic_weights(3, False, False, seed=8), 3, mixed_pred=False, early_split_nocs=False, nsample=32)
+    Pd = torch.from_numpy(P).cuda()
+    alone = {k: v.clone() for k, v in b.forward_device(Pd).items()}
+    a.forward_device(Pd)
+    shared = b.forward_device(Pd, geometry_from=a)
+    torch.cuda.synchronize()
+    for k in alone:
+        assert torch.equal(alone[k], shared[k]), k
