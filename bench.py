@@ -363,7 +363,7 @@ def main():
     peak = peaks["bf16_tflops_sustained"]
     n_fwd = 2 if (full and two_nets) else 1
     fwd_ms = sum(stage_ms.values())
-    roofline = {"bound": "tensor", "kernel": ("sa_tc_kernel" if args.precision == "f16x3" else "sa_kernel<128>") + " (%s, ANCSH net)" % dom,
+    roofline = {"bound": "tensor", "kernel": ("chain2_kernel<SA>" if args.precision == "f16x3" else "sa_kernel<128>") + " (%s, ANCSH net)" % dom,
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                 "peak_source": peaks["source"] + " bf16 sustained; kernel duration from per-stage CUDA events of a serialized pass in the same run",
                 "avg_launch_ms": stage_ms[dom], "flops_per_launch": fl[dom],
