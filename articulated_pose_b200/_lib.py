@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libancsh_b200.so")
+# ANCSH_B200_LIB: load another build of the same library (A/B runs of kernel variants); no fallback either way
+LIB_PATH = os.environ.get("ANCSH_B200_LIB") or os.path.join(_HERE, "libancsh_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

@@ -21,6 +21,7 @@
 // Numerics as in net_tc.cu: hi*hi products and the cross terms hi*lo + lo*hi go to separate f32 accumulators (the tensor
 // core accumulates with truncation), long k ranges are split over several hi*hi accumulators, the epilogue adds them in
 // round-to-nearest f32.
+#include <cstdlib>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "net_tc.cuh"
@@ -90,6 +91,33 @@ __device__ __forceinline__ bool elect_one()
 // barrier of the workers and the MMA warp (the producer warp runs free of it)
 __device__ __forceinline__ void work_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NWORK + 32) : "memory"); }
 
+// 16-column variants of the epilogue primitives (three-CTAs-per-SM build: 64 registers per thread)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void load_acc2(uint32_t trow, int G, int c0, float (&v)[16], int stride)
+{
+    uint32_t ra[16], rb[16];
+    tmem_ld16_issue(trow + c0, ra);
+    tmem_ld16_issue(trow + (uint32_t)stride + c0, rb);
+    tc::tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]) + __uint_as_float(rb[i]);
+    for (int g = 2; g <= G; ++g) {
+        tmem_ld16_issue(trow + (uint32_t)(g * stride) + c0, ra);
+        tc::tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(ra[i]);
+    }
+}
+
 // 32 accumulator columns of this thread's row: sum of the hi*hi accumulators and the cross-term accumulator
 __device__ __forceinline__ void load_acc2(uint32_t trow, int G, int c0, float (&v)[32], int stride)
 {
@@ -127,10 +155,11 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4 *dst_hi, uint4
     *dst_lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-__device__ __forceinline__ void store_operand2(uint8_t *A_hi, uint8_t *A_lo, int row, int col0, const float (&v)[32])
+template <int CW>
+__device__ __forceinline__ void store_operand2(uint8_t *A_hi, uint8_t *A_lo, int row, int col0, const float (&v)[CW])
 {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < CW / 8; ++q) {
         float w[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) w[i] = v[q * 8 + i];
@@ -140,20 +169,23 @@ __device__ __forceinline__ void store_operand2(uint8_t *A_hi, uint8_t *A_lo, int
 }
 
 // max over the 32 rows of a warp (values >= 0 after ReLU: unsigned order of the bit patterns == float order)
-__device__ __forceinline__ void pool_store2(float *orow, int S, int lane, const float (&v)[32])
+template <int CW>
+__device__ __forceinline__ void pool_store2(float *orow, int S, int lane, const float (&v)[CW])
 {
     uint32_t keep = 0;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < CW; ++i) {
         const uint32_t mx = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(v[i]));
         if (lane == i) keep = mx;
     }
-    if (S == 32) orow[lane] = __uint_as_float(keep);
-    else atomicMax(reinterpret_cast<int *>(orow + lane), (int)keep);
+    if (lane < CW) {
+        if (S == 32) orow[lane] = __uint_as_float(keep);
+        else atomicMax(reinterpret_cast<int *>(orow + lane), (int)keep);
+    }
 }
 
-template <bool SA>
-__global__ void __launch_bounds__(NTHR, 2) chain2_kernel(const __grid_constant__ Chain2Args a)
+template <bool SA, int MINB>
+__global__ void __launch_bounds__(NTHR, MINB) chain2_kernel(const __grid_constant__ Chain2Args a)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *A_hi = smem;
@@ -164,6 +196,7 @@ __global__ void __launch_bounds__(NTHR, 2) chain2_kernel(const __grid_constant__
     uint64_t *bar_acc = bar_empty + MAX_STAGES;
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bar_acc + 1);
 
+    constexpr int CW = MINB >= 3 ? 16 : 32;   // columns a worker handles at a time (register budget)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) tc::tmem_alloc(s_tmem, a.tmem_cols);
     if (tid == NWORK) {
@@ -268,10 +301,10 @@ __global__ void __launch_bounds__(NTHR, 2) chain2_kernel(const __grid_constant__
             if (a.N0) {
                 // xyz-only input (layer1): the first conv has 3 input channels -- 3 FMAs per output on the CUDA cores in
                 // exact f32 instead of a 16-deep tensor-core step plus a whole epilogue round trip through TMEM
-                for (int c0 = h * 32; c0 < a.N0; c0 += 64) {
-                    float v[32];
+                for (int c0 = h * CW; c0 < a.N0; c0 += 2 * CW) {
+                    float v[CW];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < CW / 4; ++i) {
                         const float4 bb = __ldg(reinterpret_cast<const float4 *>(a.b0 + c0) + i);
                         const float4 w0 = __ldg(reinterpret_cast<const float4 *>(a.W0 + c0) + i);
                         const float4 w1 = __ldg(reinterpret_cast<const float4 *>(a.W0 + a.N0 + c0) + i);
@@ -283,9 +316,9 @@ __global__ void __launch_bounds__(NTHR, 2) chain2_kernel(const __grid_constant__
                     }
                     if (a.relu0) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                        for (int i = 0; i < CW; ++i) v[i] = fmaxf(v[i], 0.f);
                     }
-                    store_operand2(A_hi, A_lo, r, c0, v);
+                    store_operand2<CW>(A_hi, A_lo, r, c0, v);
                 }
             } else
             // channel order [features(C), xyz(3), zero pad] (pointnet_util.py:52-57)
@@ -333,33 +366,33 @@ __global__ void __launch_bounds__(NTHR, 2) chain2_kernel(const __grid_constant__
             tc::mbar_wait(bar_acc, (uint32_t)(u & 1));
             tc::fence_after_sync();
             const float *bias = U.bias_stride ? U.bias + (size_t)(R / a.rows_per_cloud) * U.bias_stride : U.bias;
-            const int groups = U.nc >> 5;                     // 32-column groups per chunk
+            const int groups = U.nc / CW;                     // CW-column groups per chunk
             for (int j = 0; j < U.nchunks; ++j) {
                 for (int q = 0; q < groups; ++q) {
-                    if (((j * groups + q) & 1) != h) continue;        // the two halves alternate 32-column groups
-                    const int c0 = q * 32;
-                    float v[32];
+                    if (((j * groups + q) & 1) != h) continue;        // the two halves alternate column groups
+                    const int c0 = q * CW;
+                    float v[CW];
                     load_acc2(trow + (uint32_t)(j * (U.G + 1) * U.nc), U.G, c0, v, U.nc);
                     const int col = U.n0 + j * U.nc + c0;
                     const float4 *b4 = reinterpret_cast<const float4 *>(bias + col);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < CW / 4; ++i) {
                         const float4 bb = __ldg(b4 + i);
                         v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
                     }
                     if (U.relu) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                        for (int i = 0; i < CW; ++i) v[i] = fmaxf(v[i], 0.f);
                     }
                     if (U.pool) {
                         const long g = ((long)blockIdx.x * TM + wq * 32) / a.S;
-                        pool_store2(U.out + ((size_t)b * a.m + g) * U.Nfull + col, a.S, lane, v);
+                        pool_store2<CW>(U.out + ((size_t)b * a.m + g) * U.Nfull + col, a.S, lane, v);
                     } else if (U.out) {
                         float4 *o = reinterpret_cast<float4 *>(U.out + (size_t)R * U.ldo + col);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        for (int i = 0; i < CW / 4; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                     }
-                    if (U.inplace) store_operand2(A_hi, A_lo, r, col, v);
+                    if (U.inplace) store_operand2<CW>(A_hi, A_lo, r, col, v);
                 }
             }
             tc::fence_proxy_async();
@@ -381,8 +414,9 @@ struct LayerSpec {
     long bias_stride;
 };
 
-int build_units(Chain2Args &a, const LayerSpec *spec, int nspec, size_t *smem_out)
+int build_units(Chain2Args &a, const LayerSpec *spec, int nspec, size_t *smem_out, int *minb_out)
 {
+    *minb_out = 2;
     int kmax = a.K0;
     for (int i = 0; i < nspec; ++i) {
         const TcLayer &L = spec[i].L;
@@ -397,6 +431,16 @@ int build_units(Chain2Args &a, const LayerSpec *spec, int nspec, size_t *smem_ou
     size_t limit = 113 * 1024;                                 // two CTAs per SM when the operand is small enough
     a.tmem_cols = 256;
     a.nst = MAX_STAGES;
+    // Narrow chains (every accumulator set fits 128 TMEM columns when the layers are cut into 64-column chunks, operand
+    // + ring <= 1/3 of the shared memory): three CTAs per SM -- these chains are bound by the latency of the
+    // gather -> MMA -> epilogue sequence of one tile, not by any pipe, so residency is what buys throughput.
+    static const bool narrow_off = getenv("ANCSH_CHAIN_NARROW_OFF") != nullptr;   // A/B switch for profiling
+    bool narrow = !narrow_off && opbytes + (size_t)MAX_STAGES * STAGE_BYTES + tail <= 74 * 1024;
+    for (int i = 0; i < nspec && narrow; ++i) {
+        const TcLayer &L = spec[i].L;
+        if (L.K > 144 || L.N % 32 != 0 || (spec[i].inplace ? L.N > 64 : (L.N > 64 && L.N % 64 != 0))) narrow = false;
+    }
+    if (narrow) { limit = 74 * 1024; a.tmem_cols = 128; *minb_out = 3; }
     if (opbytes + (size_t)MAX_STAGES * STAGE_BYTES + tail > limit) {
         limit = 227 * 1024;
         a.tmem_cols = 512;
@@ -407,11 +451,12 @@ int build_units(Chain2Args &a, const LayerSpec *spec, int nspec, size_t *smem_ou
     a.nunits = 0;
     for (int i = 0; i < nspec; ++i) {
         const TcLayer &L = spec[i].L;
-        const int nc = L.N >= 128 ? 128 : L.N;                 // 32 / 64 / 128
+        const int nc = narrow ? (L.N >= 64 ? 64 : L.N) : (L.N >= 128 ? 128 : L.N);   // 32 / 64 / 128
         if (L.N % nc != 0) return ANCSH_ERR_UNSUPPORTED;
         const int nch = L.N / nc;
         const int together = spec[i].inplace ? nch : 1;        // chunks whose accumulators are live together
         if (together * 2 * nc > (int)a.tmem_cols) {            // e.g. a 256-wide in-place layer needs all 512 columns
+            if (narrow) return ANCSH_ERR_UNSUPPORTED;
             if (limit == 113 * 1024) { a.tmem_cols = 512; }
             if (together * 2 * nc > (int)a.tmem_cols) return ANCSH_ERR_UNSUPPORTED;
         }
@@ -437,12 +482,12 @@ int build_units(Chain2Args &a, const LayerSpec *spec, int nspec, size_t *smem_ou
     return ANCSH_OK;
 }
 
-template <bool SA>
+template <bool SA, int MINB>
 int launch_chain2(const Chain2Args &a, dim3 grid, size_t smem, cudaStream_t st)
 {
-    ANCSH_CUDA(cudaFuncSetAttribute(chain2_kernel<SA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ANCSH_CUDA(cudaFuncSetAttribute(chain2_kernel<SA>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    chain2_kernel<SA><<<grid, NTHR, smem, st>>>(a);
+    ANCSH_CUDA(cudaFuncSetAttribute(chain2_kernel<SA, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ANCSH_CUDA(cudaFuncSetAttribute(chain2_kernel<SA, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    chain2_kernel<SA, MINB><<<grid, NTHR, smem, st>>>(a);
     ANCSH_CHECK_LAUNCH();
     return ANCSH_OK;
 }
@@ -468,10 +513,12 @@ int sa_tc2_launch(const SaTcArgs &s, int B, cudaStream_t st)
     for (int l = first; l < 3; ++l) { spec[l - first].L = s.L[l]; spec[l - first].inplace = l < 2; }
     spec[2 - first].pool = 1; spec[2 - first].out = s.out;
     size_t smem = 0;
-    int rc = build_units(a, spec, 3 - first, &smem);
+    int minb = 2;
+    int rc = build_units(a, spec, 3 - first, &smem, &minb);
     if (rc) return rc;
     if (s.S != 32) ANCSH_CUDA(cudaMemsetAsync(s.out, 0, (size_t)B * s.m * s.L[2].N * sizeof(float), st));
-    return launch_chain2<true>(a, dim3((unsigned)(rows / TM), B), smem, st);
+    if (minb == 3) return launch_chain2<true, 3>(a, dim3((unsigned)(rows / TM), B), smem, st);
+    return launch_chain2<true, 2>(a, dim3((unsigned)(rows / TM), B), smem, st);
 }
 
 int chain_tc2_launch(const ChainTcArgs &c, long rows_total, cudaStream_t st)
@@ -492,7 +539,9 @@ int chain_tc2_launch(const ChainTcArgs &c, long rows_total, cudaStream_t st)
     }
     if (c.bias0) { spec[0].bias_override = c.bias0; spec[0].bias_stride = c.bias0_stride; }
     size_t smem = 0;
-    int rc = build_units(a, spec, c.nsteps, &smem);
+    int minb = 2;
+    int rc = build_units(a, spec, c.nsteps, &smem, &minb);
     if (rc) return rc;
-    return launch_chain2<false>(a, dim3((unsigned)(rows_total / TM)), smem, st);
+    if (minb == 3) return launch_chain2<false, 3>(a, dim3((unsigned)(rows_total / TM)), smem, st);
+    return launch_chain2<false, 2>(a, dim3((unsigned)(rows_total / TM)), smem, st);
 }

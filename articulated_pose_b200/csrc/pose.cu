@@ -503,7 +503,9 @@ constexpr int LM_SOLVES_PER_LANE = 3;
 constexpr int LM_PHASES = 3;
 constexpr int LM_BUDGET[LM_PHASES] = {32, 160, 0x7fffffff};   // evaluations after which a solve moves to the next phase
 constexpr int LM_PHASE_SHARE[LM_PHASES] = {1, 4, 32};         // phase p is sized for 1/share of the solves
-constexpr int LM_BLOCKS_PER_SM = 6;   // 168 registers x 64 threads
+// 4 blocks x 64 threads -> 255 registers per thread, no spills (6 blocks / 168 registers spilled 400 bytes per thread:
+// measured 8.5 -> 6.9 ms for the joint stage alone; the pipelined throughput moves by 2% only, see DESIGN.md "overlap")
+constexpr int LM_BLOCKS_PER_SM = 4;
 constexpr int LM_SLOTS = 39;     // doubles per lane in shared memory: 36 point coordinates + joint direction
 
 // objective_eval over one lane's 3+3 points; element e of the lane lives at pts[e * LMT] (conflict-free)

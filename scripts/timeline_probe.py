@@ -33,5 +33,7 @@ def off(ev, j):
     ms = ctypes.c_float(); _lib.ancsh_event_elapsed_ms(base.arr[0], ev.arr[j], ctypes.byref(ms)); return round(ms.value, 2)
 for i in range(S):
     e = evs[i]
+    print("   fwdA stages:", " ".join("%s=%.2f" % (n, off(e[0], j + 1) - off(e[0], j)) for j, n in enumerate(_lib.NET_STAGES)))
+    print("   fwdN stages:", " ".join("%s=%.2f" % (n, off(e[1], j + 1) - off(e[1], j)) for j, n in enumerate(_lib.NET_STAGES)))
     print("step", i, "fwdA %.2f-%.2f" % (off(e[0], 0), off(e[0], nst)), "fwdN %.2f-%.2f" % (off(e[1], 0), off(e[1], nst)),
           "pose:", " ".join("%s@%.2f" % (n[:6], off(e[2], j)) for j, n in enumerate(_lib.POSE_STAGES)), "end@%.2f" % off(e[2], npst))
