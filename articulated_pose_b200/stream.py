@@ -1,0 +1,83 @@
+"""Mixed-category cloud streams (BASELINE.json configs[4]: all five categories, sharded over the GPUs of one box).
+
+The reference runs one `main.py --test` + `pose_multi_process.py` per category because every category has its own
+checkpoint, part count K and cloud size N (global_info.py, lib/dataset.py:35).  A launch of the kernels here is
+homogeneous in (K, N, weights) too, so a mixed stream is bucketed by category: each rank takes its contiguous slice of
+the stream (dist.shard_range -- the pose_multi_process.py:54-63 rule), groups the slice by category, cuts every group
+into batches and pushes them through that category's AncshPipeline (the pipelines of different categories share the
+device; their batches are pipelined through AncshPipeline.run_many).  Results come back in stream order; the one
+collective is the final all-gather of the per-cloud pose records padded to the widest category
+(dist.pack_records / gather_records).
+"""
+import numpy as np
+
+from . import dist as adist
+
+
+def bucket_by_category(items):
+    """items: sequence of (category, payload) -> {category: [positions in the sequence]} (order preserved)."""
+    buckets = {}
+    for pos, (cat, _) in enumerate(items):
+        buckets.setdefault(cat, []).append(pos)
+    return buckets
+
+
+def batches(positions, batch):
+    """Cut a bucket into consecutive batches of at most `batch` positions."""
+    return [positions[i:i + batch] for i in range(0, len(positions), batch)]
+
+
+def record_matrix(results, parts, k_max):
+    """Per-cloud pose records of clouds with different part counts as ONE float64 matrix for the all-gather: row =
+    [K, record of dist.pack_records zero-padded to the width of k_max parts]."""
+    width = 1 + adist.record_width(k_max)
+    out = np.zeros((len(results), width), np.float64)
+    for i, (r, K) in enumerate(zip(results, parts)):
+        out[i, 0] = K
+        rec = adist.pack_records([r], K)[0]
+        out[i, 1:1 + rec.shape[0]] = rec
+    return out
+
+
+class MixedStream:
+    """pipelines: {category: AncshPipeline}; `load(category, payload)` -> (P (N,3) float32, joint_cls (N,) int32)."""
+
+    def __init__(self, pipelines, load, batch=256, rank=0, world=1, pad=True):
+        self.pipelines, self.load = pipelines, load
+        self.batch, self.rank, self.world, self.pad = int(batch), int(rank), int(world), bool(pad)
+
+    def my_slice(self, n_items):
+        return adist.shard_range(n_items, self.rank, self.world)
+
+    def run(self, items, unpack=True):
+        """items: the WHOLE stream [(category, payload)] (the same list on every rank).  Returns (start, end, results):
+        this rank's slice bounds and its per-cloud results in stream order."""
+        s, e = self.my_slice(len(items))
+        mine = list(items[s:e])
+        results = [None] * len(mine)
+        for cat, positions in bucket_by_category(mine).items():
+            pipe = self.pipelines[cat]
+            work = []
+            for chunk in batches(positions, self.batch):
+                loaded = [self.load(cat, mine[p][1]) for p in chunk]
+                # a ragged last batch is padded with copies of its last cloud (results dropped below): every launch of
+                # a category then has ONE shape, so the pipelined path never allocates pinned / device buffers mid-stream
+                loaded += [loaded[-1]] * (self.batch - len(loaded) if self.pad else 0)
+                work.append((np.stack([l[0] for l in loaded]).astype(np.float32),
+                             np.stack([l[1] for l in loaded]).astype(np.int32)))
+            full = [w for w in work if w[0].shape[0] == work[0][0].shape[0]]
+            outs = pipe.run_many(full, unpack=unpack)
+            for w in work[len(full):]:
+                outs += pipe.run_many([w], unpack=unpack)
+            for chunk, out in zip(batches(positions, self.batch), outs):
+                if unpack:
+                    for p, r in zip(chunk, out):
+                        results[p] = r
+                else:
+                    for i, p in enumerate(chunk):
+                        results[p] = {k: v[i] for k, v in out.items()}
+        return s, e, results
+
+    def gather(self, results, parts, k_max, device=None):
+        """The path's single collective: every rank's records -> the full (n_clouds, 1 + width(k_max)) matrix."""
+        return adist.gather_records(record_matrix(results, parts, k_max), device=device)

@@ -35,7 +35,36 @@ CATEGORIES = {
                 (2, "prismatic", (0.0, 0.0, 0.0), (0.0, 0.0, 1.0), (0.0, 0.3)),
                 (3, "prismatic", (0.0, -0.29, 0.0), (0.0, 0.0, 1.0), (0.0, 0.3))],
     ),
+    # the three remaining categories of the reference (global_info.py:30-82): two parts, one revolute joint, N = 1024
+    "oven": dict(
+        n_points=1024,
+        boxes=[((0.80, 0.60, 0.60), (0.0, 0.0, 0.0)),
+               ((0.70, 0.50, 0.04), (0.0, 0.0, 0.32))],
+        split=(0.65, 0.35),
+        joints=[(1, "revolute", (0.0, -0.25, 0.30), (1.0, 0.0, 0.0), (0.0, np.pi / 2))],
+    ),
+    "laptop": dict(
+        n_points=1024,
+        boxes=[((0.80, 0.04, 0.55), (0.0, 0.0, 0.0)),
+               ((0.80, 0.55, 0.03), (0.0, 0.295, -0.275))],
+        split=(0.5, 0.5),
+        joints=[(1, "revolute", (0.0, 0.02, -0.275), (1.0, 0.0, 0.0), (-np.pi / 3, np.pi / 6))],
+    ),
+    "washing_machine": dict(
+        n_points=1024,
+        boxes=[((0.65, 0.85, 0.65), (0.0, 0.0, 0.0)),
+               ((0.40, 0.40, 0.05), (0.0, 0.05, 0.35))],
+        split=(0.75, 0.25),
+        joints=[(1, "revolute", (-0.20, 0.05, 0.33), (0.0, 1.0, 0.0), (-np.pi / 2, 0.0))],
+    ),
 }
+
+# the reference's five benchmark categories (global_info.py: eyeglasses, oven, laptop, washing_machine, drawer)
+ALL_CATEGORIES = ("eyeglasses", "oven", "laptop", "washing_machine", "drawer")
+
+
+def n_parts(category):
+    return len(CATEGORIES[category]["boxes"])
 
 
 def _rodrigues(axis, angle):
@@ -163,3 +192,11 @@ def teacher_predictions(cloud, seed=99, nocs_sigma=0.01, outlier_frac=0.10, labe
         axis[m] = cloud["joint_axis_gt"][j - 1]
     axis += rng.normal(0, axis_sigma, size=axis.shape)
     return {"nocs_per_point": nocs.astype(np.float32), "W": W, "joint_axis_per_point": axis.astype(np.float32)}
+
+
+def mixed_stream(n_clouds, categories=ALL_CATEGORIES, seed=2024, first_id=0):
+    """BASELINE.json configs[4]: a shuffled stream of clouds drawn uniformly from `categories`.
+    Returns [(category, cloud_id)], the same list on every rank (the ranks shard it, dist.shard_range)."""
+    rng = np.random.default_rng(seed)
+    cats = rng.integers(0, len(categories), size=int(n_clouds))
+    return [(categories[int(c)], int(first_id + i)) for i, c in enumerate(cats)]

@@ -29,6 +29,8 @@ CASES = [
     ("eyeglasses", 3, 3, 32, True),
     ("eyeglasses", 3, 2, 64, False),
     ("drawer", 4, 2, 64, True),
+    ("laptop", 2, 2, 64, True),          # two-part categories (oven / laptop / washing_machine, global_info.py:30-82)
+    ("oven", 2, 2, 32, False),
 ]
 
 
