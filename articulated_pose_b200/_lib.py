@@ -125,6 +125,9 @@ POSE_STAGES = ("partition", "single_score", "single_refit", "joint_score", "join
 ancsh_pose_sample_indices = _sig("ancsh_pose_sample_indices", [ctypes.c_ulonglong, c_int, c_int, c_int, vp, vp, vp])
 ancsh_umeyama = _sig("ancsh_umeyama", [c_int, c_int, vp, vp, vp, vp, vp, vp, vp])
 
+ancsh_amodal_extent = _sig("ancsh_amodal_extent", [c_int, c_int, c_int, vp, vp, vp, vp, vp])
+ancsh_box_iou_3d = _sig("ancsh_box_iou_3d", [c_int, c_int, vp, vp, vp, vp, vp, vp])
+
 NET_STAGES = ("fps1", "fps2", "ball1", "sa1", "ball2", "sa2", "sa3", "fp1", "fp2", "fp3_heads")
 
 

@@ -261,6 +261,23 @@ int ancsh_pose_sample_indices(unsigned long long seed, int stream_id, int nprob,
 int ancsh_umeyama(int nprob, int nmax, const float *src, const float *tgt, const int *cnt, double *scale, double *R,
                   double *t, void *stream);
 
+/* ---- metric kernels behind the pose stage -------------------------------------------------------- */
+
+/* Amodal box extents of the predicted parts (evaluation/compute_miou.py:187,196-199): for cloud b and part j,
+ * extent[b,j,:] = 2 * max_i |nocs[b,i,3j:3j+3] - 0.5| over the points with argmax_k mask[b,i,k] == j (first maximum),
+ * evaluated in f32 like NumPy does on the f32 h5 arrays.  nocs (B,N,3K) f32, mask (B,N,K) f32 ->
+ * extent (B,K,3) f32, count (B,K) int32.  Empty part: extent = NaN, count = 0 (the reference raises inside np.max
+ * and its bare `except` drops the cloud, :250). */
+int ancsh_amodal_extent(int B, int N, int K, const float *nocs, const float *mask, float *extent, int *count,
+                        void *stream);
+
+/* lib/d3_utils.py:55-69 iou_3d(bbox1, bbox2, nres=50) for npairs box pairs: bbox1/bbox2 (npairs,8,3) f64 corners in
+ * get_3d_bbox's order (:7-38; pts_inside_box reads corners 4,5,7,0, :43-45) -> iou (npairs) f64 = intersect/union of the
+ * nres^3 np.linspace grid samples strictly inside both / either box, 1.0 when union == 0 (:66-67).  inter / uni
+ * (npairs) int32 receive the two counts; either may be NULL. */
+int ancsh_box_iou_3d(int npairs, int nres, const double *bbox1, const double *bbox2, double *iou, int *inter, int *uni,
+                     void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,5 +21,11 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 echo "== ncu full (dominant kernels)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'chain2_kernel|gemm_tc_kernel|single_score|joint_lm_kernel|joint_init_kernel|joint_refit|fps_kernel' -s 30 -c 16 -f -o $OUT/${TAG}_prof \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --batch 64 > $OUT/${TAG}_ncu_full.log 2>&1
+echo "== ncu dram traffic of the chain kernels at the bench batch (256)"
+timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:'chain2_kernel' -s 18 -c 6 --csv --log-file $OUT/${TAG}_chain_traffic.csv \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_traffic.log 2>&1
+fi
+if [ "$MODE" == "all" ]; then
+echo "== pipelined timeline" ; timeout 300 python scripts/timeline_probe.py 2>&1 | tail -30 | tee $OUT/${TAG}_timeline.log
 fi
 ls -la $OUT | tail -20
