@@ -596,6 +596,22 @@ static int net_forward_impl(const ancsh_net_t *net, int B, int N, const float *P
             if ((size_t)m2 * (net->sa3[0].cout_pad + net->sa3[1].cout_pad) > (size_t)N * net->fp2[1].cout || m2 % 32 != 0 ||
                 net->sa3[2].cout != net->sa3[2].cout_pad)
                 return ANCSH_ERR_UNSUPPORTED;
+            if (!tc_v1()) {
+                // conv0 (in place) + conv1 -> t2 as one warp-specialised chain: each 128-row CTA converts its operand once
+                // and streams the weights through the TMA ring (the streaming GEMM re-converts the rows for every
+                // 128-column chunk and serialises load / MMA).  conv2 (K = 512: its operand images would need 256 KB of
+                // shared memory) stays a streaming GEMM with the max over the cloud's npoint2 rows in its epilogue.
+                ChainTcArgs c{};
+                c.X1 = l2_points; c.C1 = net->sa2[2].cout; c.X2 = l2_xyz; c.C2 = 3; c.rows_per_cloud = m2;
+                c.S[0].L = tc_layer(net->sa3[0]); c.S[0].dst = TC_DST_INPLACE;
+                c.S[1].L = tc_layer(net->sa3[1]); c.S[1].dst = TC_DST_GLOBAL; c.S[1].out = t2; c.S[1].ldo = net->sa3[1].cout_pad;
+                c.nsteps = 2;
+                if ((rc = chain_tc2_launch(c, (long)B * m2, st))) return rc;
+                GemmTcArgs g{};
+                g.X1 = t2; g.C1 = net->sa3[1].cout_pad; g.X2 = nullptr; g.C2 = 0; g.L = tc_layer(net->sa3[2]);
+                g.out = l3_points; g.ldo = 0; g.pool_S = m2;
+                if ((rc = gemm_tc_launch(g, (long)B * m2, st))) return rc;
+            } else {
             GemmTcArgs g{};
             g.X1 = l2_points; g.C1 = net->sa2[2].cout; g.X2 = l2_xyz; g.C2 = 3; g.L = tc_layer(net->sa3[0]);
             g.out = t1; g.ldo = net->sa3[0].cout_pad; g.pool_S = 0;
@@ -606,6 +622,7 @@ static int net_forward_impl(const ancsh_net_t *net, int B, int N, const float *P
             g.X1 = t2; g.C1 = net->sa3[1].cout_pad; g.L = tc_layer(net->sa3[2]);
             g.out = l3_points; g.ldo = 0; g.pool_S = m2;
             if ((rc = gemm_tc_launch(g, (long)B * m2, st))) return rc;
+            }
         } else if ((rc = sa_launch<64>(a, B, st))) return rc;
     }
     // fa_layer1

@@ -26,7 +26,7 @@
 namespace {
 
 constexpr int TM = 128;      // rows per CTA == threads per CTA
-constexpr int KSLICE = 32;   // k elements per weight slice (2 MMA k-steps)
+constexpr int KSLICE = 64;   // k elements per weight slice (4 MMA k-steps)
 constexpr int NCH = 128;     // default output columns per chunk = TMEM columns per accumulator (layer1 uses 64)
 
 struct Engine {
@@ -320,33 +320,53 @@ __global__ void __launch_bounds__(TM) chain_tc_kernel(const ChainTcArgs a)
 }
 
 // ============================================================================================================
-// Streaming GEMM: neither operand is resident.  Per 32-wide k slice every thread converts its row's 32 f32 inputs to
+// Streaming GEMM: neither operand is resident.  Per GK-wide k slice every thread converts its row's GK f32 inputs to
 // the fp16 hi/lo images, the weight slice arrives by cp.async.  blockIdx.y selects a 128-column chunk.
+// Two slice buffers: the MMAs of slice i (committed to bar[i & 1]) run while the threads load and convert slice i + 1;
+// a buffer is rewritten only after the commit of the slice that last used it has arrived.
+constexpr int GK = 32;       // k elements per slice of the streaming GEMM (2 MMA k-steps)
+constexpr size_t kGemmStageA = (size_t)2 * (GK / 8) * 2048;            // hi + lo operand images of one slice
+constexpr size_t kGemmStageW = (size_t)(GK / 8) * 2 * NCH * 16;        // weight slice
+constexpr size_t kGemmSmem = 2 * (kGemmStageA + kGemmStageW) + 32;
+
 __global__ void __launch_bounds__(TM) gemm_tc_kernel(const GemmTcArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t *A_hi = smem;                                   // (KSLICE/8) * 2048
-    uint8_t *A_lo = A_hi + (KSLICE / 8) * 2048;
-    uint8_t *Wst = A_lo + (KSLICE / 8) * 2048;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(Wst + (size_t)(KSLICE / 8) * 2 * NCH * 16);
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bar + 1);
+    uint8_t *Abuf = smem;                                   // [2][hi | lo][(GK/8) * 2048]
+    uint8_t *Wbuf = smem + 2 * kGemmStageA;                 // [2][kGemmStageW]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(Wbuf + 2 * kGemmStageW);      // [2]
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bar + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long R = (long)blockIdx.x * TM + tid;
     const int n0 = blockIdx.y * NCH;
     const int NC = min(NCH, a.L.N - n0);
-    Engine e = engine_setup(Wst, bar, s_tmem, a.tmem_cols, NCH);
+    Engine e = engine_setup(Wbuf, bar, s_tmem, a.tmem_cols, NCH);
+    if (tid == 0) tc::mbar_init(bar + 1, 1);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
 
     const float *r1 = a.X1 + (size_t)R * a.C1;
     const float *r2 = a.X2 ? a.X2 + (size_t)R * a.C2 : nullptr;
-    const uint32_t a_hi0 = tc::smem_u32(A_hi), a_lo0 = tc::smem_u32(A_lo);
     const int nk16 = a.L.K / 16;
     const int G = a.max_acc;
     uint32_t startedA = 0, startedB = 0;
-    for (int k16 = 0; k16 < nk16; k16 += KSLICE / 16) {
-        const int steps = min(KSLICE / 16, nk16 - k16);
+    uint32_t phase[2] = {0, 0};
+    int it = 0;
+    for (int k16 = 0; k16 < nk16; k16 += GK / 16, ++it) {
+        const int st = it & 1;
+        const int steps = min(GK / 16, nk16 - k16);
+        uint8_t *A_hi = Abuf + (size_t)st * kGemmStageA, *A_lo = A_hi + (GK / 8) * 2048;
+        if (it >= 2) {                                      // the MMAs of slice it - 2 have read this buffer
+            tc::mbar_wait(bar + st, phase[st]);
+            phase[st] ^= 1;
+        }
+        e.Wst = Wbuf + (size_t)st * kGemmStageW;
         stage_weights(e, a.L.Wimg, a.L.N, n0, NC, k16 * 2, steps * 2);
-        for (int kc = 0; kc < steps * 2; ++kc) {
+#pragma unroll
+        for (int kc = 0; kc < GK / 8; ++kc) {
+            if (kc >= steps * 2) break;
             const int c0 = (k16 * 2 + kc) * 8;
             float v[8];
             if (c0 + 8 <= a.C1) {
@@ -367,12 +387,13 @@ __global__ void __launch_bounds__(TM) gemm_tc_kernel(const GemmTcArgs a)
         __syncthreads();
         if (tid == 0) {
             tc::fence_after_sync();
-            issue_slice(e.tmem, e.tmem + (uint32_t)(G * NCH), G, nk16, k16, steps, a_hi0, a_lo0, e.w0, NC, startedA, startedB, NCH);
-            tc::mma_commit(e.bar);
+            issue_slice(e.tmem, e.tmem + (uint32_t)(G * NCH), G, nk16, k16, steps, tc::smem_u32(A_hi), tc::smem_u32(A_lo),
+                        tc::smem_u32(e.Wst), NC, startedA, startedB, NCH);
+            tc::mma_commit(bar + st);
         }
-        tc::mbar_wait(e.bar, e.phase);
-        e.phase ^= 1;
     }
+    // tcgen05.commit tracks every MMA issued before it: the last commit covers the whole accumulation
+    if (it >= 1) tc::mbar_wait(bar + ((it - 1) & 1), phase[(it - 1) & 1]);
     tc::fence_after_sync();
     const uint32_t trow = e.tmem + ((uint32_t)(warp * 32) << 16);
     for (int c0 = 0; c0 < NC; c0 += 32) {
@@ -469,7 +490,7 @@ int gemm_tc_launch(const GemmTcArgs &a0, long rows_total, cudaStream_t st)
     a.max_acc = 1;      // one hi*hi + one cross-term accumulator = 256 columns: two CTAs per SM (3+1 accumulators were
                         // measured: 1.6x slower for 15% less error on layer3)
     a.tmem_cols = pow2_cols((a.max_acc + 1) * NCH);
-    const size_t smem = (size_t)2 * (KSLICE / 8) * 2048 + kStageBytes;
+    const size_t smem = kGemmSmem;
     ANCSH_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ANCSH_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     if (a.pool_S && a.pool_S != 32)

@@ -43,6 +43,8 @@ struct ChainTcArgs {
     long bias0_stride;
     ChainStep S[8];
     int nsteps;
+    int pool_S;               // > 0 (warp-specialised kernel only): the last step is max-pooled over groups of pool_S consecutive
+                              // rows (multiple of 32, ReLU output) into S[last].out = [rows_total / pool_S][N]
     int kmax8;                // filled by the launcher
     uint32_t tmem_cols;
 };

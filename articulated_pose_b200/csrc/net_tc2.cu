@@ -420,7 +420,9 @@ int build_units(Chain2Args &a, const LayerSpec *spec, int nspec, size_t *smem_ou
     int kmax = a.K0;
     for (int i = 0; i < nspec; ++i) {
         const TcLayer &L = spec[i].L;
-        if (!L.Wimg || L.K % 16 != 0 || L.N % 32 != 0 || L.N > 256) return ANCSH_ERR_INVALID_ARG;
+        // an in-place layer keeps all its chunks' accumulators live (<= 512 TMEM columns); an output layer is cut into
+        // independent chunk units and may be as wide as the unit list allows
+        if (!L.Wimg || L.K % 16 != 0 || L.N % 32 != 0 || L.N > (spec[i].inplace ? 256 : 1024)) return ANCSH_ERR_INVALID_ARG;
         if (i > 0 && spec[i - 1].inplace && L.K != spec[i - 1].L.N) return ANCSH_ERR_INVALID_ARG;
         kmax = L.K > kmax ? L.K : kmax;
         if (spec[i].inplace && L.N > kmax) kmax = L.N;
@@ -535,9 +537,20 @@ int chain_tc2_launch(const ChainTcArgs &c, long rows_total, cudaStream_t st)
         spec[i].inplace = c.S[i].dst == TC_DST_INPLACE;
         spec[i].out = c.S[i].out; spec[i].ldo = c.S[i].ldo;
         if (c.S[i].dst == TC_DST_GLOBAL && !c.S[i].out) return ANCSH_ERR_INVALID_ARG;
-        if (c.S[i].out && (c.S[i].ldo < c.S[i].L.N || c.S[i].ldo % 4 != 0)) return ANCSH_ERR_INVALID_ARG;
+        const bool pooled = c.pool_S > 0 && i == c.nsteps - 1;
+        if (!pooled && c.S[i].out && (c.S[i].ldo < c.S[i].L.N || c.S[i].ldo % 4 != 0)) return ANCSH_ERR_INVALID_ARG;
     }
     if (c.bias0) { spec[0].bias_override = c.bias0; spec[0].bias_stride = c.bias0_stride; }
+    if (c.pool_S > 0) {
+        // group max-pool of the last step (set abstraction with group_all, pointnet_util.py:66-91,156): the group of a
+        // warp's 32 rows is (first row) / pool_S, groups never straddle a warp
+        const ChainStep &last = c.S[c.nsteps - 1];
+        if (c.pool_S % 32 != 0 || rows_total % c.pool_S != 0 || last.dst != TC_DST_GLOBAL || !last.L.relu) return ANCSH_ERR_INVALID_ARG;
+        spec[c.nsteps - 1].pool = 1;
+        a.S = c.pool_S; a.m = 0;
+        if (c.pool_S != 32)
+            ANCSH_CUDA(cudaMemsetAsync(last.out, 0, (size_t)(rows_total / c.pool_S) * last.L.N * sizeof(float), st));
+    }
     size_t smem = 0;
     int minb = 2;
     int rc = build_units(a, spec, c.nsteps, &smem, &minb);
