@@ -125,6 +125,7 @@ POSE_STAGES = ("partition", "single_score", "single_refit", "joint_score", "join
 ancsh_pose_sample_indices = _sig("ancsh_pose_sample_indices", [ctypes.c_ulonglong, c_int, c_int, c_int, vp, vp, vp])
 ancsh_umeyama = _sig("ancsh_umeyama", [c_int, c_int, vp, vp, vp, vp, vp, vp, vp])
 
+ancsh_similarity_ransac = _sig("ancsh_similarity_ransac", [c_int, c_int, c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp])
 ancsh_amodal_extent = _sig("ancsh_amodal_extent", [c_int, c_int, c_int, vp, vp, vp, vp, vp])
 ancsh_box_iou_3d = _sig("ancsh_box_iou_3d", [c_int, c_int, vp, vp, vp, vp, vp, vp])
 

@@ -994,6 +994,192 @@ __global__ void __launch_bounds__(RT) umeyama_kernel(int nmax, const float *__re
     }
 }
 
+// ================================================================================================
+// estimateSimilarityTransform (lib/aligning.py:17-33): thresholds from the norm ratio (set_config, :88-103), 5-point
+// Umeyama RANSAC with the reference's bookkeeping (getRANSACInliers :485-507, evaluateModel :540-547), Umeyama refit
+// on the best hypothesis' inliers (:580-622).  SURVEY 8(a) row a-21.  One block per problem:
+//   1. PassT / StopT: block reduction of the point norms;
+//   2. thread h < niter: Umeyama of hypothesis h's 5 samples -> (sR | t) in shared memory;
+//   3. warp per hypothesis: residuals of all points, sum of squares and the count of inliers with a NON-ZERO INDEX
+//      (np.count_nonzero over the index array, :545 -- point 0 never counts);
+//   4. thread 0 replays the sequential loop: strict `>` on the ratio keeps the first best, the loop stops after the
+//      first iteration that leaves BestResidual < StopT;
+//   5. mask of the best hypothesis (all points when no hypothesis ever scored), block-cooperative Umeyama on it.
+// ================================================================================================
+constexpr int SIM_MAX_ITER = 256;
+
+struct SimArgs {
+    int nmax, niter;
+    const float *src, *tgt;
+    const int *cnt, *idx;
+    double *scale, *R, *t, *ratio;
+    unsigned char *inliers;
+    int *iters, *status;
+};
+
+__device__ void umeyama5(const float *S, const float *T, const int *id, double *M)
+{
+    double ms[3] = {0, 0, 0}, mt[3] = {0, 0, 0};
+    for (int k = 0; k < 5; ++k)
+        for (int c = 0; c < 3; ++c) { ms[c] += (double)S[3 * id[k] + c]; mt[c] += (double)T[3 * id[k] + c]; }
+    for (int c = 0; c < 3; ++c) { ms[c] /= 5.0; mt[c] /= 5.0; }
+    double C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, var = 0.0;
+    for (int k = 0; k < 5; ++k) {
+        double sc[3], tc[3];
+        for (int c = 0; c < 3; ++c) { sc[c] = (double)S[3 * id[k] + c] - ms[c]; tc[c] = (double)T[3 * id[k] + c] - mt[c]; }
+        for (int p = 0; p < 3; ++p)
+            for (int q = 0; q < 3; ++q) C[3 * p + q] += tc[p] * sc[q];
+        var += sc[0] * sc[0] + sc[1] * sc[1] + sc[2] * sc[2];
+    }
+    for (int i = 0; i < 9; ++i) C[i] /= 5.0;
+    double R[9], sv[3];
+    pm::kabsch_rotation(C, R);
+    pm::singular_values3(C, sv);
+    double dsum = sv[0] + sv[1] + sv[2];
+    if (pm::det3(C) < 0.0) dsum -= 2.0 * sv[2];
+    const double sf = 1.0 / (var / 5.0) * dsum;
+    double rs[3];
+    pm::matvec3(R, ms, rs);
+    for (int i = 0; i < 9; ++i) M[i] = sf * R[i];                       // OutTransform[:3,:3] = diag(s) Rotation^T = s U Vh
+    for (int c = 0; c < 3; ++c) M[9 + c] = mt[c] - sf * rs[c];           // Translation (:613)
+}
+
+__device__ __forceinline__ double sim_residual(const double *M, const float *S, const float *T, int i)
+{
+    const double x = (double)S[3 * i], y = (double)S[3 * i + 1], z = (double)S[3 * i + 2];
+    const double d0 = (double)T[3 * i] - (M[0] * x + M[1] * y + M[2] * z + M[9]);
+    const double d1 = (double)T[3 * i + 1] - (M[3] * x + M[4] * y + M[5] * z + M[10]);
+    const double d2 = (double)T[3 * i + 2] - (M[6] * x + M[7] * y + M[8] * z + M[11]);
+    return sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+}
+
+__global__ void __launch_bounds__(RT) similarity_ransac_kernel(const SimArgs a)
+{
+    extern __shared__ __align__(16) unsigned char sim_smem[];
+    float *s_src = reinterpret_cast<float *>(sim_smem);                  // n*3
+    float *s_tgt = s_src + (size_t)a.nmax * 3;
+    __shared__ double s_M[SIM_MAX_ITER * 12];
+    __shared__ double s_res[SIM_MAX_ITER];
+    __shared__ int s_nin[SIM_MAX_ITER];
+    __shared__ double s_red[(RT / 32) * 16 + 16];
+    __shared__ int s_best, s_stop;
+    const int prob = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = a.cnt[prob];
+    unsigned char *mask = a.inliers + (size_t)prob * a.nmax;
+    for (int i = tid; i < a.nmax; i += RT) mask[i] = 0;
+    if (n <= 0) {
+        if (tid == 0) {
+            a.scale[prob] = nan(""); a.ratio[prob] = 0.0; a.iters[prob] = 0; a.status[prob] = ANCSH_POSE_EMPTY_PART;
+            for (int i = 0; i < 9; ++i) a.R[(size_t)prob * 9 + i] = nan("");
+            for (int i = 0; i < 3; ++i) a.t[(size_t)prob * 3 + i] = nan("");
+        }
+        return;
+    }
+    const float *gs = a.src + (size_t)prob * a.nmax * 3, *gt = a.tgt + (size_t)prob * a.nmax * 3;
+    double nrm[2] = {0.0, 0.0};
+    for (int i = tid; i < n; i += RT) {
+        double q = 0.0, w = 0.0;
+        for (int c = 0; c < 3; ++c) {
+            const float u = gs[3 * i + c], v = gt[3 * i + c];
+            s_src[3 * i + c] = u; s_tgt[3 * i + c] = v;
+            q += (double)u * (double)u; w += (double)v * (double)v;
+        }
+        nrm[0] += sqrt(q); nrm[1] += sqrt(w);
+    }
+    block_sum<2, RT>(nrm, s_red);                                         // ends with a barrier: s_src / s_tgt visible
+    const double SourceNorm = nrm[0] / n, TargetNorm = nrm[1] / n;
+    const double RatioTS = TargetNorm / SourceNorm, RatioST = SourceNorm / TargetNorm;
+    const double PassT = RatioST > RatioTS ? RatioST : RatioTS;
+    const double StopT = PassT / 100;
+    for (int h = tid; h < a.niter; h += RT) umeyama5(s_src, s_tgt, a.idx + ((size_t)prob * a.niter + h) * 5, s_M + 12 * h);
+    __syncthreads();
+    for (int h = warp; h < a.niter; h += RT / 32) {
+        double M[12];
+        for (int k = 0; k < 12; ++k) M[k] = s_M[12 * h + k];
+        double ss = 0.0;
+        int cntin = 0;
+        for (int i = lane; i < n; i += 32) {
+            const double r = sim_residual(M, s_src, s_tgt, i);
+            ss += r * r;
+            cntin += (r < PassT && i != 0);
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            ss += __shfl_xor_sync(0xFFFFFFFFu, ss, off);
+            cntin += __shfl_xor_sync(0xFFFFFFFFu, cntin, off);
+        }
+        if (lane == 0) { s_res[h] = sqrt(ss); s_nin[h] = cntin; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double best_res = 1e10;
+        int best_nin = 0, best = -1, it = 0;
+        for (int h = 0; h < a.niter; ++h) {
+            ++it;
+            if (s_nin[h] > best_nin) { best_nin = s_nin[h]; best_res = s_res[h]; best = h; }
+            if (best_res < StopT) break;
+        }
+        s_best = best; s_stop = it;
+        a.iters[prob] = it;
+        a.ratio[prob] = (double)best_nin / (double)n;
+    }
+    __syncthreads();
+    const int best = s_best;
+    double M[12];
+    if (best >= 0)
+        for (int k = 0; k < 12; ++k) M[k] = s_M[12 * best + k];
+    // Umeyama over the inliers of the best hypothesis (BestInlierIdx; arange(n) when nothing scored, :488)
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int i = tid; i < n; i += RT) {
+        const bool in = best < 0 || sim_residual(M, s_src, s_tgt, i) < PassT;
+        mask[i] = in;
+        if (in) {
+            for (int c = 0; c < 3; ++c) { acc[c] += (double)s_src[3 * i + c]; acc[3 + c] += (double)s_tgt[3 * i + c]; }
+            acc[6] += 1.0;
+        }
+    }
+    block_sum<7, RT>(acc, s_red);
+    const int nin = (int)acc[6];
+    const double ratio = a.ratio[prob];
+    if (nin == 0 || ratio < 0.1) {            // the reference returns four Nones below 0.1 (:25-27)
+        if (tid == 0) {
+            a.status[prob] = ANCSH_POSE_NO_INLIERS;
+            a.scale[prob] = nan("");
+            for (int i = 0; i < 9; ++i) a.R[(size_t)prob * 9 + i] = nan("");
+            for (int i = 0; i < 3; ++i) a.t[(size_t)prob * 3 + i] = nan("");
+        }
+        return;
+    }
+    double ms[3], mt[3];
+    for (int c = 0; c < 3; ++c) { ms[c] = acc[c] / nin; mt[c] = acc[3 + c] / nin; }
+    double v[12];
+    for (int k = 0; k < 12; ++k) v[k] = 0.0;
+    for (int i = tid; i < n; i += RT) {
+        if (!mask[i]) continue;
+        double sc[3], tc[3];
+        for (int c = 0; c < 3; ++c) { sc[c] = (double)s_src[3 * i + c] - ms[c]; tc[c] = (double)s_tgt[3 * i + c] - mt[c]; }
+        for (int p = 0; p < 3; ++p)
+            for (int q = 0; q < 3; ++q) v[3 * p + q] += tc[p] * sc[q];
+        for (int c = 0; c < 3; ++c) v[9 + c] += sc[c] * sc[c];
+    }
+    block_sum<12, RT>(v, s_red);
+    if (tid == 0) {
+        double C[9], R[9], sv[3];
+        for (int i = 0; i < 9; ++i) C[i] = v[i] / nin;
+        pm::kabsch_rotation(C, R);
+        pm::singular_values3(C, sv);
+        double dsum = sv[0] + sv[1] + sv[2];
+        if (pm::det3(C) < 0.0) dsum -= 2.0 * sv[2];
+        const double sf = 1.0 / ((v[9] + v[10] + v[11]) / nin) * dsum;
+        a.scale[prob] = sf;
+        a.status[prob] = 0;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) a.R[(size_t)prob * 9 + 3 * i + j] = R[3 * j + i];      // Rotation = (U Vh)^T (:606)
+        double rs[3];
+        pm::matvec3(R, ms, rs);
+        for (int j = 0; j < 3; ++j) a.t[(size_t)prob * 3 + j] = mt[j] - sf * rs[j];
+    }
+}
+
 __global__ void sample_indices_kernel(unsigned long long seed, int stream_id, int nprob, int niter, const int *n_per,
                                       int *idx)
 {
@@ -1174,6 +1360,22 @@ extern "C" int ancsh_umeyama(int nprob, int nmax, const float *src, const float 
     if (nprob < 0 || nmax <= 0 || !src || !tgt || !cnt || !scale || !R || !t) return ANCSH_ERR_INVALID_ARG;
     if (nprob == 0) return ANCSH_OK;
     umeyama_kernel<<<nprob, RT, 0, (cudaStream_t)stream>>>(nmax, src, tgt, cnt, scale, R, t);
+    ANCSH_CHECK_LAUNCH();
+    return ANCSH_OK;
+}
+
+extern "C" int ancsh_similarity_ransac(int nprob, int nmax, int niter, const float *src, const float *tgt, const int *cnt,
+                                       const int *idx, double *scale, double *R, double *t, double *inlier_ratio,
+                                       unsigned char *inliers, int *iters_run, int *status, void *stream)
+{
+    if (nprob < 0 || nmax <= 0 || nmax > 8192 || niter <= 0 || niter > SIM_MAX_ITER) return ANCSH_ERR_INVALID_ARG;
+    if (nprob == 0) return ANCSH_OK;
+    if (!src || !tgt || !cnt || !idx || !scale || !R || !t || !inlier_ratio || !inliers || !iters_run || !status)
+        return ANCSH_ERR_INVALID_ARG;
+    SimArgs a{nmax, niter, src, tgt, cnt, idx, scale, R, t, inlier_ratio, inliers, iters_run, status};
+    const size_t smem = (size_t)nmax * 6 * sizeof(float);
+    ANCSH_CUDA(cudaFuncSetAttribute(similarity_ransac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    similarity_ransac_kernel<<<nprob, RT, smem, (cudaStream_t)stream>>>(a);
     ANCSH_CHECK_LAUNCH();
     return ANCSH_OK;
 }

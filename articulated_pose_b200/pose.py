@@ -301,3 +301,62 @@ def compute_gt_pose(P, nocs_gt, cls_gt, n_parts, device="cuda:0"):
         rt[3, 3] = 1
         rts.append(rt)
     return {"scale": {"gt": [s[j] for j in range(n_parts)]}, "rt": {"gt": rts}}
+
+
+def similarity_ransac(src, tgt, cnt, sample_idx, device="cuda:0"):
+    """Batched estimateSimilarityTransform (lib/aligning.py:17-33) through ancsh_similarity_ransac:
+    src/tgt (nprob,nmax,3), cnt (nprob), sample_idx (nprob,niter,5) int (the reference's np.random.randint(n, size=5)
+    draws, each < cnt[p]).  Returns a dict of arrays: scale (nprob), rotation (nprob,3,3) [(U Vh)^T], translation (nprob,3),
+    inlier_ratio, inliers (nprob,nmax) bool, iters (nprob), status (nprob)."""
+    dev = torch.device(device)
+    s = torch.from_numpy(np.ascontiguousarray(src, np.float32)).to(dev)
+    t = torch.from_numpy(np.ascontiguousarray(tgt, np.float32)).to(dev)
+    c_host = np.ascontiguousarray(cnt, np.int32)
+    idx_host = np.ascontiguousarray(sample_idx, np.int32)
+    nprob, nmax, _ = s.shape
+    if t.shape != s.shape or c_host.shape != (nprob,) or idx_host.ndim != 3 or idx_host.shape[0] != nprob or idx_host.shape[2] != 5:
+        raise ValueError("similarity_ransac: src/tgt (nprob,nmax,3), cnt (nprob), sample_idx (nprob,niter,5)")
+    if (idx_host < 0).any() or (idx_host >= np.maximum(c_host, 1)[:, None, None]).any():
+        raise ValueError("similarity_ransac: sample indices must lie in [0, cnt)")
+    niter = idx_host.shape[1]
+    c = torch.from_numpy(c_host).to(dev)
+    idx = torch.from_numpy(idx_host).to(dev)
+    scale = torch.empty(nprob, dtype=torch.float64, device=dev)
+    R = torch.empty((nprob, 3, 3), dtype=torch.float64, device=dev)
+    tr = torch.empty((nprob, 3), dtype=torch.float64, device=dev)
+    ratio = torch.empty(nprob, dtype=torch.float64, device=dev)
+    inl = torch.empty((nprob, nmax), dtype=torch.uint8, device=dev)
+    iters = torch.empty(nprob, dtype=torch.int32, device=dev)
+    status = torch.empty(nprob, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.ancsh_similarity_ransac(nprob, nmax, niter, s.data_ptr(), t.data_ptr(), c.data_ptr(), idx.data_ptr(),
+                                                scale.data_ptr(), R.data_ptr(), tr.data_ptr(), ratio.data_ptr(), inl.data_ptr(),
+                                                iters.data_ptr(), status.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                   "ancsh_similarity_ransac")
+    return {"scale": scale.cpu().numpy(), "rotation": R.cpu().numpy(), "translation": tr.cpu().numpy(),
+            "inlier_ratio": ratio.cpu().numpy(), "inliers": inl.cpu().numpy().astype(bool), "iters": iters.cpu().numpy(),
+            "status": status.cpu().numpy()}
+
+
+def estimateSimilarityTransform(source, target, rt_pre=None, verbose=False, sample_idx=None, seed=0, device="cuda:0"):
+    """Drop-in for lib/aligning.py:17-33 estimateSimilarityTransform(source, target): (n,3) arrays ->
+    (Scales (3,), Rotation (3,3), Translation (3,), OutTransform (4,4)), or four Nones when the best inlier ratio is below
+    0.1.  `sample_idx` (100,5) replays given draws; otherwise they come from a seeded generator (the reference uses the
+    unseeded global np.random).  rt_pre (an externally supplied rotation, unused by every caller in the reference) is not
+    supported."""
+    if rt_pre is not None:
+        raise NotImplementedError("rt_pre is not supported")
+    source, target = np.asarray(source), np.asarray(target)
+    n = source.shape[0]
+    if sample_idx is None:
+        sample_idx = np.random.default_rng(seed).integers(0, n, size=(100, 5))
+    r = similarity_ransac(source[None], target[None], np.array([n]), np.asarray(sample_idx)[None], device)
+    if r["status"][0] != 0:
+        if verbose or r["inlier_ratio"][0] < 0.1:
+            print('[ WARN ] - Something is wrong. Small BestInlierRatio: ', r["inlier_ratio"][0])
+        return None, None, None, None
+    sf, Rot, tr = r["scale"][0], r["rotation"][0], r["translation"][0]
+    out = np.identity(4)
+    out[:3, :3] = sf * Rot.T                                                 # diag(Scales) @ Rotation.T (:616)
+    out[:3, 3] = tr
+    return np.array([sf, sf, sf]), Rot, tr, out

@@ -261,6 +261,19 @@ int ancsh_pose_sample_indices(unsigned long long seed, int stream_id, int nprob,
 int ancsh_umeyama(int nprob, int nmax, const float *src, const float *tgt, const int *cnt, double *scale, double *R,
                   double *t, void *stream);
 
+/* estimateSimilarityTransform (lib/aligning.py:17-33): per problem the thresholds of set_config
+ * (:88-103: PassT = max(|T|/|S|, |S|/|T|) of the mean point norms, StopT = PassT / 100), the 5-point Umeyama RANSAC of
+ * getRANSACInliers (:485-507) over niter <= 256 hypotheses whose samples are idx (nprob,niter,5) (the reference draws them
+ * from np.random.randint), evaluateModel's bookkeeping (:540-547, incl. np.count_nonzero over the inlier INDICES, i.e.
+ * point 0 never counts, strict `>` on the ratio, stop once BestResidual < StopT), and the Umeyama refit on the best
+ * hypothesis' inliers.  src/tgt (nprob,nmax,3) f32, cnt (nprob) ->
+ * scale (nprob), R (nprob,9) [reference convention (U Vh)^T], t (nprob,3), inlier_ratio (nprob) = BestInlierRatio,
+ * inliers (nprob,nmax) bytes = BestInlierIdx as a mask, iters_run (nprob), status (nprob): 0, ANCSH_POSE_EMPTY_PART, or
+ * ANCSH_POSE_NO_INLIERS when BestInlierRatio < 0.1 (the reference returns four Nones, :25-27) -> NaN model. */
+int ancsh_similarity_ransac(int nprob, int nmax, int niter, const float *src, const float *tgt, const int *cnt,
+                            const int *idx, double *scale, double *R, double *t, double *inlier_ratio,
+                            unsigned char *inliers, int *iters_run, int *status, void *stream);
+
 /* ---- metric kernels behind the pose stage -------------------------------------------------------- */
 
 /* Amodal box extents of the predicted parts (evaluation/compute_miou.py:187,196-199): for cloud b and part j,

@@ -239,3 +239,55 @@ def estimate_similarity_umeyama(SourceHom, TargetHom):
     OutTransform[:3, :3] = np.diag(Scales) @ Rotation.T
     OutTransform[:3, 3] = Translation
     return Scales, Rotation, Translation, OutTransform
+
+
+# ---------------------------------------------------------------- lib/aligning.py:17-33, 88-103, 485-507, 540-547
+# estimateSimilarityTransform: the NOCS-style per-part baseline (5-point Umeyama RANSAC, <= 100 iterations, thresholds from
+# the source/target norm ratio, Umeyama refit on the best hypothesis' inliers).  SURVEY 8(a) row a-21.  `sample_idx`
+# (MaxIterations, 5) replaces the reference's unseeded np.random.randint(n, size=5) draws.
+def set_config(source, target):
+    SourceHom = np.transpose(np.hstack([source, np.ones([source.shape[0], 1])]))
+    TargetHom = np.transpose(np.hstack([target, np.ones([target.shape[0], 1])]))
+    TargetNorm = np.mean(np.linalg.norm(target, axis=1))
+    SourceNorm = np.mean(np.linalg.norm(source, axis=1))
+    RatioTS = TargetNorm / SourceNorm
+    RatioST = SourceNorm / TargetNorm
+    PassT = RatioST if RatioST > RatioTS else RatioTS
+    return SourceHom, TargetHom, PassT, PassT / 100
+
+
+def evaluate_model(OutTransform, SourceHom, TargetHom, PassThreshold):
+    Diff = TargetHom - np.matmul(OutTransform, SourceHom)
+    ResidualVec = np.linalg.norm(Diff[:3, :], axis=0)
+    Residual = np.linalg.norm(ResidualVec)
+    InlierIdx = np.where(ResidualVec < PassThreshold)
+    nInliers = np.count_nonzero(InlierIdx)          # counts the non-zero INDICES (:545): point 0 is never counted
+    return Residual, nInliers / SourceHom.shape[1], InlierIdx[0]
+
+
+def get_ransac_inliers(SourceHom, TargetHom, sample_idx, PassThreshold, StopThreshold):
+    BestResidual, BestInlierRatio = 1e10, 0
+    BestInlierIdx = np.arange(SourceHom.shape[1])
+    iters = 0
+    for RandIdx in np.asarray(sample_idx):
+        iters += 1
+        _, _, _, OutTransform = estimate_similarity_umeyama(SourceHom[:, RandIdx], TargetHom[:, RandIdx])
+        Residual, InlierRatio, InlierIdx = evaluate_model(OutTransform, SourceHom, TargetHom, PassThreshold)
+        if InlierRatio > BestInlierRatio:
+            BestResidual, BestInlierRatio, BestInlierIdx = Residual, InlierRatio, InlierIdx
+        if BestResidual < StopThreshold:
+            break
+    return BestInlierIdx, BestInlierRatio, iters
+
+
+def estimate_similarity_transform(source, target, sample_idx, return_info=False):
+    """(Scales, Rotation, Translation, OutTransform) or four Nones when the best inlier ratio is below 0.1 (:25-27)."""
+    source, target = np.asarray(source, np.float64), np.asarray(target, np.float64)
+    SourceHom, TargetHom, PassT, StopT = set_config(source, target)
+    idx, ratio, iters = get_ransac_inliers(SourceHom, TargetHom, sample_idx, PassT, StopT)
+    info = {"inlier_idx": idx, "inlier_ratio": ratio, "iters": iters, "pass_t": PassT}
+    if ratio < 0.1:
+        out = (None, None, None, None)
+    else:
+        out = estimate_similarity_umeyama(SourceHom[:, idx], TargetHom[:, idx])
+    return out + (info,) if return_info else out
