@@ -58,7 +58,7 @@ class Pred(ctypes.Structure):
 
 WS_FIELDS = ("fps_idx1", "l1_xyz", "fps_idx2", "l2_xyz", "ball_idx1", "ball_cnt1", "ball_idx2", "ball_cnt2",
              "l1_points", "l2_points", "l3_points", "fp1_bias", "l2_points_fp", "l1_points_fp", "interp3", "raw_heads",
-             "total_bytes")
+             "nn_idx2", "nn_w2", "nn_idx3", "nn_w3", "total_bytes")
 
 
 class WsLayout(ctypes.Structure):

@@ -158,8 +158,21 @@ __global__ void __launch_bounds__(256) cloud_bias_kernel(const float *__restrict
     for (int k = threadIdx.x; k < cin; k += blockDim.x) s_f[k] = feat[(size_t)b * cin + k];
     __syncthreads();
     for (int o = threadIdx.x; o < cout_pad; o += blockDim.x) {
+        // the FMA chain is serial in k (fixed summation order); the loads are not: 32 of them in flight per thread
+        // (4 in flight left the kernel waiting on L2 latency: 0.11 ms for a 0.13 GFLOP matvec batch, now 0.06 ms and
+        // L2-bandwidth bound -- every block streams the whole 1 MB matrix; grouping 4 clouds per block to cut that
+        // traffic was measured slower, 64 blocks are too few to hide the load latency)
         float acc = 0.f;
-        for (int k = 0; k < cin; ++k) acc = fmaf(s_f[k], __ldg(W + (size_t)k * cout_pad + o), acc);
+        const float *w = W + o;
+        int k = 0;
+        for (; k + 32 <= cin; k += 32) {
+            float wv[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) wv[i] = __ldg(w + (size_t)(k + i) * cout_pad);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc = fmaf(s_f[k + i], wv[i], acc);
+        }
+        for (; k < cin; ++k) acc = fmaf(s_f[k], __ldg(w + (size_t)k * cout_pad), acc);
         out[(size_t)b * cout_pad + o] = acc + bias[o];
     }
 }
@@ -375,10 +388,12 @@ static int fp_launch(const FpArgs &a0, int B, cudaStream_t st)
 // Tensor-core path of the point-wise stages: interpolation and head activations as light kernels around
 // chain_tc_kernel (net_tc.cu)
 // ================================================================================================
-// three_nn + inverse-distance weights + three_interpolate -> (B,n1,C2) in global memory (pointnet_util.py:217-223)
+// three_nn + inverse-distance weights + three_interpolate -> (B,n1,C2) in global memory (pointnet_util.py:217-223);
+// the (idx, weight) tables are pure geometry and are also written out for the second network of the pipeline
 __global__ void __launch_bounds__(NT) fp_interp_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2,
                                                        const float *__restrict__ points2, int n1, int m2, int C2,
-                                                       float *__restrict__ out)
+                                                       float *__restrict__ out, int *__restrict__ idx_out,
+                                                       float *__restrict__ w_out)
 {
     constexpr int TMI = 64, PARTS = NT / TMI;
     extern __shared__ __align__(16) float s_known[];   // m2*3
@@ -416,6 +431,9 @@ __global__ void __launch_bounds__(NT) fp_interp_kernel(const float *__restrict__
             three_weights(best.d1, best.d2, best.d3, w1, w2, w3);
             s_w[row * 3 + 0] = w1; s_w[row * 3 + 1] = w2; s_w[row * 3 + 2] = w3;
             s_i[row * 3 + 0] = best.i1; s_i[row * 3 + 1] = best.i2; s_i[row * 3 + 2] = best.i3;
+            const size_t o = ((size_t)b * n1 + row0 + row) * 3;          // geometry tables for a second network (fp_blend_kernel)
+            w_out[o] = w1; w_out[o + 1] = w2; w_out[o + 2] = w3;
+            idx_out[o] = best.i1; idx_out[o + 1] = best.i2; idx_out[o + 2] = best.i3;
         }
     }
     __syncthreads();
@@ -433,6 +451,45 @@ __global__ void __launch_bounds__(NT) fp_interp_kernel(const float *__restrict__
             x.z = interp3_unfused(u.z, v.z, w.z, w1, w2, w3);
             x.w = interp3_unfused(u.w, v.w, w.w, w1, w2, w3);
             *reinterpret_cast<float4 *>(o + c4 * 4) = x;
+        }
+    }
+}
+
+// three_interpolate (tf_interpolate.cpp:107-127) -> (B,n1,C2) rows in global memory.  One warp per row, RB rows per pass
+// so that 3 * RB 16-byte loads are in flight per lane before the first blend.
+__global__ void __launch_bounds__(NT) fp_blend_kernel(const float *__restrict__ points2, const int *__restrict__ idx,
+                                                      const float *__restrict__ wgt, int n1, int m2, int C2,
+                                                      float *__restrict__ out)
+{
+    constexpr int TMI = 64, RB = 4;
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long row0 = (long)blockIdx.x * TMI;
+    const float *src = points2 + (size_t)b * m2 * C2;
+    for (int r = warp * RB; r < TMI; r += (NT / 32) * RB) {
+        const size_t g = ((size_t)b * n1 + row0 + r) * 3;
+        int id[RB][3];
+        float w[RB][3];
+#pragma unroll
+        for (int j = 0; j < RB; ++j)
+#pragma unroll
+            for (int t = 0; t < 3; ++t) { id[j][t] = __ldg(idx + g + 3 * j + t); w[j][t] = __ldg(wgt + g + 3 * j + t); }
+        for (int c4 = lane; c4 < C2 / 4; c4 += 32) {
+            float4 u[RB], v[RB], x[RB];
+#pragma unroll
+            for (int j = 0; j < RB; ++j) {
+                u[j] = ldg4(src + (size_t)id[j][0] * C2 + c4 * 4);
+                v[j] = ldg4(src + (size_t)id[j][1] * C2 + c4 * 4);
+                x[j] = ldg4(src + (size_t)id[j][2] * C2 + c4 * 4);
+            }
+#pragma unroll
+            for (int j = 0; j < RB; ++j) {
+                float4 y;
+                y.x = interp3_unfused(u[j].x, v[j].x, x[j].x, w[j][0], w[j][1], w[j][2]);
+                y.y = interp3_unfused(u[j].y, v[j].y, x[j].y, w[j][0], w[j][1], w[j][2]);
+                y.z = interp3_unfused(u[j].z, v[j].z, x[j].z, w[j][0], w[j][1], w[j][2]);
+                y.w = interp3_unfused(u[j].w, v[j].w, x[j].w, w[j][0], w[j][1], w[j][2]);
+                *reinterpret_cast<float4 *>(out + ((size_t)b * n1 + row0 + r + j) * C2 + c4 * 4) = y;
+            }
         }
     }
 }
@@ -511,6 +568,10 @@ extern "C" int ancsh_net_plan(const ancsh_net_t *net, int B, int N, ancsh_ws_lay
     L->l1_points_fp = take(b * m1 * net->fp2[1].cout * 4);
     L->interp3 = take(net->use_tensor_cores ? b * N * net->fp2[1].cout * 4 : 0);
     L->raw_heads = take(net->use_tensor_cores ? b * N * 64 * 4 * 2 : 0);
+    L->nn_idx2 = take(net->use_tensor_cores ? b * m1 * 3 * 4 : 0);
+    L->nn_w2 = take(net->use_tensor_cores ? b * m1 * 3 * 4 : 0);
+    L->nn_idx3 = take(net->use_tensor_cores ? b * N * 3 * 4 : 0);
+    L->nn_w3 = take(net->use_tensor_cores ? b * N * 3 * 4 : 0);
     L->total_bytes = off;
     return ANCSH_OK;
 }
@@ -534,7 +595,8 @@ static int net_forward_impl(const ancsh_net_t *net, int B, int N, const float *P
     const bool shared = geo_net != nullptr && geo_ws != nullptr;
     if (shared) {
         if (geo_net->npoint1 != net->npoint1 || geo_net->npoint2 != net->npoint2 || geo_net->nsample1 != net->nsample1 ||
-            geo_net->nsample2 != net->nsample2 || geo_net->radius1 != net->radius1 || geo_net->radius2 != net->radius2)
+            geo_net->nsample2 != net->nsample2 || geo_net->radius1 != net->radius1 || geo_net->radius2 != net->radius2 ||
+            geo_net->use_tensor_cores != net->use_tensor_cores)       // the three_nn tables exist on the tensor-core path only
             return ANCSH_ERR_INVALID_ARG;
         if ((rc = ancsh_net_plan(geo_net, B, N, &GL)) != ANCSH_OK) return rc;
         gws = (char *)const_cast<void *>(geo_ws);
@@ -663,7 +725,13 @@ static int net_forward_impl(const ancsh_net_t *net, int B, int N, const float *P
             float *interp2 = (float *)(ws + L.interp3);
             const int C2 = net->fp1[1].cout;
             if (m1 % 64 != 0 || (size_t)m1 * C2 > (size_t)N * net->fp2[1].cout) return ANCSH_ERR_UNSUPPORTED;
-            fp_interp_kernel<<<dim3(m1 / 64, B), NT, (size_t)m2 * 3 * sizeof(float), st>>>(l1_xyz, l2_xyz, l2_fp, m1, m2, C2, interp2);
+            int *nn_i = (int *)(gws + GL.nn_idx2);
+            float *nn_w = (float *)(gws + GL.nn_w2);
+            if (!shared)
+                fp_interp_kernel<<<dim3(m1 / 64, B), NT, (size_t)m2 * 3 * sizeof(float), st>>>(l1_xyz, l2_xyz, l2_fp, m1, m2, C2,
+                                                                                            interp2, nn_i, nn_w);
+            else
+                fp_blend_kernel<<<dim3(m1 / 64, B), NT, 0, st>>>(l2_fp, nn_i, nn_w, m1, m2, C2, interp2);
             ANCSH_CHECK_LAUNCH();
             ChainTcArgs c{};
             c.X1 = interp2; c.C1 = C2; c.X2 = l1_points; c.C2 = net->sa1[2].cout; c.rows_per_cloud = m1;
@@ -693,7 +761,13 @@ static int net_forward_impl(const ancsh_net_t *net, int B, int N, const float *P
             if (N % 64 != 0 || C2 % 8 != 0 || net->nocs_heads.cout_pad != 64 || net->joint_heads.cout_pad != 64 ||
                 11 * net->n_parts + 1 > 64)
                 return ANCSH_ERR_UNSUPPORTED;
-            fp_interp_kernel<<<dim3(N / 64, B), NT, (size_t)m1 * 3 * sizeof(float), st>>>(P, l1_xyz, l1_fp, N, m1, C2, interp3);
+            int *nn_i = (int *)(gws + GL.nn_idx3);
+            float *nn_w = (float *)(gws + GL.nn_w3);
+            if (!shared)
+                fp_interp_kernel<<<dim3(N / 64, B), NT, (size_t)m1 * 3 * sizeof(float), st>>>(P, l1_xyz, l1_fp, N, m1, C2, interp3,
+                                                                                           nn_i, nn_w);
+            else
+                fp_blend_kernel<<<dim3(N / 64, B), NT, 0, st>>>(l1_fp, nn_i, nn_w, N, m1, C2, interp3);
             ANCSH_CHECK_LAUNCH();
             ChainTcArgs c{};
             c.X1 = interp3; c.C1 = C2; c.X2 = P; c.C2 = 3; c.rows_per_cloud = N; c.bias0 = nullptr; c.bias0_stride = 0;

@@ -142,6 +142,10 @@ typedef struct {
     size_t l1_points_fp; /* f32 (B,npoint1,128) fa_layer2 output */
     size_t interp3;      /* f32 (B,N,128) interpolated features of fa_layer3 (tensor-core path only) */
     size_t raw_heads;    /* f32 2 x (B,N,64) raw linear outputs of nocs_net / joint_net (tensor-core path only) */
+    size_t nn_idx2;      /* int32 (B,npoint1,3) three_nn of l1_xyz in l2_xyz (fa_layer2); geometry, shared like the FPS indices */
+    size_t nn_w2;        /* f32   (B,npoint1,3) inverse-distance weights (pointnet_util.py:219-222) */
+    size_t nn_idx3;      /* int32 (B,N,3) three_nn of P in l1_xyz (fa_layer3) */
+    size_t nn_w3;        /* f32   (B,N,3) */
     size_t total_bytes;
 } ancsh_ws_layout_t;
 

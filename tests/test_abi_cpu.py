@@ -35,7 +35,7 @@ def test_struct_sizes_match_header():
     from articulated_pose_b200 import _lib
     assert ctypes.sizeof(_lib.Layer) == 48
     assert ctypes.sizeof(_lib.Pred) == 88
-    assert ctypes.sizeof(_lib.WsLayout) == 17 * 8
+    assert ctypes.sizeof(_lib.WsLayout) == 21 * 8
     assert ctypes.sizeof(_lib.Net) == 40 + 22 * 48
 
 
