@@ -127,6 +127,7 @@ ancsh_umeyama = _sig("ancsh_umeyama", [c_int, c_int, vp, vp, vp, vp, vp, vp, vp]
 
 ancsh_similarity_ransac = _sig("ancsh_similarity_ransac", [c_int, c_int, c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp])
 ancsh_amodal_extent = _sig("ancsh_amodal_extent", [c_int, c_int, c_int, vp, vp, vp, vp, vp])
+ancsh_joint_vote = _sig("ancsh_joint_vote", [c_int, c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp, ctypes.c_float, vp, vp, vp, vp])
 ancsh_box_iou_3d = _sig("ancsh_box_iou_3d", [c_int, c_int, vp, vp, vp, vp, vp, vp])
 
 NET_STAGES = ("fps1", "fps2", "ball1", "sa1", "ball2", "sa2", "sa3", "fp1", "fp2", "fp3_heads")

@@ -156,6 +156,90 @@ __global__ void __launch_bounds__(MT) box_iou_kernel(int nres, const double *__r
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// joint parameter voting (evaluation/eval_joint_params.py:178-190).  Per cloud and joint j = 1..K-1 over the points
+// whose argmax(index_per_point) == j:
+//     joint axis  = median(joint_axis_per_point[idx], axis=0)
+//     joint point = median((gn + unitvec * (1 - heatmap) * thres_r)[idx], axis=0)
+// with gn[i] = gocs_per_point[i, 3c:3c+3], c = argmax(instance_per_point[i]) (:160-166; gn_width == 3: gocs[i, :3]).
+// All f32 like NumPy on the f32 h5 arrays: ((u * (1 - h)) * 0.2f) then the sum, un-contracted; np.median = middle element or
+// the f32 mean (a + b) / 2 of the two middle ones; an empty joint gives NaN (np.median of an empty slice).
+// One CTA per cloud; the six value columns of a joint are sorted together by a bitonic network in shared memory.
+// ---------------------------------------------------------------------------------------------------------------------
+struct VoteArgs {
+    int N, K, gn_width, n_index;
+    const float *gocs, *mask, *unitvec, *heatmap, *joint_axis, *index;
+    float thres_r;
+    float *axis_out, *pt_out;
+    int *count;
+};
+
+__global__ void __launch_bounds__(MT) joint_vote_kernel(const VoteArgs a)
+{
+    extern __shared__ float s_val[];                    // 6 * npow2
+    __shared__ int s_n;
+    const int N = a.N, K = a.K, b = blockIdx.x, tid = threadIdx.x;
+    int npow2 = 1;
+    while (npow2 < N) npow2 <<= 1;
+    for (int j = 1; j < K; ++j) {
+        __syncthreads();
+        if (tid == 0) s_n = 0;
+        for (int i = tid; i < 6 * npow2; i += MT) s_val[i] = __int_as_float(0x7f800000);   // +inf padding sorts last
+        __syncthreads();
+        for (int i = tid; i < N; i += MT) {
+            const size_t g = (size_t)b * N + i;
+            const float *q = a.index + g * a.n_index;
+            int jc = 0;
+            float bv = q[0];
+            for (int k = 1; k < a.n_index; ++k)
+                if (q[k] > bv) { bv = q[k]; jc = k; }
+            if (jc != j) continue;
+            int c = 0;
+            if (a.gn_width != 3) {
+                const float *m = a.mask + g * K;
+                float mv = m[0];
+                for (int k = 1; k < K; ++k)
+                    if (m[k] > mv) { mv = m[k]; c = k; }
+            }
+            const float *gn = a.gocs + g * a.gn_width + 3 * c;
+            const float om = __fsub_rn(1.0f, a.heatmap[g]);
+            const int p = atomicAdd(&s_n, 1);           // order is irrelevant: the columns are sorted independently
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                s_val[d * npow2 + p] = a.joint_axis[g * 3 + d];
+                const float off = __fmul_rn(__fmul_rn(a.unitvec[g * 3 + d], om), a.thres_r);
+                s_val[(3 + d) * npow2 + p] = __fadd_rn(gn[d], off);
+            }
+        }
+        __syncthreads();
+        const int nj = s_n;
+        for (int k = 2; k <= npow2; k <<= 1)
+            for (int jj = k >> 1; jj > 0; jj >>= 1) {
+                for (int t = tid; t < 6 * npow2; t += MT) {
+                    const int c = t / npow2, i = t - c * npow2, ixj = i ^ jj;
+                    if (ixj > i) {
+                        float *v = s_val + c * npow2;
+                        const bool up = (i & k) == 0;
+                        const float x = v[i], y = v[ixj];
+                        if ((x > y) == up) { v[i] = y; v[ixj] = x; }
+                    }
+                }
+                __syncthreads();
+            }
+        if (tid < 6) {
+            const float *v = s_val + tid * npow2;
+            float med;
+            if (nj == 0) med = __int_as_float(0x7fc00000);
+            else if (nj & 1) med = v[nj / 2];
+            else med = __fdiv_rn(__fadd_rn(v[nj / 2 - 1], v[nj / 2]), 2.0f);
+            float *o = (tid < 3 ? a.axis_out : a.pt_out) + ((size_t)b * (K - 1) + (j - 1)) * 3 + (tid % 3);
+            *o = med;
+        }
+        if (tid == 0) a.count[(size_t)b * (K - 1) + (j - 1)] = nj;
+    }
+}
+
 }  // namespace
 
 extern "C" int ancsh_amodal_extent(int B, int N, int K, const float *nocs, const float *mask, float *extent, int *count,
@@ -176,6 +260,25 @@ extern "C" int ancsh_box_iou_3d(int npairs, int nres, const double *bbox1, const
     if (npairs == 0) return ANCSH_OK;
     if (!bbox1 || !bbox2 || !iou) return ANCSH_ERR_INVALID_ARG;
     box_iou_kernel<<<npairs, MT, 0, (cudaStream_t)stream>>>(nres, bbox1, bbox2, iou, inter, uni);
+    ANCSH_CHECK_LAUNCH();
+    return ANCSH_OK;
+}
+
+extern "C" int ancsh_joint_vote(int B, int N, int K, int gn_width, int n_index, const float *gocs, const float *mask,
+                                const float *unitvec, const float *heatmap, const float *joint_axis, const float *index_per_point,
+                                float thres_r, float *axis_out, float *pt_out, int *count, void *stream)
+{
+    if (B < 0 || N <= 0 || N > 8192 || K < 2 || K > 64 || n_index < 1 || (gn_width != 3 && gn_width != 3 * K))
+        return ANCSH_ERR_INVALID_ARG;
+    if (B == 0) return ANCSH_OK;
+    if (!gocs || !mask || !unitvec || !heatmap || !joint_axis || !index_per_point || !axis_out || !pt_out || !count)
+        return ANCSH_ERR_INVALID_ARG;
+    int npow2 = 1;
+    while (npow2 < N) npow2 <<= 1;
+    const size_t smem = (size_t)6 * npow2 * sizeof(float);
+    ANCSH_CUDA(cudaFuncSetAttribute(joint_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VoteArgs a{N, K, gn_width, n_index, gocs, mask, unitvec, heatmap, joint_axis, index_per_point, thres_r, axis_out, pt_out, count};
+    joint_vote_kernel<<<B, MT, smem, (cudaStream_t)stream>>>(a);
     ANCSH_CHECK_LAUNCH();
     return ANCSH_OK;
 }

@@ -94,3 +94,31 @@ def part_ious(nocs_pred, mask_pred, rotation, translation, scale, rt_gt, s_gt, e
     iou = iou_3d_batch(gt.reshape(-1, 8, 3), np.nan_to_num(pr).reshape(-1, 8, 3), nres, device).reshape(B, K)
     iou[~ok] = np.nan
     return iou, ext
+
+
+def joint_vote(gocs, mask_pred, unitvec_pred, heatmap_pred, orient_pred, index_per_point, thres_r=0.2, device="cuda:0"):
+    """Joint parameter voting of evaluation/eval_joint_params.py:178-190 for a batch: gocs (B,N,3K or 3) [h5
+    'gocs_per_point'], mask_pred (B,N,K) ['instance_per_point'], unitvec_pred (B,N,3), heatmap_pred (B,N,1) or (B,N),
+    orient_pred (B,N,3) ['joint_axis_per_point'], index_per_point (B,N,J).  Returns per cloud the reference's
+    `joints['pred']` list: [{'l': median axis, 'p': median joint point} for j in 1..K-1] (f32; NaN where a joint has no
+    voters), plus the voter counts (B,K-1)."""
+    dev = torch.device(device)
+
+    def dv(x):
+        t = x if torch.is_tensor(x) else torch.from_numpy(np.ascontiguousarray(x, np.float32))
+        return t.to(dev).contiguous()
+    g, m, u, h, o, ix = (dv(x) for x in (gocs, mask_pred, unitvec_pred, heatmap_pred, orient_pred, index_per_point))
+    B, N, K = m.shape
+    if g.shape[:2] != (B, N) or g.shape[2] not in (3, 3 * K) or tuple(u.shape) != (B, N, 3) or tuple(o.shape) != (B, N, 3) or \
+            h.numel() != B * N or ix.shape[:2] != (B, N) or any(t.dtype != torch.float32 for t in (g, m, u, h, o, ix)):
+        raise ValueError("joint_vote: f32 arrays gocs (B,N,3K|3), mask (B,N,K), unitvec/orient (B,N,3), heatmap (B,N[,1]), index (B,N,J)")
+    axis = torch.empty((B, K - 1, 3), dtype=torch.float32, device=dev)
+    pt = torch.empty((B, K - 1, 3), dtype=torch.float32, device=dev)
+    cnt = torch.empty((B, K - 1), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.ancsh_joint_vote(B, N, K, g.shape[2], ix.shape[2], g.data_ptr(), m.data_ptr(), u.data_ptr(), h.data_ptr(),
+                                         o.data_ptr(), ix.data_ptr(), float(thres_r), axis.data_ptr(), pt.data_ptr(),
+                                         cnt.data_ptr(), torch.cuda.current_stream().cuda_stream), "ancsh_joint_vote")
+    axis, pt = axis.cpu().numpy(), pt.cpu().numpy()
+    joints = [[{"l": axis[b, j], "p": pt[b, j]} for j in range(K - 1)] for b in range(B)]
+    return joints, cnt.cpu().numpy()

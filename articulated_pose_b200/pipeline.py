@@ -126,15 +126,21 @@ class AncshPipeline:
         pending = [None] * self.N_SLOTS
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream()
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            copy_stream = self._copy_stream
 
             def drain(slot):
                 if pending[slot] is None:
                     return
                 i, out = pending[slot]
-                main.wait_event(self._slot(B, N, slot)["pose_done"])
-                for k, v in out.items():
-                    bufs[slot]["hpose"][k].copy_(v, non_blocking=True)
-                bufs[slot]["copied"].record(main)
+                # D2H on its own stream behind the slot's pose stage only: on the main stream the copy would queue behind
+                # the forwards of the newer batches and the host would fall a whole pipeline depth behind the device
+                copy_stream.wait_event(self._slot(B, N, slot)["pose_done"])
+                with torch.cuda.stream(copy_stream):
+                    for k, v in out.items():
+                        bufs[slot]["hpose"][k].copy_(v, non_blocking=True)
+                    bufs[slot]["copied"].record(copy_stream)
                 bufs[slot]["copied"].synchronize()
                 h = {k: v.numpy().copy() for k, v in bufs[slot]["hpose"].items()}
                 results[i] = unpack_results(h, self.K) if unpack else h

@@ -326,6 +326,9 @@ def main():
         return pipe.net.forward(P_host, copy=False)
     for _ in range(2):
         e2e_call()
+    if full:   # warm-up of the call that is timed below: run_many pins its staging buffers and creates its copy stream on first use
+        pipe.run_many([(P_host, jc_host)] * max(args.warmup, 3))
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
@@ -363,8 +366,13 @@ def main():
     peak = peaks["bf16_tflops_sustained"]
     n_fwd = 2 if (full and two_nets) else 1
     fwd_ms = sum(stage_ms.values())
+    # dram__bytes_read.sum + dram__bytes_write.sum of that launch from the committed ncu capture of this same command
+    # (profiles/r01u_chain_traffic.csv: batch 256, nsample 32, eyeglasses); null for any other configuration
+    NCU_TRAFFIC = {"sa1": 19673088 + 18748160, "sa2": 24419584 + 352256}
+    ncu_cfg = args.precision == "f16x3" and B == 256 and N == 1024 and args.nsample == 32 and args.category == "eyeglasses"
     roofline = {"bound": "tensor", "kernel": ("chain2_kernel<SA>" if args.precision == "f16x3" else "sa_kernel<128>") + " (%s, ANCSH net)" % dom,
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": NCU_TRAFFIC[dom] if ncu_cfg else None,
+                "traffic_source": "profiles/r01u_chain_traffic.csv (ncu dram bytes of this launch, same command)" if ncu_cfg else None,
                 "peak_source": peaks["source"] + " bf16 sustained; kernel duration from per-stage CUDA events of a serialized pass in the same run",
                 "avg_launch_ms": stage_ms[dom], "flops_per_launch": fl[dom],
                 "stage_ms": {k: round(v, 4) for k, v in {**stage_ms, **extra_ms}.items()},

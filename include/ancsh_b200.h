@@ -295,6 +295,16 @@ int ancsh_amodal_extent(int B, int N, int K, const float *nocs, const float *mas
 int ancsh_box_iou_3d(int npairs, int nres, const double *bbox1, const double *bbox2, double *iou, int *inter, int *uni,
                      void *stream);
 
+/* Joint parameter voting (evaluation/eval_joint_params.py:178-190): for cloud b and joint j = 1..K-1, over
+ * the points with argmax(index_per_point) == j (first maximum; index_per_point is n_index wide -- 3 even for the 4-part
+ * drawer, lib/architecture.py:129), axis_out[b,j-1,:] = median(joint_axis_per_point), pt_out[b,j-1,:] =
+ * median(gn + unitvec * (1 - heatmap) * thres_r) with gn[i] = gocs[i, 3c:3c+3], c = argmax(mask[i]) (gn_width == 3K) or
+ * gocs[i, :3] (gn_width == 3), all in f32 like NumPy on the f32 h5 arrays.  count (B,K-1) = voters; none -> NaN.
+ * gocs (B,N,gn_width), mask (B,N,K), unitvec / joint_axis (B,N,3), heatmap (B,N,1), index_per_point (B,N,n_index) f32. */
+int ancsh_joint_vote(int B, int N, int K, int gn_width, int n_index, const float *gocs, const float *mask,
+                     const float *unitvec, const float *heatmap, const float *joint_axis, const float *index_per_point,
+                     float thres_r, float *axis_out, float *pt_out, int *count, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,3 +84,26 @@ def part_boxes(extent, s, r, t):
     bb = get_3d_bbox(extent, shift=np.array([1 / 2, 1 / 2, 1 / 2])).transpose() * s
     rt = compose_rt(np.asarray(r), np.asarray(t))
     return np.dot(bb, rt[:3, :3].T) + rt[:3, 3]
+
+
+def joint_vote(gocs, mask_pred, unitvec_pred, heatmap_pred, orient_pred, index_per_point, num_parts, thres_r=0.2):
+    """evaluation/eval_joint_params.py:139-140,153-166,178-190 for one cloud (the script body is not importable: this is
+    a line-by-line restatement of its NumPy calls, "parity unpinned" beyond that).  Returns the list `joints['pred']`:
+    [{'l': median axis (3,), 'p': median joint point (3,)} for j in 1..num_parts-1]."""
+    joint_cls_pred = np.argmax(index_per_point, axis=1)
+    cls_per_pt_pred = np.argmax(mask_pred, axis=1)
+    gn_final = np.zeros((gocs.shape[0], 3), gocs.dtype)
+    for j in range(num_parts):
+        idx = np.where(cls_per_pt_pred == j)[0]
+        gn_final[idx, :] = gocs[idx, :3] if gocs.shape[1] == 3 else gocs[idx, j * 3:j * 3 + 3]
+    out = []
+    with np.errstate(all="ignore"):
+        for j in range(1, num_parts):
+            offset = unitvec_pred * (1 - heatmap_pred.reshape(-1, 1)) * thres_r
+            joint_pts = gn_final + offset
+            idx = np.where(joint_cls_pred == j)[0]
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                out.append({"l": np.median(orient_pred[idx], axis=0), "p": np.median(joint_pts[idx], axis=0)})
+    return out

@@ -61,3 +61,22 @@ def test_live_reference_iou_and_inside():
         assert float(d3.iou_3d(a, b, nres=23)) == float(iou_np.iou_3d(a, b, 23))
         pts = rng.uniform(-1, 1, (500, 3))
         np.testing.assert_array_equal(d3.pts_inside_box(pts, b).reshape(-1), iou_np.pts_inside_box(pts, b))
+
+
+def test_joint_vote_restatement_on_teacher_predictions():
+    """With teacher predictions the voted axis is the GT axis up to the injected noise and every joint has voters."""
+    from articulated_pose_b200 import synthetic
+    cloud = synthetic.make_cloud(3)
+    pred = synthetic.teacher_predictions(cloud)
+    K = 3
+    N = cloud["P"].shape[0]
+    index = np.eye(3, dtype=np.float32)[cloud["joint_cls_gt"]]
+    gocs = np.tile(cloud["nocs_gt"], (1, K)).astype(np.float32)
+    unit = np.zeros((N, 3), np.float32); heat = np.ones((N, 1), np.float32)
+    out = iou_np.joint_vote(gocs, pred["W"], unit, heat, pred["joint_axis_per_point"], index, K)
+    assert len(out) == K - 1
+    for j in range(1, K):
+        sel = cloud["joint_cls_gt"] == j
+        assert sel.sum() > 0
+        np.testing.assert_array_equal(out[j - 1]["l"], np.median(pred["joint_axis_per_point"][sel], axis=0))
+        assert out[j - 1]["p"].dtype == np.float32

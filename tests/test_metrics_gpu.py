@@ -105,3 +105,37 @@ def test_part_ious_of_exact_predictions_are_high():
     iou, ext = metrics.part_ious(nocs, W, rt_gt[:, :, :3, :3], rt_gt[:, :, :3, 3], s_gt, rt_gt, s_gt, ext_gt)
     np.testing.assert_array_equal(ext, ext_gt.astype(np.float32))
     assert (iou > 0.97).all(), iou
+
+
+@pytest.mark.parametrize("cat,gn3", [("eyeglasses", False), ("drawer", False), ("eyeglasses", True)])
+def test_joint_vote_matches_oracle_bit_exact(cat, gn3):
+    """ancsh_joint_vote on the network's own outputs (random-weight network: every branch of the argmaxes is exercised)
+    against the NumPy restatement of eval_joint_params.py:178-190 -- medians are order statistics: bit-exact."""
+    from articulated_pose_b200 import metrics, synthetic, weights
+    from articulated_pose_b200.network import AncshNet
+    from oracle import iou_np
+    ids = range(70, 74)
+    P, clouds = synthetic.make_batch(ids, cat)
+    K = clouds[0]["n_parts"]
+    pred = AncshNet(weights.synthetic_weights(K), K, nsample=32).forward(P)
+    gocs = pred["gocs_per_point"][:, :, :3].copy() if gn3 else pred["gocs_per_point"]
+    # a random-weight network votes for one joint class only: scatter the votes (seeded) so that every joint has voters
+    rng = np.random.default_rng(8)
+    pred["index_per_point"] = rng.dirichlet(np.ones(3), size=pred["index_per_point"].shape[:2]).astype(np.float32)
+    pred["W"] = rng.dirichlet(np.ones(K), size=pred["W"].shape[:2]).astype(np.float32)
+    joints, cnt = metrics.joint_vote(gocs, pred["W"], pred["unitvec_per_point"], pred["heatmap_per_point"],
+                                     pred["joint_axis_per_point"], pred["index_per_point"])
+    total = 0
+    for b in range(len(clouds)):
+        ref = iou_np.joint_vote(gocs[b], pred["W"][b], pred["unitvec_per_point"][b], pred["heatmap_per_point"][b],
+                                pred["joint_axis_per_point"][b], pred["index_per_point"][b], K)
+        jc = np.argmax(pred["index_per_point"][b], axis=1)
+        for j in range(K - 1):
+            assert cnt[b, j] == int((jc == j + 1).sum())
+            total += cnt[b, j]
+            np.testing.assert_array_equal(joints[b][j]["l"], ref[j]["l"])          # NaN == NaN for empty joints
+            np.testing.assert_array_equal(joints[b][j]["p"], ref[j]["p"])
+            assert joints[b][j]["l"].dtype == np.float32 == ref[j]["l"].dtype
+    assert total > 0 and (cnt[:, :2] > 100).all()
+    if cat == "drawer":          # index_per_point is 3 wide (architecture.py:129): joint 3 can never be voted for
+        assert (cnt[:, 2] == 0).all() and all(np.isnan(joints[b][2]["p"]).all() for b in range(len(clouds)))
