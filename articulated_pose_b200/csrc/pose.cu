@@ -12,6 +12,7 @@
 //   joint_refit_kernel     first-max hypothesis, masks, block-cooperative LM refit on all inliers
 //   umeyama_kernel         lib/aligning.py:580-622 (GT poses, compute_gt_pose.py:87)
 #include <stdlib.h>
+#include <cstdlib>
 #include "common.cuh"
 #include "pose_math.cuh"
 
@@ -1309,7 +1310,13 @@ extern "C" int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in
             int dev = 0, sms = 148;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            const long cap = (long)sms * LM_BLOCKS_PER_SM;
+            // Resident LM blocks per SM.  Measured (B200, 256 clouds): the first phase takes 6.9 / 6.7 / 6.7 / 7.2 ms of
+            // joint stage with 4 / 3 / 2 / 1 blocks per SM -- it is bound by the latency of each lane's serial solve, not by
+            // the number of lanes -- while one block per SM leaves three quarters of the register file to the forward CTAs
+            // of the overlapped batches: 25.1k instead of 24.4k clouds/s in the pipelined run.  ANCSH_LM_BLOCKS_PER_SM
+            // (1..4) overrides.
+            static const int lm_cap = getenv("ANCSH_LM_BLOCKS_PER_SM") ? atoi(getenv("ANCSH_LM_BLOCKS_PER_SM")) : 1;
+            const long cap = (long)sms * (lm_cap >= 1 && lm_cap <= LM_BLOCKS_PER_SM ? lm_cap : 1);
             int *lists = (int *)(recs + nsolves);              // 2 x nsolves work-list entries behind the records
             for (int ph = 0; ph < LM_PHASES; ++ph) {
                 const long items = ph == 0 ? nsolves : nsolves / LM_PHASE_SHARE[ph] + 1;

