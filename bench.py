@@ -393,8 +393,11 @@ def main():
             "clocks": clocks,
             "e2e": {"value": world * B * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
-            "gpu_launches": (16 + (12 if n_fwd == 2 else 0) + (8 if full else 0)) * args.steps,   # kernels per forward (the second
-            # network reuses the first one's FPS / ball-query launches) / per pose stage (profiles/*launches*)
+            # kernels of this library per step, counted in profiles/r01w_launches.csv: 15 per forward (2 fps, 2 ball query,
+            # 6 chain2, 1 gemm_tc, cloud_bias, 2 fp_interp, heads_act), 11 for the second network (no fps / ball query,
+            # fp_blend instead of fp_interp), 10 per pose stage (partition, single score + refit, joint init, 3 LM phases,
+            # model, verify, refit); memsets and the L2 flush are not counted
+            "gpu_launches": (15 + (11 if n_fwd == 2 else 0) + (10 if full else 0)) * args.steps,
             "roofline": roofline}
 
     if not args.no_cpu_baseline:
