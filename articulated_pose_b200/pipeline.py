@@ -72,7 +72,7 @@ class AncshPipeline:
 
     def submit(self, P, joint_cls, slot=0, net_events=None, net_b_events=None, pose_events=None):
         """Asynchronous run_device: the forwards are enqueued on the current stream, the pose stage on an
-        internal high-priority side stream (one per slot) that waits for them; buffers are per `slot` (cycle through
+        internal side stream (one per slot) that waits for them; buffers are per `slot` (cycle through
         N_SLOTS slots).  The slow tail
         of the joint LM solves then overlaps the next batch's forwards.  Returns the slot's pose tensors; call
         `join()` (or wait on the returned dict's "done" event) before reading them."""
