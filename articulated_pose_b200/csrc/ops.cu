@@ -1,5 +1,6 @@
 // ops.cu -- op-level kernels of the PointNet++ hot path (sm_100a): farthest point sampling, gather,
 // ball query, group, three_nn, three_interpolate.  Arithmetic contracts: SURVEY.md section 8(a).
+#include <cstdlib>
 #include "common.cuh"
 #include "ops.cuh"
 
@@ -111,6 +112,9 @@ int ancsh_fps_impl(int b, int n, int m, const float *xyz, int *idx, float *new_x
     if (b == 0 || m == 0) return ANCSH_OK;
     if (n <= 256) return fps_launch<128, 2>(b, n, m, xyz, idx, new_xyz, st);
     if (n <= 512) return fps_launch<128, 4>(b, n, m, xyz, idx, new_xyz, st);
+    static const int variant = getenv("ANCSH_FPS_VARIANT") ? atoi(getenv("ANCSH_FPS_VARIANT")) : 0;   // A/B probe
+    if (n <= 1024 && variant == 1) return fps_launch<512, 2>(b, n, m, xyz, idx, new_xyz, st);
+    if (n <= 1024 && variant == 2) return fps_launch<128, 8>(b, n, m, xyz, idx, new_xyz, st);
     if (n <= 1024) return fps_launch<256, 4>(b, n, m, xyz, idx, new_xyz, st);
     if (n <= 2048) return fps_launch<256, 8>(b, n, m, xyz, idx, new_xyz, st);
     if (n <= 4096) return fps_launch<512, 8>(b, n, m, xyz, idx, new_xyz, st);
