@@ -45,3 +45,24 @@ def test_product_does_not_import_oracle():
         src = open(py).read()
         assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), py
         assert "liboracle" not in src, py
+
+
+def test_argument_validation_needs_no_gpu():
+    """Entry points reject bad sizes / NULL pointers with ANCSH_ERR_INVALID_ARG before touching the device (the reference's
+    OP_REQUIRES -> InvalidArgument, tf_sampling.cpp:105), and empty batches are a no-op."""
+    from articulated_pose_b200 import _lib
+    INVALID = -1
+    assert _lib.ancsh_box_iou_3d(-1, 50, None, None, None, None, None, None) == INVALID
+    assert _lib.ancsh_box_iou_3d(4, 0, None, None, None, None, None, None) == INVALID
+    assert _lib.ancsh_box_iou_3d(4, 50, None, None, None, None, None, None) == INVALID          # NULL boxes
+    assert _lib.ancsh_box_iou_3d(0, 50, None, None, None, None, None, None) == _lib.OK          # empty batch
+    assert _lib.ancsh_amodal_extent(2, 0, 3, None, None, None, None, None) == INVALID
+    assert _lib.ancsh_amodal_extent(0, 1024, 3, None, None, None, None, None) == _lib.OK
+    assert _lib.ancsh_joint_vote(2, 1024, 3, 5, 3, None, None, None, None, None, None, 0.2, None, None, None, None) == INVALID  # gn width
+    assert _lib.ancsh_joint_vote(2, 1024, 1, 3, 3, None, None, None, None, None, None, 0.2, None, None, None, None) == INVALID  # K < 2
+    assert _lib.ancsh_joint_vote(0, 1024, 3, 9, 3, None, None, None, None, None, None, 0.2, None, None, None, None) == _lib.OK
+    assert _lib.ancsh_similarity_ransac(2, 512, 0, None, None, None, None, None, None, None, None, None, None, None, None) == INVALID
+    assert _lib.ancsh_similarity_ransac(2, 512, 300, None, None, None, None, None, None, None, None, None, None, None, None) == INVALID
+    assert _lib.ancsh_similarity_ransac(0, 512, 100, None, None, None, None, None, None, None, None, None, None, None, None) == _lib.OK
+    assert _lib.ancsh_umeyama(3, 0, None, None, None, None, None, None, None) == INVALID
+    assert _lib.ancsh_fps(2, 0, 4, None, None, None, None) != _lib.OK
