@@ -11,6 +11,8 @@ Pinned against the reference's own d3_utils.iou_3d imported unmodified (tests/te
 The dot products are written out left to right (the reference calls np.matmul on an (n,3)x(3,1) product whose BLAS
 summation order is not specified); the goldens show the counts agree.
 """
+import warnings
+
 import numpy as np
 
 
@@ -97,13 +99,11 @@ def joint_vote(gocs, mask_pred, unitvec_pred, heatmap_pred, orient_pred, index_p
         idx = np.where(cls_per_pt_pred == j)[0]
         gn_final[idx, :] = gocs[idx, :3] if gocs.shape[1] == 3 else gocs[idx, j * 3:j * 3 + 3]
     out = []
-    with np.errstate(all="ignore"):
+    with np.errstate(all="ignore"), warnings.catch_warnings():
+        warnings.simplefilter("ignore")                   # np.median of an empty slice warns and returns NaN
         for j in range(1, num_parts):
             offset = unitvec_pred * (1 - heatmap_pred.reshape(-1, 1)) * thres_r
             joint_pts = gn_final + offset
             idx = np.where(joint_cls_pred == j)[0]
-            import warnings
-            with warnings.catch_warnings():
-                warnings.simplefilter("ignore")
-                out.append({"l": np.median(orient_pred[idx], axis=0), "p": np.median(joint_pts[idx], axis=0)})
+            out.append({"l": np.median(orient_pred[idx], axis=0), "p": np.median(joint_pts[idx], axis=0)})
     return out
