@@ -45,7 +45,8 @@ class Net(ctypes.Structure):
                 ("npoint2", c_int), ("nsample2", c_int), ("radius2", ctypes.c_float),
                 ("sa1", Layer * 3), ("sa2", Layer * 3), ("sa3", Layer * 3),
                 ("fp1_global", Layer), ("fp1", Layer * 2), ("fp2", Layer * 2), ("fp3", Layer * 3),
-                ("fc1", Layer), ("nocs_heads", Layer), ("fc3", Layer * 2), ("joint_heads", Layer)]
+                ("fc1", Layer), ("nocs_heads", Layer), ("fc3", Layer * 2), ("joint_heads", Layer),
+                ("tc_bias_step", c_int), ("sa1_conv0_host", ctypes.c_void_p)]
 
 
 PRED_FIELDS = ("W", "nocs_per_point", "confi_per_point", "heatmap_per_point", "unitvec_per_point",

@@ -128,18 +128,56 @@ static bool tc_v1()
     return v;
 }
 
-// tensor-core variant of a set-abstraction stage (net_tc.cu); falls back to nothing: errors propagate
-static int sa_tc_from(const SaArgs &s, int B, cudaStream_t st)
+// A/B switches for profiling (read once): ANCSH_SA_LEAN_OFF = generic chain kernel for layer1 / layer2,
+// ANCSH_BALL_FUSED_OFF = separate ball-query kernel in front of the lean kernel
+static bool sa_lean_off()
 {
+    static const bool v = getenv("ANCSH_SA_LEAN_OFF") != nullptr;
+    return v;
+}
+static bool ball_fused_off()
+{
+    static const bool v = getenv("ANCSH_BALL_FUSED_OFF") != nullptr;
+    return v;
+}
+
+// tensor-core variant of a set-abstraction stage.  `idx_ready`: s.idx already holds the ball-query result (shared
+// geometry); otherwise the layer-specialised kernel (net_lean.cu) runs the ball query itself and leaves a copy of the
+// indices in s.idx / cnt for the second network of the pipeline, or -- shapes it does not cover -- the separate
+// ball-query kernel runs in front of the generic chain kernel (net_tc2.cu).  Errors propagate; no other fallback.
+static int sa_tc_from(const ancsh_net_t *net, const SaArgs &s, int B, float radius, int *idx_rw, int *cnt_rw, bool idx_ready,
+                      cudaStream_t st)
+{
+    if (s.L[2].cout != s.L[2].cout_pad) return ANCSH_ERR_INVALID_ARG;
+    TcLayer L[3];
+    for (int l = 0; l < 3; ++l) {
+        L[l].Wimg = reinterpret_cast<const __half *>(s.L[l].W_tc);
+        L[l].bias = s.L[l].b; L[l].K = s.L[l].cin_pad; L[l].N = s.L[l].cout_pad; L[l].relu = s.L[l].relu;
+        L[l].has_bias_step = net->tc_bias_step;
+    }
+    int rc;
+    if (!sa_lean_off() && !tc_v1() && idx_rw) {
+        SaLeanArgs2 t{};
+        t.xyz = s.xyz; t.points = s.points; t.new_xyz = s.new_xyz; t.out = s.out;
+        t.n = s.n; t.m = s.m; t.S = s.S; t.C = s.C; t.radius = radius;
+        t.w0_host = s.C == 0 ? net->sa1_conv0_host : nullptr;
+        for (int l = 0; l < 3; ++l) t.L[l] = L[l];
+        const bool fused = !idx_ready && !ball_fused_off();
+        if (fused) { t.idx_in = nullptr; t.idx_out = idx_rw; t.cnt_out = cnt_rw; }
+        else {
+            if (!idx_ready && (rc = ancsh_ball_query_impl(B, s.n, s.m, radius, s.S, s.xyz, s.new_xyz, idx_rw, cnt_rw, st))) return rc;
+            idx_ready = true;
+            t.idx_in = idx_rw;
+        }
+        rc = sa_lean_launch(t, B, st);
+        if (rc != ANCSH_ERR_UNSUPPORTED) return rc;
+    }
+    if (idx_rw && !idx_ready && (rc = ancsh_ball_query_impl(B, s.n, s.m, radius, s.S, s.xyz, s.new_xyz, idx_rw, cnt_rw, st))) return rc;
     SaTcArgs t{};
     t.xyz = s.xyz; t.points = s.points; t.new_xyz = s.new_xyz; t.idx = s.idx; t.out = s.out;
     t.n = s.n; t.m = s.m; t.S = s.S; t.C = s.C;
     t.W0 = s.L[0].W;
-    for (int l = 0; l < 3; ++l) {
-        t.L[l].Wimg = reinterpret_cast<const __half *>(s.L[l].W_tc);
-        t.L[l].bias = s.L[l].b; t.L[l].K = s.L[l].cin_pad; t.L[l].N = s.L[l].cout_pad; t.L[l].relu = s.L[l].relu;
-    }
-    if (s.L[2].cout != s.L[2].cout_pad) return ANCSH_ERR_INVALID_ARG;
+    for (int l = 0; l < 3; ++l) t.L[l] = L[l];
     return tc_v1() ? sa_tc_launch(t, B, st) : sa_tc2_launch(t, B, st);
 }
 
@@ -532,11 +570,12 @@ __global__ void __launch_bounds__(256) heads_act_kernel(const float *__restrict_
     o.index_per_point[(size_t)r * 3 + 2] = e2 / es;
 }
 
-static TcLayer tc_layer(const ancsh_layer_t &l)
+static TcLayer tc_layer(const ancsh_layer_t &l, int has_bias_step = 0)
 {
     TcLayer t;
     t.Wimg = reinterpret_cast<const __half *>(l.W_tc);
     t.bias = l.b; t.K = l.cin_pad; t.N = l.cout_pad; t.relu = l.relu;
+    t.has_bias_step = has_bias_step;
     return t;
 }
 
@@ -623,26 +662,28 @@ static int net_forward_impl(const ancsh_net_t *net, int B, int N, const float *P
     if (!shared && (rc = ancsh_fps_impl(B, m1, m2, l1_xyz, fps2, l2_xyz, st))) return rc;
     STAGE_MARK();
 
-    // layer1
-    if (!shared && (rc = ancsh_ball_query_impl(B, N, m1, net->radius1, net->nsample1, P, l1_xyz, bidx1, bcnt1, st))) return rc;
+    // layer1 (tensor-core path: the ball query runs inside the set-abstraction kernel, stage BALL1 is empty)
+    if (!shared && !net->use_tensor_cores &&
+        (rc = ancsh_ball_query_impl(B, N, m1, net->radius1, net->nsample1, P, l1_xyz, bidx1, bcnt1, st))) return rc;
     STAGE_MARK();
     {
         SaArgs a{};
         a.xyz = P; a.points = nullptr; a.new_xyz = l1_xyz; a.idx = bidx1; a.out = l1_points;
         a.L[0] = net->sa1[0]; a.L[1] = net->sa1[1]; a.L[2] = net->sa1[2];
         a.n = N; a.m = m1; a.S = net->nsample1; a.C = 0;
-        if ((rc = net->use_tensor_cores ? sa_tc_from(a, B, st) : sa_launch<128>(a, B, st))) return rc;
+        if ((rc = net->use_tensor_cores ? sa_tc_from(net, a, B, net->radius1, bidx1, bcnt1, shared, st) : sa_launch<128>(a, B, st))) return rc;
     }
     // layer2
     STAGE_MARK();
-    if (!shared && (rc = ancsh_ball_query_impl(B, m1, m2, net->radius2, net->nsample2, l1_xyz, l2_xyz, bidx2, bcnt2, st))) return rc;
+    if (!shared && !net->use_tensor_cores &&
+        (rc = ancsh_ball_query_impl(B, m1, m2, net->radius2, net->nsample2, l1_xyz, l2_xyz, bidx2, bcnt2, st))) return rc;
     STAGE_MARK();
     {
         SaArgs a{};
         a.xyz = l1_xyz; a.points = l1_points; a.new_xyz = l2_xyz; a.idx = bidx2; a.out = l2_points;
         a.L[0] = net->sa2[0]; a.L[1] = net->sa2[1]; a.L[2] = net->sa2[2];
         a.n = m1; a.m = m2; a.S = net->nsample2; a.C = net->sa1[2].cout;
-        if ((rc = net->use_tensor_cores ? sa_tc_from(a, B, st) : sa_launch<128>(a, B, st))) return rc;
+        if ((rc = net->use_tensor_cores ? sa_tc_from(net, a, B, net->radius2, bidx2, bcnt2, shared, st) : sa_launch<128>(a, B, st))) return rc;
     }
     // layer3 (group_all)
     STAGE_MARK();

@@ -7,6 +7,7 @@ struct TcLayer {
     const __half *Wimg;   // [K/8][2 (hi,lo)][N][8] fp16: W^T pre-split and pre-tiled (weights.tc_image)
     const float *bias;           // [N] f32 (BN folded)
     int K, N, relu;              // K = cin_pad (multiple of 16), N = cout_pad (64 / 128 / 256)
+    int has_bias_step;           // the image carries the extra bias k-step after K (ancsh_net_t::tc_bias_step)
 };
 
 struct SaTcArgs {
@@ -23,6 +24,20 @@ struct SaTcArgs {
 
 int sa_tc_launch(const SaTcArgs &a, int B, cudaStream_t st);
 int sa_tc2_launch(const SaTcArgs &a, int B, cudaStream_t st);    // warp-specialised version (net_tc2.cu)
+
+// ---- layer-specialised set abstraction with fused ball query (net_lean.cu) --------------------------------------
+struct SaLeanArgs2 {
+    const float *xyz, *points, *new_xyz;
+    const int *idx_in;           // (B,m,S) ball-query indices, or NULL: the kernel runs the ball query itself
+    int *idx_out, *cnt_out;      // idx_in == NULL: optional copies of idx (B,m,S) / pts_cnt (B,m)
+    float *out;                  // (B,m,L[2].N)
+    TcLayer L[3];
+    int n, m, S, C;
+    float radius;
+    const float *w0_host;        // HOST: ancsh_net_t::sa1_conv0_host (C == 0 only)
+};
+// ANCSH_ERR_UNSUPPORTED when the stage is not one of the specialised shapes (caller falls back to sa_tc2_launch)
+int sa_lean_launch(const SaLeanArgs2 &a, int B, cudaStream_t st);
 
 // ---- generic row-tile chain (feature propagation / heads) ------------------------------------------------------
 enum { TC_DST_INPLACE = 0, TC_DST_GLOBAL = 1 };

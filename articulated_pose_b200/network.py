@@ -82,6 +82,11 @@ class AncshNet:
             dst.W, dst.b = base + 4 * wo, base + 4 * bo
             dst.W_tc = tc_base + 2 * tc_offs[slot] if slot in tc_offs else None
             dst.cin, dst.cout, dst.cin_pad, dst.cout_pad, dst.relu = pl.cin, pl.cout, pl.cin_pad, pl.cout_pad, pl.relu
+        net.tc_bias_step = 1
+        l0 = self.layers["sa1[0]"]
+        self._sa1_conv0 = np.ascontiguousarray(np.concatenate([l0.W[:3, :64].ravel(), l0.b[:64]]).astype(np.float32)) \
+            if l0.cout_pad == 64 and l0.cin == 3 else None
+        net.sa1_conv0_host = self._sa1_conv0.ctypes.data if self._sa1_conv0 is not None else None
         self._net = net
         self._ws = {}       # (B,N) -> (workspace tensor, layout)
         self._host = {}     # (B,N) -> pinned staging buffers

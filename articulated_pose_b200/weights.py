@@ -180,10 +180,22 @@ def bf16_bits_to_f32(b):
     return (b.astype(np.uint32) << 16).view(np.float32)
 
 
-def tc_image(W):
+def tc_image(W, b=None):
     """Tensor-core operand image of a padded weight matrix W [cin_pad][cout_pad] (f32): W^T split into
-    hi = fp16(w), lo = fp16(w - hi) (round to nearest even), tiled as [cin_pad/8][2][cout_pad][8] fp16 bit patterns
-    (csrc/tc_common.cuh).  hi + lo carries ~22 significant bits of w."""
+    hi = fp16(w), lo = fp16(w - hi) (round to nearest even), tiled as [K/8][2][cout_pad][8] fp16 bit patterns
+    (csrc/tc_common.cuh).  hi + lo carries ~22 significant bits of w.
+    With a bias b [cout_pad], K = cin_pad + 16: the extra k-step holds the rows (fp16(b), fp16(b - fp16(b)), 0 ...), so
+    that a GEMM whose operand has ones in those two columns adds the bias (csrc/net_lean.cu); kernels that use
+    K = cin_pad never read it."""
+    if b is not None:
+        b = np.asarray(b, np.float32)
+        if np.abs(b).max(initial=0.0) >= 65504:
+            raise ValueError("bias exceeds the fp16 range of the tensor-core path")
+        b_hi = b.astype(np.float16).astype(np.float32)
+        b_lo = (b - b_hi).astype(np.float16).astype(np.float32)
+        extra = np.zeros((16, W.shape[1]), np.float32)
+        extra[0], extra[1] = b_hi, b_lo
+        W = np.concatenate([np.asarray(W, np.float32), extra], axis=0)
     K, N = W.shape
     Wt = np.ascontiguousarray(W.T, np.float32)                       # [N][K]
     if np.abs(Wt).max() >= 65504:
@@ -203,7 +215,7 @@ def flatten_tc_images(layers):
     """uint16 buffer with the tensor-core images of the layers that run on tcgen05, 256-byte aligned offsets."""
     off, offs, parts = 0, {}, []
     for slot in TC_SLOTS:
-        img = tc_image(layers[slot].W).ravel()
+        img = tc_image(layers[slot].W, layers[slot].b).ravel()
         offs[slot] = off
         parts.append((off, img))
         off = (off + img.size + 127) // 128 * 128

@@ -105,6 +105,12 @@ typedef struct {
     ancsh_layer_t nocs_heads;  /* 128 -> [W(K) | nocs(3K) | scale(K) | trans(3K) | confi(1)], fc11_1 folded */
     ancsh_layer_t fc3[2];      /* joint_net/fc3_0, fc3_1 */
     ancsh_layer_t joint_heads; /* 128 -> [joint_axis(3) | unitvec(3) | heatmap(1) | index(3)] */
+    int tc_bias_step; /* 1: every W_tc image carries one extra 16-deep k-step after cin_pad whose rows are (fp16(b),
+                         fp16(b - fp16(b)), 0, ...): the bias is added by the GEMM itself (weights.tc_image /
+                         ancsh_tc_image); required by the layer-specialised kernels (net_lean.cu) */
+    const float *sa1_conv0_host; /* HOST pointer or NULL: 256 floats = rows 0..2 of the BN-folded sa1[0].W (64 columns)
+                                    followed by its bias; the xyz-only first conv of layer1 is evaluated on the CUDA cores
+                                    with these values in the kernel parameter (constant) bank */
 } ancsh_net_t;
 
 /* Output tensors of pred_dict (architecture.py:141-159), each (B,N,width) f32 dense.  gocs_per_point,

@@ -36,7 +36,7 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(_lib.Layer) == 48
     assert ctypes.sizeof(_lib.Pred) == 88
     assert ctypes.sizeof(_lib.WsLayout) == 21 * 8
-    assert ctypes.sizeof(_lib.Net) == 40 + 22 * 48
+    assert ctypes.sizeof(_lib.Net) == 40 + 22 * 48 + 16
 
 
 def test_product_does_not_import_oracle():

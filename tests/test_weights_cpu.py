@@ -62,3 +62,18 @@ def test_tc_image_layout_and_split():
     assert np.abs(lo).max() <= np.abs(Wm).max() * 2 ** -10
     flat, offs = W.flatten_tc_images(W.pack_network(W.synthetic_weights(3), 3))
     assert all(o % 128 == 0 for o in offs.values()) and set(offs) == set(W.TC_SLOTS)
+
+
+def test_tc_image_bias_step():
+    """The extra 16-deep k-step after cin_pad carries (fp16(b), fp16(b - fp16(b)), 0 ...): a GEMM whose operand has ones
+    in those two columns adds the bias (csrc/net_lean.cu); the first cin_pad/8 slices equal the image without bias."""
+    rng = np.random.default_rng(1)
+    Wm = rng.normal(size=(32, 64)).astype(np.float32)
+    b = rng.normal(size=(64,)).astype(np.float32)
+    img = W.tc_image(Wm, b)
+    assert img.shape == (6, 2, 64, 8)
+    np.testing.assert_array_equal(img[:4], W.tc_image(Wm))
+    step = img[4:, 0].view(np.float16).astype(np.float32)           # hi image of the bias step: [2][64][8]
+    np.testing.assert_allclose(step[0, :, 0] + step[0, :, 1], b, rtol=2 ** -20, atol=1e-7)
+    assert not step[0, :, 2:].any() and not step[1].any()
+    assert not img[4:, 1].any()                                      # the lo image of the bias step is empty
