@@ -135,6 +135,11 @@ static bool sa_lean_off()
     static const bool v = getenv("ANCSH_SA_LEAN_OFF") != nullptr;
     return v;
 }
+static bool fps_prefix_off()
+{
+    static const bool v = getenv("ANCSH_FPS_PREFIX_OFF") != nullptr;
+    return v;
+}
 static bool ball_fused_off()
 {
     static const bool v = getenv("ANCSH_BALL_FUSED_OFF") != nullptr;
@@ -657,9 +662,11 @@ static int net_forward_impl(const ancsh_net_t *net, int B, int N, const float *P
 
     // sampling (pointnet_util.py:47) -- level 2 samples the level-1 centroids
     STAGE_MARK();
-    if (!shared && (rc = ancsh_fps_impl(B, N, m1, P, fps1, l1_xyz, st))) return rc;
+    // (level 2 is the prefix of level 1 whenever the reference's tie rule orders ties by index: one launch for both)
+    const bool fps_prefix = m1 <= 512 && m2 <= m1 && !fps_prefix_off();
+    if (!shared && (rc = ancsh_fps2_impl(B, N, m1, P, fps1, l1_xyz, fps_prefix ? m2 : 0, fps2, l2_xyz, st))) return rc;
     STAGE_MARK();
-    if (!shared && (rc = ancsh_fps_impl(B, m1, m2, l1_xyz, fps2, l2_xyz, st))) return rc;
+    if (!shared && !fps_prefix && (rc = ancsh_fps_impl(B, m1, m2, l1_xyz, fps2, l2_xyz, st))) return rc;
     STAGE_MARK();
 
     // layer1 (tensor-core path: the ball query runs inside the set-abstraction kernel, stage BALL1 is empty)

@@ -22,7 +22,9 @@
 //     tf_grouping_g.cu:3-36: first nsample in index order, padded with the first hit), indices handed to the gathering
 //     threads through shared memory.
 // Numerics: unchanged from net_tc2.cu (hi*hi and cross terms in separate f32 TMEM accumulators, summed in the epilogue).
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "net_tc.cuh"
@@ -63,8 +65,17 @@ struct SaLeanArgs {
     int nst;
     int nunits;
     LUnit U[MAXU];
+    long long *trace;         // profiling aid (ANCSH_LEAN_TRACE): per-CTA clock64() stamps of the phase boundaries, or NULL
     float w0[4 * 64];         // xyz-only first conv: rows 0..2 = W[k][0..63], row 3 = bias
 };
+
+// slot layout of a CTA's trace record: [0..31] worker warp 0, [32..63] worker warp 4, [64..127] MMA warp, tiles 0 and 1 only
+constexpr int TRACE_SLOTS = 128;
+#define LEAN_TRACE(base, k)                                                                                              \
+    do {                                                                                                                 \
+        if (a.trace && lane == 0 && t < 2)                                                                               \
+            a.trace[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * TRACE_SLOTS + (base) + t * ((base) == 64 ? 32 : 16) + (k)] = clock64(); \
+    } while (0)
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
@@ -254,12 +265,15 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
         const uint64_t on0 = tc::smem_desc(ones0, 2048u, 128u);
         for (int t = 0; t < ntiles; ++t) {
             work_sync();                                          // operand of the tile gathered, TMEM drained
+            LEAN_TRACE(64, 0);
             for (int u = 0; u < a.nunits; ++u) {
                 const LUnit &U = a.U[u];
                 tc::fence_after_sync();
                 const uint32_t hh = tmem, cr = tmem + (U.transposed ? (uint32_t)TM : (U.piece_bytes >> 4));
                 for (int kk = 0; kk < U.nk; ++kk) {
                     tc::mbar_wait(bar_full + slot, (uint32_t)(round & 1));
+                    if (kk == 0) LEAN_TRACE(64, 1 + 4 * u);
+                    if (kk == U.nk - 1) LEAN_TRACE(64, 2 + 4 * u);
                     if (elect_one()) {
                         const uint32_t st = ring0 + (uint32_t)slot * STAGE_BYTES;
                         const uint64_t wh = tc::smem_desc(st, 2u * U.piece_bytes, 128u);
@@ -283,8 +297,10 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
                 }
                 if (elect_one()) tc::mma_commit(bar_acc);
                 __syncwarp();
+                LEAN_TRACE(64, 3 + 4 * u);
                 tc::fence_before_sync();
                 work_sync();                                      // epilogue done: operand rewritten / TMEM drained
+                LEAN_TRACE(64, 4 + 4 * u);
             }
         }
     } else {
@@ -294,6 +310,8 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
         uint32_t uc = 0;                                          // units completed (parity of bar_acc)
         for (int t = 0; t < ntiles; ++t) {
             const int tile = blockIdx.x * ntiles + t;
+            const int tb = (warp == 0 ? 0 : 32);                  // trace base (warps 0 and 4 record)
+            if (warp == 0 || warp == 4) LEAN_TRACE(tb, 0);
             const long R = (long)tile * TM + r;                   // row inside the cloud = centroid * S + sample
             const int g = (int)(R / S);
             int id;
@@ -332,6 +350,7 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
                     if (lane == 0 && a.cnt_out) a.cnt_out[(size_t)b * a.m + cen] = cnt;
                 }
                 gather_sync();
+                if (warp == 0 || warp == 4) LEAN_TRACE(tb, 1);
                 id = s_idx[r];
                 if (a.idx_out && h == 0) a.idx_out[(size_t)b * a.m * S + R] = id;
             } else {
@@ -373,35 +392,45 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
                     }
                 }
             }
+            if (warp == 0 || warp == 4) LEAN_TRACE(tb, 2);
             tc::fence_proxy_async();
             work_sync();                                          // operand gathered
+            if (warp == 0 || warp == 4) LEAN_TRACE(tb, 3);
             // ---- in-place layers ----
             if (NSTD == 2) {
                 tc::mbar_wait(bar_acc, uc & 1u); ++uc;
+                if (warp == 0 || warp == 4) LEAN_TRACE(tb, 4);
                 tc::fence_after_sync();
                 epi_inplace<N0>(trow, h, r, A_hi, A_lo);
+                if (warp == 0 || warp == 4) LEAN_TRACE(tb, 5);
                 tc::fence_proxy_async();
                 tc::fence_before_sync();
                 work_sync();
             }
             {
                 tc::mbar_wait(bar_acc, uc & 1u); ++uc;
+                if (warp == 0 || warp == 4) LEAN_TRACE(tb, 6);
                 tc::fence_after_sync();
                 epi_inplace<N1>(trow, h, r, A_hi, A_lo);
+                if (warp == 0 || warp == 4) LEAN_TRACE(tb, 7);
                 tc::fence_proxy_async();
                 tc::fence_before_sync();
                 work_sync();
+                if (warp == 0 || warp == 4) LEAN_TRACE(tb, 8);
             }
             // ---- pooled layer, transposed: lane = output channel ----
 #pragma unroll
             for (int blk = 0; blk < NTB; ++blk) {
                 tc::mbar_wait(bar_acc, uc & 1u); ++uc;
+                if (warp == 0 || warp == 4) LEAN_TRACE(tb, 9 + 3 * blk);
                 tc::fence_after_sync();
                 const int ch = blk * 128 + wq * 32 + lane;
                 float *out_c = a.out + ((size_t)b * a.m + (size_t)tile * (TM / S)) * N2 + ch;
                 epi_pool_T<S>(trow, h, __ldg(a.bias_last + ch), out_c, N2);
+                if (warp == 0 || warp == 4) LEAN_TRACE(tb, 10 + 3 * blk);
                 tc::fence_before_sync();
                 work_sync();
+                if (warp == 0 || warp == 4) LEAN_TRACE(tb, 11 + 3 * blk);
             }
         }
         if (warp == 0) tc::tmem_dealloc(tmem, TMEM_COLS);
@@ -478,6 +507,32 @@ int sa_lean_launch(const SaLeanArgs2 &s, int B, cudaStream_t st)
     const size_t smem = (size_t)2 * k8 * 2048 + 4096 + (size_t)a.nst * STAGE_BYTES + (2 * MAX_STAGES + 1) * sizeof(uint64_t) + 16 +
                         TM * sizeof(int);
     const dim3 grid((unsigned)(tiles / a.tiles_per_cta), (unsigned)B);
-    if (sa1) return dispatch<0, 64, 64, 128>(a, s.S, ball, grid, smem, st);
-    return dispatch<128, 128, 128, 256>(a, s.S, ball, grid, smem, st);
+    // profiling aid: ANCSH_LEAN_TRACE=<file prefix> dumps the phase time stamps of the 4th launch of each stage
+    static const char *trace_path = getenv("ANCSH_LEAN_TRACE");
+    static int trace_calls[2] = {0, 0};
+    long long *trace_dev = nullptr;
+    const size_t trace_n = (size_t)grid.x * grid.y * TRACE_SLOTS;
+    if (trace_path && ++trace_calls[sa1 ? 0 : 1] == 4) {
+        if (cudaMalloc(&trace_dev, trace_n * sizeof(long long)) != cudaSuccess) trace_dev = nullptr;
+        else cudaMemsetAsync(trace_dev, 0, trace_n * sizeof(long long), st);
+    }
+    a.trace = trace_dev;
+    const int rc = sa1 ? dispatch<0, 64, 64, 128>(a, s.S, ball, grid, smem, st) : dispatch<128, 128, 128, 256>(a, s.S, ball, grid, smem, st);
+    if (trace_dev) {
+        std::vector<long long> h(trace_n);
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h.data(), trace_dev, trace_n * sizeof(long long), cudaMemcpyDeviceToHost);
+        cudaFree(trace_dev);
+        char name[512];
+        snprintf(name, sizeof name, "%s_%s.txt", trace_path, sa1 ? "sa1" : "sa2");
+        if (FILE *f = fopen(name, "w")) {
+            fprintf(f, "# grid %u x %u, %d tiles per CTA; one line per CTA: %d clock64 stamps\n", grid.x, grid.y, a.tiles_per_cta, TRACE_SLOTS);
+            for (size_t c = 0; c < (size_t)grid.x * grid.y; c += 37) {       // a sample of the CTAs
+                for (int k = 0; k < TRACE_SLOTS; ++k) fprintf(f, "%lld ", h[c * TRACE_SLOTS + k]);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
+    return rc;
 }

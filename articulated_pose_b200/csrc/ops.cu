@@ -17,7 +17,8 @@ __device__ __forceinline__ int fps_key_to_index(uint32_t key) { return (int)((ke
 
 template <int NT, int PPT>
 __global__ void __launch_bounds__(NT) fps_kernel(int n, int m, const float *__restrict__ xyz, int *__restrict__ idx_out,
-                                                 float *__restrict__ new_xyz)
+                                                 float *__restrict__ new_xyz, int m2, int *__restrict__ idx2_out,
+                                                 float *__restrict__ new_xyz2)
 {
     extern __shared__ float s_xyz[];  // n*3 floats
     __shared__ uint32_t s_val[2][NT / 32];
@@ -51,6 +52,12 @@ __global__ void __launch_bounds__(NT) fps_kernel(int n, int m, const float *__re
             new_xyz[((size_t)b * m) * 3 + 0] = s_xyz[0];
             new_xyz[((size_t)b * m) * 3 + 1] = s_xyz[1];
             new_xyz[((size_t)b * m) * 3 + 2] = s_xyz[2];
+        }
+        if (m2 > 0) {
+            idx2_out[(size_t)b * m2] = 0;
+            new_xyz2[((size_t)b * m2) * 3 + 0] = s_xyz[0];
+            new_xyz2[((size_t)b * m2) * 3 + 1] = s_xyz[1];
+            new_xyz2[((size_t)b * m2) * 3 + 2] = s_xyz[2];
         }
     }
     for (int j = 1; j < m; ++j) {
@@ -88,12 +95,23 @@ __global__ void __launch_bounds__(NT) fps_kernel(int n, int m, const float *__re
                 new_xyz[((size_t)b * m + j) * 3 + 1] = s_xyz[old * 3 + 1];
                 new_xyz[((size_t)b * m + j) * 3 + 2] = s_xyz[old * 3 + 2];
             }
+            if (j < m2) {
+                // Second-level sampling of the sampled points themselves (ancsh_fps_prefix): greedy farthest point sampling
+                // of a sequence that is already in farthest-point order returns its prefix -- index j, or index 0 once the
+                // distinct points are exhausted (all distances zero: this level re-picked point 0 at round j, and so
+                // would the second level).
+                idx2_out[(size_t)b * m2 + j] = old == 0 ? 0 : j;
+                new_xyz2[((size_t)b * m2 + j) * 3 + 0] = s_xyz[old * 3 + 0];
+                new_xyz2[((size_t)b * m2 + j) * 3 + 1] = s_xyz[old * 3 + 1];
+                new_xyz2[((size_t)b * m2 + j) * 3 + 2] = s_xyz[old * 3 + 2];
+            }
         }
     }
 }
 
 template <int NT, int PPT>
-static int fps_launch(int b, int n, int m, const float *xyz, int *idx, float *new_xyz, cudaStream_t st)
+static int fps_launch(int b, int n, int m, const float *xyz, int *idx, float *new_xyz, int m2, int *idx2, float *new_xyz2,
+                      cudaStream_t st)
 {
     size_t smem = (size_t)n * 3 * sizeof(float);
     if (smem > 40 * 1024) {   // static shared memory counts against the 48 KB default limit too
@@ -101,23 +119,35 @@ static int fps_launch(int b, int n, int m, const float *xyz, int *idx, float *ne
             cudaSuccess)
             return ANCSH_ERR_CUDA;
     }
-    fps_kernel<NT, PPT><<<b, NT, smem, st>>>(n, m, xyz, idx, new_xyz);
+    fps_kernel<NT, PPT><<<b, NT, smem, st>>>(n, m, xyz, idx, new_xyz, m2, idx2, new_xyz2);
     ANCSH_CHECK_LAUNCH();
     return ANCSH_OK;
 }
 
 int ancsh_fps_impl(int b, int n, int m, const float *xyz, int *idx, float *new_xyz, cudaStream_t st)
 {
+    return ancsh_fps2_impl(b, n, m, xyz, idx, new_xyz, 0, nullptr, nullptr, st);
+}
+
+// Two-level sampling in one launch: level 1 = FPS of xyz (m of n points), level 2 = FPS of the m sampled points
+// (m2 <= m of them), as pointnet_sa_module does for layer1 / layer2 (pointnet_util.py:47, architectures.py:62-70).
+// Level 2 is not computed: its result is the prefix of level 1 (see fps_kernel).  Valid under the reference kernel's tie
+// rule only while m <= 512 (tie key = index), which the caller checks; tests/test_ops_gpu.py compares with a real second
+// FPS launch, duplicates and exhausted clouds included.
+int ancsh_fps2_impl(int b, int n, int m, const float *xyz, int *idx, float *new_xyz, int m2, int *idx2, float *new_xyz2,
+                    cudaStream_t st)
+{
     if (b < 0 || n <= 0 || m < 0 || !xyz || !idx) return ANCSH_ERR_INVALID_ARG;
+    if (m2 < 0 || m2 > m || (m2 > 0 && (!idx2 || !new_xyz2 || m > 512))) return ANCSH_ERR_INVALID_ARG;
     if (b == 0 || m == 0) return ANCSH_OK;
-    if (n <= 256) return fps_launch<128, 2>(b, n, m, xyz, idx, new_xyz, st);
-    if (n <= 512) return fps_launch<128, 4>(b, n, m, xyz, idx, new_xyz, st);
+    if (n <= 256) return fps_launch<128, 2>(b, n, m, xyz, idx, new_xyz, m2, idx2, new_xyz2, st);
+    if (n <= 512) return fps_launch<128, 4>(b, n, m, xyz, idx, new_xyz, m2, idx2, new_xyz2, st);
     // block shape for n <= 1024 measured on B200 (256 clouds, m = 512): 512x2 0.79 ms, 256x4 0.366, 128x8 0.356, 64x16 0.55,
     // 32x32 1.03 -- fewer warps shorten the barrier and the cross-warp scan until the per-warp distance updates dominate
-    if (n <= 1024) return fps_launch<128, 8>(b, n, m, xyz, idx, new_xyz, st);
-    if (n <= 2048) return fps_launch<256, 8>(b, n, m, xyz, idx, new_xyz, st);
-    if (n <= 4096) return fps_launch<512, 8>(b, n, m, xyz, idx, new_xyz, st);
-    if (n <= 8192) return fps_launch<512, 16>(b, n, m, xyz, idx, new_xyz, st);
+    if (n <= 1024) return fps_launch<128, 8>(b, n, m, xyz, idx, new_xyz, m2, idx2, new_xyz2, st);
+    if (n <= 2048) return fps_launch<256, 8>(b, n, m, xyz, idx, new_xyz, m2, idx2, new_xyz2, st);
+    if (n <= 4096) return fps_launch<512, 8>(b, n, m, xyz, idx, new_xyz, m2, idx2, new_xyz2, st);
+    if (n <= 8192) return fps_launch<512, 16>(b, n, m, xyz, idx, new_xyz, m2, idx2, new_xyz2, st);
     return ANCSH_ERR_UNSUPPORTED;
 }
 
@@ -268,6 +298,14 @@ int ancsh_fps(int b, int n, int m, const float *inp, float *temp, int *out, void
     (void)temp;
     if (m > n && n > 0) { /* the reference happily re-picks points; so do we */ }
     return ancsh_fps_impl(b, n, m, inp, out, nullptr, (cudaStream_t)stream);
+}
+
+int ancsh_fps_two_level(int b, int n, int m1, int m2, const float *inp, int *out1, float *xyz1, int *out2, float *xyz2,
+                        void *stream)
+{
+    if (!out1 || !xyz1 || !out2 || !xyz2 || m2 <= 0) return ANCSH_ERR_INVALID_ARG;
+    if (m1 > 512) return ANCSH_ERR_UNSUPPORTED;
+    return ancsh_fps2_impl(b, n, m1, inp, out1, xyz1, m2, out2, xyz2, (cudaStream_t)stream);
 }
 
 int ancsh_gather_point(int b, int n, int m, const float *inp, const int *idx, float *out, void *stream)

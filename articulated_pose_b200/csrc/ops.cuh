@@ -58,5 +58,7 @@ __device__ __forceinline__ void three_weights(float d1, float d2, float d3, floa
 }
 
 int ancsh_fps_impl(int b, int n, int m, const float *xyz, int *idx, float *new_xyz, cudaStream_t st);
+int ancsh_fps2_impl(int b, int n, int m, const float *xyz, int *idx, float *new_xyz, int m2, int *idx2, float *new_xyz2,
+                    cudaStream_t st);
 int ancsh_ball_query_impl(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2, int *idx,
                           int *pts_cnt, cudaStream_t st);

@@ -36,6 +36,23 @@ def farthest_point_sample(npoint, inp):
     return out
 
 
+def farthest_point_sample_two_level(npoint1, npoint2, inp):
+    """Both sampling levels of the trunk in one launch (pointnet_util.py:47 for layer1 and layer2,
+    architectures.py:62-70): returns (idx1 (B,npoint1), xyz1 (B,npoint1,3), idx2 (B,npoint2), xyz2 (B,npoint2,3)) with
+    idx2 = farthest_point_sample(npoint2, xyz1).  Bit-exact with two launches; npoint1 <= 512."""
+    inp = _chk(inp, "inp", torch.float32, 3)
+    b, n, _ = inp.shape
+    if npoint2 > npoint1:
+        raise ValueError("npoint2 must not exceed npoint1")
+    idx1 = torch.empty((b, npoint1), dtype=torch.int32, device=inp.device)
+    xyz1 = torch.empty((b, npoint1, 3), dtype=torch.float32, device=inp.device)
+    idx2 = torch.empty((b, npoint2), dtype=torch.int32, device=inp.device)
+    xyz2 = torch.empty((b, npoint2, 3), dtype=torch.float32, device=inp.device)
+    _lib.check(_lib.ancsh_fps_two_level(b, n, npoint1, npoint2, inp.data_ptr(), idx1.data_ptr(), xyz1.data_ptr(),
+                                        idx2.data_ptr(), xyz2.data_ptr(), _stream()), "ancsh_fps_two_level")
+    return idx1, xyz1, idx2, xyz2
+
+
 def gather_point(inp, idx):
     """inp (B,N,3), idx (B,M) int32 -> (B,M,3) (tf_sampling.py:29-37)."""
     inp = _chk(inp, "inp", torch.float32, 3)

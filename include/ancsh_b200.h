@@ -42,6 +42,14 @@ const char *ancsh_version(void);
  * Bit-exact with the reference kernel, including its tie rule.  n <= 8192. */
 int ancsh_fps(int b, int n, int m, const float *inp, float *temp, int *out, void *stream);
 
+/* Both sampling levels of the PointNet++ trunk in one launch: out1 (b,m1) = farthest_point_sample(m1, inp) and
+ * xyz1 (b,m1,3) = gather_point(inp, out1) (layer1, pointnet_util.py:47), out2 (b,m2) = farthest_point_sample(m2, xyz1)
+ * and xyz2 (b,m2,3) = gather_point(xyz1, out2) (layer2).  The second level is the prefix of the first (greedy farthest
+ * point order), so it costs nothing; bit-exact with two launches of the reference kernel while m1 <= 512 (its tie rule,
+ * tf_sampling_g.cu:146-161, orders equal distances by index only below 512 points) -- ANCSH_ERR_UNSUPPORTED otherwise. */
+int ancsh_fps_two_level(int b, int n, int m1, int m2, const float *inp, int *out1, float *xyz1, int *out2, float *xyz2,
+                        void *stream);
+
 /* Replaces gatherpointLauncher (tf_sampling_g.cu:206; tf_sampling.py:29 gather_point(inp, idx)).
  * inp (b,n,3), idx (b,m) -> out (b,m,3). */
 int ancsh_gather_point(int b, int n, int m, const float *inp, const int *idx, float *out, void *stream);

@@ -75,6 +75,33 @@ def test_fps_all_points_identical():
     assert got[0, 1] == 512
 
 
+@pytest.mark.parametrize("n,m1,m2,kind", [(1024, 512, 128, "random"), (1024, 512, 128, "dup"), (2048, 512, 128, "dup"),
+                                          (700, 300, 300, "dup"), (1024, 512, 128, "few"), (1024, 512, 128, "one"),
+                                          (640, 512, 128, "tiled")])
+def test_fps_two_level_equals_two_launches(n, m1, m2, kind):
+    """The second sampling level is served as the prefix of the first (ancsh_fps_two_level); it must equal a real second
+    launch on the sampled points -- duplicated points (ties), clouds with fewer distinct points than samples (the
+    kernel re-picks index 0 once all distances are zero) and loader-style tiled clouds (lib/dataset.py:290-317) included."""
+    from articulated_pose_b200 import tf_ops
+    b = 3
+    xyz = _clouds(300 + n + m1, b, n, kind == "dup")
+    if kind == "few":
+        xyz[:] = xyz[:, :90].repeat(n // 90 + 1, axis=1)[:, :n]          # 90 distinct points < m2
+    if kind == "one":
+        xyz[:] = xyz[:, :1]
+    if kind == "tiled":
+        xyz[:] = np.concatenate([xyz[:, :400], xyz[:, :240]], axis=1)     # 400 distinct points: between m2 and m1
+    d = _dev(xyz)
+    idx1, xyz1, idx2, xyz2 = tf_ops.farthest_point_sample_two_level(m1, m2, d)
+    ref1 = tf_ops.farthest_point_sample(m1, d)
+    ref_xyz1 = tf_ops.gather_point(d, ref1)
+    ref2 = tf_ops.farthest_point_sample(m2, ref_xyz1)
+    ref_xyz2 = tf_ops.gather_point(ref_xyz1, ref2)
+    assert torch.equal(idx1, ref1) and torch.equal(xyz1, ref_xyz1)
+    assert torch.equal(idx2, ref2), (idx2[0, :8], ref2[0, :8])
+    assert torch.equal(xyz2, ref_xyz2)
+
+
 BQ_CASES = [(4, 1024, 512, 0.2, 64, 0.5), (4, 512, 128, 0.4, 64, 0.5), (2, 1024, 512, 0.2, 32, 0.5),
             (2, 1024, 512, 0.05, 64, 1.0), (2, 2048, 512, 0.2, 64, 0.7), (2, 100, 37, 0.3, 16, 0.5), (1, 33, 5, 10.0, 48, 0.5)]
 
