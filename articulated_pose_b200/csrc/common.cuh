@@ -4,8 +4,12 @@
 #include <stdint.h>
 #include "../../include/ancsh_b200.h"
 
+// every kernel launch of the library goes through this macro: it also feeds the diagnostic launch counter
+// (ancsh_launch_count, a relaxed atomic; the only process-wide state of the library)
+void ancsh_count_launch();
 #define ANCSH_CHECK_LAUNCH()                                   \
     do {                                                       \
+        ancsh_count_launch();                                  \
         cudaError_t e__ = cudaGetLastError();                  \
         if (e__ != cudaSuccess) return ANCSH_ERR_CUDA;         \
     } while (0)

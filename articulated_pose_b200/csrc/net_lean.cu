@@ -33,21 +33,43 @@ namespace {
 
 constexpr int TM = 128;                 // rows per tile
 constexpr int NWORK = 256;              // worker threads
-constexpr int NTHR = NWORK + 64;        // + MMA warp + producer warp
-constexpr int STAGE_BYTES = 8192;       // one ring stage = one 16-deep k-step of <= 128 weight rows (hi + lo)
+constexpr int NTHR = NWORK + 64;        // + MMA warp + producer warp (one lane of each runs the role)
 constexpr int MAX_STAGES = 8;
 constexpr int MAXU = 4;
 constexpr uint32_t TMEM_COLS = 256;
+
+// Compile-time plan of a stage: units = the GEMMs of a tile in issue order.
+//   in-place units (standard orientation, activations = A operand): conv0 (only with input features) and conv1, each with
+//   the bias k-step; then N2 / 128 transposed pooled blocks of the last conv (weights = A operand).
+template <int C, int N0, int N1, int N2>
+struct Plan {
+    static constexpr int K0 = C == 0 ? N0 : (C + 3 + 15) / 16 * 16;          // width of the gathered operand
+    static constexpr int KMAX = K0 > N0 ? (K0 > N1 ? K0 : N1) : (N0 > N1 ? N0 : N1);
+    static constexpr int K8 = KMAX / 8;
+    static constexpr int NSTD = C == 0 ? 1 : 2;
+    static constexpr int NTB = N2 / 128;
+    static constexpr int NU = NSTD + NTB;
+    __host__ __device__ static constexpr bool transposed(int u) { return u >= NSTD; }
+    __host__ __device__ static constexpr int kin(int u) { return C == 0 ? (u == 0 ? N0 : N1) : (u == 0 ? K0 : (u == 1 ? N0 : N1)); }
+    __host__ __device__ static constexpr int nc(int u) { return transposed(u) ? 128 : (C == 0 ? N1 : (u == 0 ? N0 : N1)); }    // weight rows of the unit
+    __host__ __device__ static constexpr int nk(int u) { return kin(u) / 16 + (transposed(u) ? 0 : 1); }                      // k-steps incl. bias step
+    __host__ __device__ static constexpr int kstep_bytes(int u) { return nc(u) * 64; }                                        // 2 kc x (hi, lo) x nc x 16 B
+    __host__ __device__ static constexpr int unit_bytes(int u) { return nk(u) * kstep_bytes(u); }
+    __host__ __device__ static constexpr int all_bytes() { int t = 0; for (int u = 0; u < NU; ++u) t += unit_bytes(u); return t; }
+    // weights of all units fit shared memory next to the operand: loaded once per CTA, one ring slot per unit
+    static constexpr bool RESIDENT = all_bytes() + 2 * K8 * 2048 <= 100 * 1024;
+    __host__ __device__ static constexpr int kps(int u) { return RESIDENT ? nk(u) : 1; }                                      // k-steps per ring stage
+    __host__ __device__ static constexpr int max_unit_bytes() { int t = 0; for (int u = 0; u < NU; ++u) t = unit_bytes(u) > t ? unit_bytes(u) : t; return t; }
+    static constexpr int SLOT_BYTES = RESIDENT ? max_unit_bytes() : 8192;
+    static constexpr int NST = RESIDENT ? NU : 4;
+    static_assert(N2 % 128 == 0 && NU <= MAXU && NST <= MAX_STAGES, "layer widths");
+    static_assert(C % 8 == 0 && N0 % 64 == 0 && N1 % 64 == 0, "layer widths");
+};
 
 struct LUnit {
     const uint8_t *img;       // weight image [K/8][hi|lo][Nfull][8] fp16, offset to the unit's first row
     uint32_t kstep_stride;    // bytes between consecutive k-steps in the image (4 * Nfull * 16)
     uint32_t piece_stride;    // bytes between the four (kc, hi|lo) blocks of a k-step (Nfull * 16)
-    uint32_t piece_bytes;     // rows of this unit * 16
-    int nk;                   // k-steps, including the bias step
-    int bias;                 // the last k-step is the bias step (A = ones slab, hi*hi product only)
-    int transposed;           // D^T = W^T x Act^T (weights are the A operand)
-    uint32_t idesc;
 };
 
 struct SaLeanArgs {
@@ -62,8 +84,6 @@ struct SaLeanArgs {
     int n, m;
     float radius;
     int tiles_per_cta;
-    int nst;
-    int nunits;
     LUnit U[MAXU];
     long long *trace;         // profiling aid (ANCSH_LEAN_TRACE): per-CTA clock64() stamps of the phase boundaries, or NULL
     float w0[4 * 64];         // xyz-only first conv: rows 0..2 = W[k][0..63], row 3 = bias
@@ -81,19 +101,16 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                  "r"(bytes), "r"(tc::smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ bool elect_one()
-{
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void work_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NWORK + 32) : "memory"); }
 __device__ __forceinline__ void gather_sync() { asm volatile("bar.sync 2, %0;" ::"n"(NWORK) : "memory"); }
 
 // {upper half, lower half} = {fp16(hi_elem), fp16(lo_elem)}, round to nearest, optionally clamped at 0 (ReLU)
@@ -129,7 +146,8 @@ __device__ __forceinline__ float max3(float a, float b, float c)
 }
 
 // epilogue of an in-place layer: this thread's row, columns [h*N/2, (h+1)*N/2): (hi*hi + cross) -> ReLU -> split -> operand
-template <int N>
+// ACC1: one accumulator holds both sums (cross terms issued first, see the MMA role)
+template <int N, bool ACC1>
 __device__ __forceinline__ void epi_inplace(uint32_t trow, int h, int r, uint8_t *A_hi, uint8_t *A_lo)
 {
 #pragma unroll
@@ -137,13 +155,14 @@ __device__ __forceinline__ void epi_inplace(uint32_t trow, int h, int r, uint8_t
         const int c0 = h * (N / 2) + cc;
         uint32_t ra[32], rb[32];
         tc::tmem_ld32_issue(trow + (uint32_t)c0, ra);
-        tc::tmem_ld32_issue(trow + (uint32_t)(N + c0), rb);
+        if (!ACC1) tc::tmem_ld32_issue(trow + (uint32_t)(N + c0), rb);
         tc::tmem_wait_ld();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             float v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(ra[q * 8 + i]) + __uint_as_float(rb[q * 8 + i]);
+            for (int i = 0; i < 8; ++i)
+                v[i] = ACC1 ? __uint_as_float(ra[q * 8 + i]) : __uint_as_float(ra[q * 8 + i]) + __uint_as_float(rb[q * 8 + i]);
             const int kc = (c0 >> 3) + q;
             split8_lean<true>(v, A_hi + (size_t)kc * 2048 + r * 16, A_lo + (size_t)kc * 2048 + r * 16);
         }
@@ -152,7 +171,7 @@ __device__ __forceinline__ void epi_inplace(uint32_t trow, int h, int r, uint8_t
 
 // epilogue of a transposed pooled block: this thread's TMEM lane = one output channel, columns [h*64, h*64+64) = rows of
 // 64 / S centroids.  out_c points at out[centroid 0 of the tile][channel of this lane]; ld = channels per centroid.
-template <int S>
+template <int S, bool ACC1>
 __device__ __forceinline__ void epi_pool_T(uint32_t trow, int h, float bias, float *out_c, int ld)
 {
     static_assert(S == 32 || S == 64, "nsample 32 or 64");
@@ -164,11 +183,13 @@ __device__ __forceinline__ void epi_pool_T(uint32_t trow, int h, float bias, flo
             const int c0 = h * 64 + g * S + cc;
             uint32_t ra[32], rb[32];
             tc::tmem_ld32_issue(trow + (uint32_t)c0, ra);
-            tc::tmem_ld32_issue(trow + (uint32_t)(TM + c0), rb);
+            if (!ACC1) tc::tmem_ld32_issue(trow + (uint32_t)(TM + c0), rb);
             tc::tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; i += 2)
-                mx = max3(mx, __uint_as_float(ra[i]) + __uint_as_float(rb[i]), __uint_as_float(ra[i + 1]) + __uint_as_float(rb[i + 1]));
+            for (int i = 0; i < 32; i += 2) {
+                if (ACC1) mx = max3(mx, __uint_as_float(ra[i]), __uint_as_float(ra[i + 1]));
+                else mx = max3(mx, __uint_as_float(ra[i]) + __uint_as_float(rb[i]), __uint_as_float(ra[i + 1]) + __uint_as_float(rb[i + 1]));
+            }
         }
         const int centroid = h * (64 / S) + g;
         out_c[(size_t)centroid * ld] = fmaxf(mx + bias, 0.f);   // relu(max(x) + b) == max(relu(x + b))
@@ -192,115 +213,178 @@ __device__ __forceinline__ void conv0_xyz(const SaLeanArgs &a, const float (&rel
     }
 }
 
+// ---- MMA role: all tcgen05.mma of unit U of the plan (one thread) -------------------------------------------------
+struct MmaCtx {
+    uint64_t ah0, al0, on0;          // descriptors of the activation images and the ones slab
+    uint32_t ring0, tmem;
+    uint64_t *bar_full, *bar_empty;
+    int slot, round;                 // ring position (streaming plans)
+};
+
+template <class P, int U, bool ACC1>
+__device__ __forceinline__ void issue_unit(MmaCtx &c, bool first_tile)
+{
+    constexpr bool T = P::transposed(U);
+    constexpr int NC = P::nc(U), NK = P::nk(U), KPS = P::kps(U);
+    constexpr uint32_t idesc = T ? tc::instr_desc_f16(128, TM) : tc::instr_desc_f16(TM, NC);
+    constexpr bool BIAS = !T;
+    const uint32_t hh = c.tmem, cr = ACC1 ? c.tmem : c.tmem + (uint32_t)(T ? TM : NC);
+    static_assert(!ACC1 || P::RESIDENT, "one-accumulator order needs the unit's weights resident (two passes)");
+    if (ACC1) {
+        // cross terms first, hi*hi products on top: the small products are summed among themselves before the
+        // (truncating) accumulator grows large
+        const uint32_t st = c.ring0 + (uint32_t)U * P::SLOT_BYTES;
+        if (first_tile) tc::mbar_wait(c.bar_full + U, 0u);
+        const uint64_t wh0 = tc::smem_desc(st, 2u * NC * 16u, 128u), wl0 = wh0 + (uint64_t)NC;
+#pragma unroll
+        for (int kk = 0; kk < NK - (BIAS ? 1 : 0); ++kk) {
+            const uint64_t wh = wh0 + (uint64_t)(kk * NC * 4), wl = wl0 + (uint64_t)(kk * NC * 4);       // k-step = NC * 64 B
+            const uint64_t ah = c.ah0 + (uint64_t)(kk * 256), al = c.al0 + (uint64_t)(kk * 256);
+            if (!T) { tc::mma_f16(cr, ah, wl, idesc, kk > 0); tc::mma_f16(cr, al, wh, idesc, 1u); }
+            else { tc::mma_f16(cr, wh, al, idesc, kk > 0); tc::mma_f16(cr, wl, ah, idesc, 1u); }
+        }
+#pragma unroll
+        for (int kk = 0; kk < NK; ++kk) {
+            const uint64_t wh = wh0 + (uint64_t)(kk * NC * 4);
+            const uint64_t ah = c.ah0 + (uint64_t)(kk * 256);
+            if (BIAS && kk == NK - 1) tc::mma_f16(hh, c.on0, wh, idesc, 1u);
+            else if (!T) tc::mma_f16(hh, ah, wh, idesc, 1u);
+            else tc::mma_f16(hh, wh, ah, idesc, 1u);
+        }
+        return;
+    }
+#pragma unroll
+    for (int s0 = 0; s0 < NK; s0 += KPS) {
+        uint32_t st;
+        if (P::RESIDENT) {
+            st = c.ring0 + (uint32_t)U * P::SLOT_BYTES;
+            if (first_tile) tc::mbar_wait(c.bar_full + U, 0u);
+        } else {
+            st = c.ring0 + (uint32_t)c.slot * P::SLOT_BYTES;
+            tc::mbar_wait(c.bar_full + c.slot, (uint32_t)(c.round & 1));
+        }
+        const uint64_t wh0 = tc::smem_desc(st, 2u * NC * 16u, 128u), wl0 = wh0 + (uint64_t)NC;
+#pragma unroll
+        for (int j = 0; j < KPS; ++j) {
+            const int kk = s0 + j;
+            const uint64_t wh = wh0 + (uint64_t)(j * NC * 4), wl = wl0 + (uint64_t)(j * NC * 4);
+            const uint64_t ah = c.ah0 + (uint64_t)(kk * 256), al = c.al0 + (uint64_t)(kk * 256);          // 2 * 2048 / 16
+            if (BIAS && kk == NK - 1) {
+                tc::mma_f16(hh, c.on0, wh, idesc, 1u);
+            } else if (!T) {
+                tc::mma_f16(hh, ah, wh, idesc, kk > 0);
+                tc::mma_f16(cr, ah, wl, idesc, kk > 0);
+                tc::mma_f16(cr, al, wh, idesc, 1u);
+            } else {
+                tc::mma_f16(hh, wh, ah, idesc, kk > 0);
+                tc::mma_f16(cr, wh, al, idesc, kk > 0);
+                tc::mma_f16(cr, wl, ah, idesc, 1u);
+            }
+        }
+        if (!P::RESIDENT) {
+            tc::mma_commit(c.bar_empty + c.slot);
+            if (++c.slot == P::NST) { c.slot = 0; ++c.round; }
+        }
+    }
+}
+
 // C: feature channels of the dataset (0: xyz only, first conv on the CUDA cores).  N0/N1/N2: layer widths.
-// S: nsample (32 / 64).  BALL: ball query in the kernel.
-template <int C, int N0, int N1, int N2, int S, bool BALL>
+// S: nsample (32 / 64).  BALL: ball query in the kernel.  ACC1: one TMEM accumulator per output (resident plans only).
+template <int C, int N0, int N1, int N2, int S, bool BALL, bool ACC1>
 __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant__ SaLeanArgs a)
 {
-    constexpr int K0 = C == 0 ? N0 : (C + 3 + 15) / 16 * 16;                  // width of the gathered operand
-    constexpr int KMAX = K0 > N0 ? (K0 > N1 ? K0 : N1) : (N0 > N1 ? N0 : N1);
-    constexpr int K8 = KMAX / 8;
-    constexpr int NSTD = C == 0 ? 1 : 2;                                      // in-place (standard orientation) units
-    constexpr int NTB = N2 / 128;                                             // transposed pooled blocks
-    static_assert(N2 % 128 == 0 && NSTD + NTB <= MAXU, "layer widths");
-    static_assert(C % 8 == 0 && N0 % 64 == 0 && N1 % 64 == 0, "layer widths");
+    using P = Plan<C, N0, N1, N2>;
+    constexpr int K0 = P::K0, K8 = P::K8, NSTD = P::NSTD, NTB = P::NTB, NU = P::NU;
+    constexpr int CPT = TM / S;                                               // centroids per tile
+    constexpr int WPC = (NWORK / 32) / CPT;                                   // warps per centroid in the ball query
 
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *A_hi = smem;
     uint8_t *A_lo = A_hi + (size_t)K8 * 2048;
     uint8_t *ones = A_lo + (size_t)K8 * 2048;                                 // [2 kc][128 rows][8] fp16: (1, 1, 0 ...)
     uint8_t *ring = ones + 4096;
-    uint64_t *bar_full = reinterpret_cast<uint64_t *>(ring + (size_t)a.nst * STAGE_BYTES);
+    uint64_t *bar_full = reinterpret_cast<uint64_t *>(ring + (size_t)P::NST * P::SLOT_BYTES);
     uint64_t *bar_empty = bar_full + MAX_STAGES;
-    uint64_t *bar_acc = bar_empty + MAX_STAGES;
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bar_acc + 1);
-    int *s_idx = reinterpret_cast<int *>(s_tmem + 4);                         // [TM]
+    uint64_t *bar_acc = bar_empty + MAX_STAGES;                               // MMA thread -> workers: accumulators complete
+    uint64_t *bar_ready = bar_acc + 1;                                        // workers -> MMA thread: operand written / TMEM drained
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bar_ready + 1);
+    int *s_cnt = reinterpret_cast<int *>(s_tmem + 4);                         // [8] hits found by each ball-query warp
+    int *s_idx = s_cnt + 8;                                                   // [8 warps][S] ball-query hit lists
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) tc::tmem_alloc(s_tmem, TMEM_COLS);
     if (tid == NWORK) {
         for (int s = 0; s < MAX_STAGES; ++s) { tc::mbar_init(bar_full + s, 1); tc::mbar_init(bar_empty + s, 1); }
         tc::mbar_init(bar_acc, 1);
+        tc::mbar_init(bar_ready, NWORK / 32);
     }
     if (tid < TM) {
         *reinterpret_cast<uint4 *>(ones + tid * 16) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
         *reinterpret_cast<uint4 *>(ones + 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
+    tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = *s_tmem;
-    const uint32_t a_hi0 = tc::smem_u32(A_hi), a_lo0 = tc::smem_u32(A_lo), ring0 = tc::smem_u32(ring), ones0 = tc::smem_u32(ones);
     const int b = blockIdx.y;
     const int ntiles = a.tiles_per_cta;
 
     if (warp == NWORK / 32 + 1) {
-        // =========================== producer warp: weight k-steps -> ring ===========================
-        int slot = 0, round = 0;
-        for (int t = 0; t < ntiles; ++t)
-            for (int u = 0; u < a.nunits; ++u) {
-                const LUnit &U = a.U[u];
-                for (int kk = 0; kk < U.nk; ++kk) {
-                    if (round > 0) tc::mbar_wait(bar_empty + slot, (uint32_t)((round - 1) & 1));
-                    if (elect_one()) {
-                        mbar_expect_tx(bar_full + slot, 4u * U.piece_bytes);
-                        const uint32_t dst = ring0 + (uint32_t)slot * STAGE_BYTES;
-                        const uint8_t *src = U.img + (size_t)kk * U.kstep_stride;
-                        if (U.piece_stride == U.piece_bytes) {
-                            bulk_g2s(dst, src, 4u * U.piece_bytes, bar_full + slot);
-                        } else {
+        // =========================== producer (one thread): weight stages -> ring ===========================
+        if (lane == 0) {
+            const uint32_t ring0 = tc::smem_u32(ring);
+            int slot = 0, round = 0;
+            for (int t = 0; t < (P::RESIDENT ? 1 : ntiles); ++t) {
 #pragma unroll
-                            for (int p = 0; p < 4; ++p)
-                                bulk_g2s(dst + (uint32_t)p * U.piece_bytes, src + (size_t)p * U.piece_stride, U.piece_bytes, bar_full + slot);
+                for (int u = 0; u < NU; ++u) {
+                    const LUnit &U = a.U[u];
+                    const uint32_t piece = (uint32_t)P::nc(u) * 16u;
+                    for (int s0 = 0; s0 < P::nk(u); s0 += P::kps(u)) {
+                        if (!P::RESIDENT && round > 0) tc::mbar_wait(bar_empty + slot, (uint32_t)((round - 1) & 1));
+                        mbar_expect_tx(bar_full + slot, (uint32_t)P::kps(u) * 4u * piece);
+                        for (int j = 0; j < P::kps(u); ++j) {
+                            const uint32_t dst = ring0 + (uint32_t)slot * P::SLOT_BYTES + (uint32_t)j * 4u * piece;
+                            const uint8_t *src = U.img + (size_t)(s0 + j) * U.kstep_stride;
+                            if (U.piece_stride == piece) {
+                                bulk_g2s(dst, src, 4u * piece, bar_full + slot);
+                            } else {
+#pragma unroll
+                                for (int p = 0; p < 4; ++p)
+                                    bulk_g2s(dst + (uint32_t)p * piece, src + (size_t)p * U.piece_stride, piece, bar_full + slot);
+                            }
                         }
+                        if (++slot == P::NST) { slot = 0; ++round; }
                     }
-                    __syncwarp();
-                    if (++slot == a.nst) { slot = 0; ++round; }
                 }
             }
+        }
     } else if (warp == NWORK / 32) {
-        // =========================== MMA warp ===========================
-        int slot = 0, round = 0;
-        const uint64_t ah0 = tc::smem_desc(a_hi0, 2048u, 128u), al0 = tc::smem_desc(a_lo0, 2048u, 128u);
-        const uint64_t on0 = tc::smem_desc(ones0, 2048u, 128u);
-        for (int t = 0; t < ntiles; ++t) {
-            work_sync();                                          // operand of the tile gathered, TMEM drained
-            LEAN_TRACE(64, 0);
-            for (int u = 0; u < a.nunits; ++u) {
-                const LUnit &U = a.U[u];
+        // =========================== MMA role (one thread) ===========================
+        if (lane == 0) {
+            MmaCtx c;
+            c.ah0 = tc::smem_desc(tc::smem_u32(A_hi), 2048u, 128u);
+            c.al0 = tc::smem_desc(tc::smem_u32(A_lo), 2048u, 128u);
+            c.on0 = tc::smem_desc(tc::smem_u32(ones), 2048u, 128u);
+            c.ring0 = tc::smem_u32(ring); c.tmem = tmem; c.bar_full = bar_full; c.bar_empty = bar_empty;
+            c.slot = 0; c.round = 0;
+            uint32_t rp = 0;                                      // phase of bar_ready
+            for (int t = 0; t < ntiles; ++t) {
+                tc::mbar_wait(bar_ready, rp & 1u); ++rp;          // operand of the tile gathered, TMEM drained
                 tc::fence_after_sync();
-                const uint32_t hh = tmem, cr = tmem + (U.transposed ? (uint32_t)TM : (U.piece_bytes >> 4));
-                for (int kk = 0; kk < U.nk; ++kk) {
-                    tc::mbar_wait(bar_full + slot, (uint32_t)(round & 1));
-                    if (kk == 0) LEAN_TRACE(64, 1 + 4 * u);
-                    if (kk == U.nk - 1) LEAN_TRACE(64, 2 + 4 * u);
-                    if (elect_one()) {
-                        const uint32_t st = ring0 + (uint32_t)slot * STAGE_BYTES;
-                        const uint64_t wh = tc::smem_desc(st, 2u * U.piece_bytes, 128u);
-                        const uint64_t wl = wh + (uint64_t)(U.piece_bytes >> 4);
-                        const uint64_t ah = ah0 + (uint64_t)(kk * 256), al = al0 + (uint64_t)(kk * 256);   // 2 * 2048 / 16
-                        if (U.bias && kk == U.nk - 1) {
-                            tc::mma_f16(hh, on0, wh, U.idesc, 1u);
-                        } else if (!U.transposed) {
-                            tc::mma_f16(hh, ah, wh, U.idesc, kk > 0);
-                            tc::mma_f16(cr, ah, wl, U.idesc, kk > 0);
-                            tc::mma_f16(cr, al, wh, U.idesc, 1u);
-                        } else {
-                            tc::mma_f16(hh, wh, ah, U.idesc, kk > 0);
-                            tc::mma_f16(cr, wh, al, U.idesc, kk > 0);
-                            tc::mma_f16(cr, wl, ah, U.idesc, 1u);
-                        }
-                        tc::mma_commit(bar_empty + slot);
-                    }
-                    __syncwarp();
-                    if (++slot == a.nst) { slot = 0; ++round; }
+                LEAN_TRACE(64, 0);
+#pragma unroll
+                for (int u = 0; u < NU; ++u) {
+                    if (u == 0) issue_unit<P, 0, ACC1>(c, t == 0);
+                    if (u == 1) issue_unit<P, 1 < NU ? 1 : 0, ACC1>(c, t == 0);
+                    if (u == 2) issue_unit<P, 2 < NU ? 2 : 0, ACC1>(c, t == 0);
+                    if (u == 3) issue_unit<P, 3 < NU ? 3 : 0, ACC1>(c, t == 0);
+                    tc::mma_commit(bar_acc);
+                    LEAN_TRACE(64, 3 + 4 * u);
+                    tc::mbar_wait(bar_ready, rp & 1u); ++rp;      // epilogue done: operand rewritten / TMEM drained
+                    tc::fence_after_sync();
+                    LEAN_TRACE(64, 4 + 4 * u);
                 }
-                if (elect_one()) tc::mma_commit(bar_acc);
-                __syncwarp();
-                LEAN_TRACE(64, 3 + 4 * u);
-                tc::fence_before_sync();
-                work_sync();                                      // epilogue done: operand rewritten / TMEM drained
-                LEAN_TRACE(64, 4 + 4 * u);
             }
         }
     } else {
@@ -308,6 +392,13 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
         const int r = tid & (TM - 1), h = tid >> 7, wq = warp & 3;
         const uint32_t trow = tmem + ((uint32_t)(wq * 32) << 16);
         uint32_t uc = 0;                                          // units completed (parity of bar_acc)
+        // everything this thread wrote (operand / TMEM reads) is done: tell the MMA thread
+        auto ready = [&]() {
+            tc::fence_proxy_async();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_ready);
+        };
         for (int t = 0; t < ntiles; ++t) {
             const int tile = blockIdx.x * ntiles + t;
             const int tb = (warp == 0 ? 0 : 32);                  // trace base (warps 0 and 4 record)
@@ -316,43 +407,61 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
             const int g = (int)(R / S);
             int id;
             if (BALL) {
-                if (warp < TM / S) {
-                    // query_ball_point for centroid `cen` (tf_grouping_g.cu:3-36): first S points in index order with
-                    // max(sqrt(d2), 1e-20) < radius, row padded with the first hit (all zeros when the ball is empty)
-                    const int cen = tile * (TM / S) + warp;
+                // query_ball_point (tf_grouping_g.cu:3-36): first S points in index order with max(sqrt(d2), 1e-20) < radius,
+                // row padded with the first hit (all zeros when the ball is empty).  WPC warps per centroid, each scans a
+                // contiguous range of the points and keeps an ordered hit list; the lists are concatenated in range order.
+                {
+                    const int cl = warp / WPC, part = warp % WPC;          // centroid of the tile, range of this warp
+                    const int cen = tile * CPT + cl;
                     const float *c3 = a.new_xyz + ((size_t)b * a.m + cen) * 3;
                     const float x2 = __ldg(c3), y2 = __ldg(c3 + 1), z2 = __ldg(c3 + 2);
                     const float *p1 = a.xyz + (size_t)b * a.n * 3;
+                    const int per = ((a.n + WPC - 1) / WPC + 31) & ~31;
+                    const int k_beg = part * per, k_end = min(a.n, k_beg + per);
                     int *row = s_idx + warp * S;
-                    int cnt = 0, first = 0;
-                    for (int base = 0; base < a.n; base += 32) {
-                        const int k = base + lane;
-                        bool in = false;
-                        if (k < a.n) {
-                            const float dx = x2 - __ldg(p1 + k * 3 + 0);
-                            const float dy = y2 - __ldg(p1 + k * 3 + 1);
-                            const float dz = z2 - __ldg(p1 + k * 3 + 2);
-                            float d = __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))));
-                            d = fmaxf(d, 1e-20f);
-                            in = d < a.radius;
+                    int cnt = 0;
+                    for (int base = k_beg; base < k_end && cnt < S; base += 64) {
+                        bool in[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int k = base + u * 32 + lane;
+                            in[u] = false;
+                            if (k < k_end) {
+                                const float dx = x2 - __ldg(p1 + k * 3 + 0);
+                                const float dy = y2 - __ldg(p1 + k * 3 + 1);
+                                const float dz = z2 - __ldg(p1 + k * 3 + 2);
+                                float d = __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))));
+                                d = fmaxf(d, 1e-20f);
+                                in[u] = d < a.radius;
+                            }
                         }
-                        const unsigned mask = __ballot_sync(0xFFFFFFFFu, in);
-                        if (mask) {
-                            if (cnt == 0) first = base + __ffs(mask) - 1;
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const unsigned mask = __ballot_sync(0xFFFFFFFFu, in[u]);
                             const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
-                            if (in && pos < S) row[pos] = k;
+                            if (in[u] && pos < S) row[pos] = base + u * 32 + lane;
                             cnt += __popc(mask);
-                            if (cnt >= S) break;
                         }
                     }
-                    cnt = min(cnt, S);
-                    for (int l = cnt + lane; l < S; l += 32) row[l] = first;
-                    if (lane == 0 && a.cnt_out) a.cnt_out[(size_t)b * a.m + cen] = cnt;
+                    if (lane == 0) s_cnt[warp] = min(cnt, S);
                 }
                 gather_sync();
                 if (warp == 0 || warp == 4) LEAN_TRACE(tb, 1);
-                id = s_idx[r];
-                if (a.idx_out && h == 0) a.idx_out[(size_t)b * a.m * S + R] = id;
+                {
+                    const int cl = r / S;
+                    int j = r - cl * S, total = 0, first = 0, found = -1;
+                    bool have_first = false;
+#pragma unroll
+                    for (int p = 0; p < WPC; ++p) {
+                        const int w = cl * WPC + p, cp = s_cnt[w];
+                        if (!have_first && cp > 0) { first = s_idx[w * S]; have_first = true; }
+                        if (found < 0 && j < cp) found = s_idx[w * S + j];
+                        j -= cp; total += cp;
+                    }
+                    id = found >= 0 ? found : first;
+                    if (a.idx_out && h == 0) a.idx_out[(size_t)b * a.m * S + R] = id;
+                    if (a.cnt_out && h == 0 && r % S == 0) a.cnt_out[(size_t)b * a.m + g] = min(total, S);
+                }
             } else {
                 id = __ldg(a.idx_in + (size_t)b * a.m * S + R);
             }
@@ -368,15 +477,15 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
                 const float *prow = a.points + ((size_t)b * a.n + id) * C;
                 constexpr int HALF = K0 / 16;                     // kc slices per thread
 #pragma unroll
-                for (int q0 = 0; q0 < HALF; q0 += 3) {
-                    float4 p[6];
+                for (int q0 = 0; q0 < HALF; q0 += 4) {
+                    float4 p[8];
 #pragma unroll
-                    for (int q = 0; q < 3; ++q) {
+                    for (int q = 0; q < 4; ++q) {
                         const int kc = h * HALF + q0 + q;
                         if (q0 + q < HALF && kc * 8 < C) { p[2 * q] = ldg4(prow + kc * 8); p[2 * q + 1] = ldg4(prow + kc * 8 + 4); }
                     }
 #pragma unroll
-                    for (int q = 0; q < 3; ++q) {
+                    for (int q = 0; q < 4; ++q) {
                         const int kc = h * HALF + q0 + q;
                         if (q0 + q >= HALF) continue;
                         float v[8];
@@ -393,30 +502,23 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
                 }
             }
             if (warp == 0 || warp == 4) LEAN_TRACE(tb, 2);
-            tc::fence_proxy_async();
-            work_sync();                                          // operand gathered
-            if (warp == 0 || warp == 4) LEAN_TRACE(tb, 3);
+            ready();                                              // operand gathered
             // ---- in-place layers ----
             if (NSTD == 2) {
                 tc::mbar_wait(bar_acc, uc & 1u); ++uc;
                 if (warp == 0 || warp == 4) LEAN_TRACE(tb, 4);
                 tc::fence_after_sync();
-                epi_inplace<N0>(trow, h, r, A_hi, A_lo);
+                epi_inplace<N0, ACC1>(trow, h, r, A_hi, A_lo);
                 if (warp == 0 || warp == 4) LEAN_TRACE(tb, 5);
-                tc::fence_proxy_async();
-                tc::fence_before_sync();
-                work_sync();
+                ready();
             }
             {
                 tc::mbar_wait(bar_acc, uc & 1u); ++uc;
                 if (warp == 0 || warp == 4) LEAN_TRACE(tb, 6);
                 tc::fence_after_sync();
-                epi_inplace<N1>(trow, h, r, A_hi, A_lo);
+                epi_inplace<N1, ACC1>(trow, h, r, A_hi, A_lo);
                 if (warp == 0 || warp == 4) LEAN_TRACE(tb, 7);
-                tc::fence_proxy_async();
-                tc::fence_before_sync();
-                work_sync();
-                if (warp == 0 || warp == 4) LEAN_TRACE(tb, 8);
+                ready();
             }
             // ---- pooled layer, transposed: lane = output channel ----
 #pragma unroll
@@ -425,37 +527,35 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
                 if (warp == 0 || warp == 4) LEAN_TRACE(tb, 9 + 3 * blk);
                 tc::fence_after_sync();
                 const int ch = blk * 128 + wq * 32 + lane;
-                float *out_c = a.out + ((size_t)b * a.m + (size_t)tile * (TM / S)) * N2 + ch;
-                epi_pool_T<S>(trow, h, __ldg(a.bias_last + ch), out_c, N2);
+                float *out_c = a.out + ((size_t)b * a.m + (size_t)tile * CPT) * N2 + ch;
+                epi_pool_T<S, ACC1>(trow, h, __ldg(a.bias_last + ch), out_c, N2);
                 if (warp == 0 || warp == 4) LEAN_TRACE(tb, 10 + 3 * blk);
-                tc::fence_before_sync();
-                work_sync();
-                if (warp == 0 || warp == 4) LEAN_TRACE(tb, 11 + 3 * blk);
+                ready();
             }
         }
+        // the last ready() was consumed by the MMA thread before it left its loop; TMEM is idle
+        asm volatile("bar.sync 3, %0;" ::"n"(NWORK) : "memory");
         if (warp == 0) tc::tmem_dealloc(tmem, TMEM_COLS);
     }
 }
 
 // ---- host -------------------------------------------------------------------------------------------------------
-LUnit make_unit(const TcLayer &L, int n0, int nc, bool bias, bool transposed)
+LUnit make_unit(const TcLayer &L, int n0)
 {
     LUnit U{};
     U.img = reinterpret_cast<const uint8_t *>(L.Wimg) + (size_t)n0 * 16;
     U.kstep_stride = 4u * (uint32_t)L.N * 16u;
     U.piece_stride = (uint32_t)L.N * 16u;
-    U.piece_bytes = (uint32_t)nc * 16u;
-    U.nk = L.K / 16 + (bias ? 1 : 0);
-    U.bias = bias ? 1 : 0;
-    U.transposed = transposed ? 1 : 0;
-    U.idesc = transposed ? tc::instr_desc_f16(128, TM) : tc::instr_desc_f16(TM, nc);
     return U;
 }
 
-template <int C, int N0, int N1, int N2, int S, bool BALL>
-int launch(const SaLeanArgs &a, dim3 grid, size_t smem, cudaStream_t st)
+template <int C, int N0, int N1, int N2, int S, bool BALL, bool ACC1>
+int launch(const SaLeanArgs &a, dim3 grid, cudaStream_t st)
 {
-    auto k = sa_lean_kernel<C, N0, N1, N2, S, BALL>;
+    using P = Plan<C, N0, N1, N2>;
+    const size_t smem = (size_t)2 * P::K8 * 2048 + 4096 + (size_t)P::NST * P::SLOT_BYTES + (2 * MAX_STAGES + 2) * sizeof(uint64_t) + 16 +
+                        8 * sizeof(int) + 8 * S * sizeof(int);
+    auto k = sa_lean_kernel<C, N0, N1, N2, S, BALL, ACC1>;
     ANCSH_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ANCSH_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     k<<<grid, NTHR, smem, st>>>(a);
@@ -463,11 +563,11 @@ int launch(const SaLeanArgs &a, dim3 grid, size_t smem, cudaStream_t st)
     return ANCSH_OK;
 }
 
-template <int C, int N0, int N1, int N2>
-int dispatch(const SaLeanArgs &a, int S, bool ball, dim3 grid, size_t smem, cudaStream_t st)
+template <int C, int N0, int N1, int N2, bool ACC1>
+int dispatch(const SaLeanArgs &a, int S, bool ball, dim3 grid, cudaStream_t st)
 {
-    if (S == 32) return ball ? launch<C, N0, N1, N2, 32, true>(a, grid, smem, st) : launch<C, N0, N1, N2, 32, false>(a, grid, smem, st);
-    if (S == 64) return ball ? launch<C, N0, N1, N2, 64, true>(a, grid, smem, st) : launch<C, N0, N1, N2, 64, false>(a, grid, smem, st);
+    if (S == 32) return ball ? launch<C, N0, N1, N2, 32, true, ACC1>(a, grid, st) : launch<C, N0, N1, N2, 32, false, ACC1>(a, grid, st);
+    if (S == 64) return ball ? launch<C, N0, N1, N2, 64, true, ACC1>(a, grid, st) : launch<C, N0, N1, N2, 64, false, ACC1>(a, grid, st);
     return ANCSH_ERR_UNSUPPORTED;
 }
 
@@ -490,23 +590,23 @@ int sa_lean_launch(const SaLeanArgs2 &s, int B, cudaStream_t st)
     a.xyz = s.xyz; a.points = s.points; a.new_xyz = s.new_xyz; a.idx_in = s.idx_in; a.idx_out = s.idx_out; a.cnt_out = s.cnt_out;
     a.out = s.out; a.bias_last = s.L[2].bias; a.n = s.n; a.m = s.m; a.radius = s.radius;
     const int tiles = (int)(rows / TM);
-    a.tiles_per_cta = tiles % 4 == 0 ? 4 : (tiles % 2 == 0 ? 2 : 1);
-    int k8;
+    // resident weights (layer1): long-lived CTAs amortise the one-time weight load; streamed weights: 4 tiles per CTA
+    int tpc = sa1 ? 16 : 4;
+    while (tpc > 1 && tiles % tpc != 0) tpc >>= 1;
+    a.tiles_per_cta = tpc;
     if (sa1) {
         for (int i = 0; i < 256; ++i) a.w0[i] = s.w0_host[i];
-        a.U[0] = make_unit(s.L[1], 0, 64, true, false);
-        a.U[1] = make_unit(s.L[2], 0, 128, false, true);
-        a.nunits = 2; k8 = 8; a.nst = 6;
+        a.U[0] = make_unit(s.L[1], 0);
+        a.U[1] = make_unit(s.L[2], 0);
     } else {
-        a.U[0] = make_unit(s.L[0], 0, 128, true, false);
-        a.U[1] = make_unit(s.L[1], 0, 128, true, false);
-        a.U[2] = make_unit(s.L[2], 0, 128, false, true);
-        a.U[3] = make_unit(s.L[2], 128, 128, false, true);
-        a.nunits = 4; k8 = 18; a.nst = 4;
+        a.U[0] = make_unit(s.L[0], 0);
+        a.U[1] = make_unit(s.L[1], 0);
+        a.U[2] = make_unit(s.L[2], 0);
+        a.U[3] = make_unit(s.L[2], 128);
     }
-    const size_t smem = (size_t)2 * k8 * 2048 + 4096 + (size_t)a.nst * STAGE_BYTES + (2 * MAX_STAGES + 1) * sizeof(uint64_t) + 16 +
-                        TM * sizeof(int);
     const dim3 grid((unsigned)(tiles / a.tiles_per_cta), (unsigned)B);
+    // A/B switch: ANCSH_LEAN_ACC1 = one TMEM accumulator per output for the resident plan (cross terms issued first)
+    static const bool acc1 = getenv("ANCSH_LEAN_ACC1") != nullptr;
     // profiling aid: ANCSH_LEAN_TRACE=<file prefix> dumps the phase time stamps of the 4th launch of each stage
     static const char *trace_path = getenv("ANCSH_LEAN_TRACE");
     static int trace_calls[2] = {0, 0};
@@ -517,7 +617,8 @@ int sa_lean_launch(const SaLeanArgs2 &s, int B, cudaStream_t st)
         else cudaMemsetAsync(trace_dev, 0, trace_n * sizeof(long long), st);
     }
     a.trace = trace_dev;
-    const int rc = sa1 ? dispatch<0, 64, 64, 128>(a, s.S, ball, grid, smem, st) : dispatch<128, 128, 128, 256>(a, s.S, ball, grid, smem, st);
+    const int rc = sa1 ? (acc1 ? dispatch<0, 64, 64, 128, true>(a, s.S, ball, grid, st) : dispatch<0, 64, 64, 128, false>(a, s.S, ball, grid, st))
+                       : dispatch<128, 128, 128, 256, false>(a, s.S, ball, grid, st);
     if (trace_dev) {
         std::vector<long long> h(trace_n);
         cudaStreamSynchronize(st);

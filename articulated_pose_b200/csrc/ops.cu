@@ -1,8 +1,12 @@
 // ops.cu -- op-level kernels of the PointNet++ hot path (sm_100a): farthest point sampling, gather,
 // ball query, group, three_nn, three_interpolate.  Arithmetic contracts: SURVEY.md section 8(a).
+#include <atomic>
 #include <cstdlib>
 #include "common.cuh"
 #include "ops.cuh"
+
+static std::atomic<unsigned long long> g_launches{0};
+void ancsh_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // =====================================================================================================
 // Farthest point sampling.  Reference: tf_sampling_g.cu:105-170 (one 512-thread block per cloud, running
@@ -291,7 +295,9 @@ __global__ void __launch_bounds__(256) three_interp_kernel(int m, int c, long ro
 // =====================================================================================================
 extern "C" {
 
-const char *ancsh_version(void) { return "ancsh_b200 0.1 sm_100a"; }
+const char *ancsh_version(void) { return "ancsh_b200 0.2 sm_100a"; }
+
+unsigned long long ancsh_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int ancsh_fps(int b, int n, int m, const float *inp, float *temp, int *out, void *stream)
 {

@@ -31,6 +31,10 @@ extern "C" {
 /* library / build identification: returns e.g. "ancsh_b200 0.1 sm_100a" */
 const char *ancsh_version(void);
 
+/* Diagnostic: number of kernels this library has launched in this process so far (monotonic, all threads and streams;
+ * memsets / copies are not counted).  bench.py reports the difference over its timed region as `gpu_launches`. */
+unsigned long long ancsh_launch_count(void);
+
 /* ------------------------------------------------------------------------------------------------
  * Op level -- one entry point per native op on the path.
  * ---------------------------------------------------------------------------------------------- */
