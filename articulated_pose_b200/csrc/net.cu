@@ -551,28 +551,32 @@ __global__ void __launch_bounds__(256) heads_act_kernel(const float *__restrict_
     for (int k = 1; k < K; ++k) mx = fmaxf(mx, x[k]);
     float sum = 0.f;
     for (int k = 0; k < K; ++k) { x[k] = expf(x[k] - mx); sum += x[k]; }
-    for (int k = 0; k < K; ++k) o.W[(size_t)r * K + k] = x[k] / sum;
-    for (int k = K; k < 4 * K; ++k) { x[k] = sigmoidf_(x[k]); o.nocs_per_point[(size_t)r * 3 * K + (k - K)] = x[k]; }
+    // every output is optional (NULL = not requested), like copy_tile_out of the f32 path
+    if (o.W) for (int k = 0; k < K; ++k) o.W[(size_t)r * K + k] = x[k] / sum;
+    for (int k = K; k < 4 * K; ++k) { x[k] = sigmoidf_(x[k]); if (o.nocs_per_point) o.nocs_per_point[(size_t)r * 3 * K + (k - K)] = x[k]; }
     if (mixed) {
-        for (int k = 4 * K; k < 5 * K; ++k) { x[k] = sigmoidf_(x[k]); o.global_scale[(size_t)r * K + (k - 4 * K)] = x[k]; }
-        for (int k = 5 * K; k < 8 * K; ++k) { x[k] = tanhf(x[k]); o.global_translation[(size_t)r * 3 * K + (k - 5 * K)] = x[k]; }
-        o.confi_per_point[r] = sigmoidf_(x[8 * K]);
-        for (int k = 0; k < 3 * K; ++k)
-            o.gocs_per_point[(size_t)r * 3 * K + k] = __fadd_rn(__fmul_rn(x[K + k], x[4 * K + k / 3]), x[5 * K + k]);
-    } else {
+        for (int k = 4 * K; k < 5 * K; ++k) { x[k] = sigmoidf_(x[k]); if (o.global_scale) o.global_scale[(size_t)r * K + (k - 4 * K)] = x[k]; }
+        for (int k = 5 * K; k < 8 * K; ++k) { x[k] = tanhf(x[k]); if (o.global_translation) o.global_translation[(size_t)r * 3 * K + (k - 5 * K)] = x[k]; }
+        if (o.confi_per_point) o.confi_per_point[r] = sigmoidf_(x[8 * K]);
+        if (o.gocs_per_point)
+            for (int k = 0; k < 3 * K; ++k)
+                o.gocs_per_point[(size_t)r * 3 * K + k] = __fadd_rn(__fmul_rn(x[K + k], x[4 * K + k / 3]), x[5 * K + k]);
+    } else if (o.confi_per_point) {
         o.confi_per_point[r] = sigmoidf_(x[4 * K]);
     }
     const float4 *s2 = reinterpret_cast<const float4 *>(raw2 + (size_t)r * 64);
     const float4 j0 = __ldg(s2), j1 = __ldg(s2 + 1), j2 = __ldg(s2 + 2);
     const float y[10] = {j0.x, j0.y, j0.z, j0.w, j1.x, j1.y, j1.z, j1.w, j2.x, j2.y};
-    for (int k = 0; k < 3; ++k) o.joint_axis_per_point[(size_t)r * 3 + k] = tanhf(y[k]);
-    for (int k = 0; k < 3; ++k) o.unitvec_per_point[(size_t)r * 3 + k] = tanhf(y[3 + k]);
-    o.heatmap_per_point[r] = sigmoidf_(y[6]);
-    const float m2 = fmaxf(y[7], fmaxf(y[8], y[9]));
-    const float e0 = expf(y[7] - m2), e1 = expf(y[8] - m2), e2 = expf(y[9] - m2), es = e0 + e1 + e2;
-    o.index_per_point[(size_t)r * 3 + 0] = e0 / es;
-    o.index_per_point[(size_t)r * 3 + 1] = e1 / es;
-    o.index_per_point[(size_t)r * 3 + 2] = e2 / es;
+    if (o.joint_axis_per_point) for (int k = 0; k < 3; ++k) o.joint_axis_per_point[(size_t)r * 3 + k] = tanhf(y[k]);
+    if (o.unitvec_per_point) for (int k = 0; k < 3; ++k) o.unitvec_per_point[(size_t)r * 3 + k] = tanhf(y[3 + k]);
+    if (o.heatmap_per_point) o.heatmap_per_point[r] = sigmoidf_(y[6]);
+    if (o.index_per_point) {
+        const float m2 = fmaxf(y[7], fmaxf(y[8], y[9]));
+        const float e0 = expf(y[7] - m2), e1 = expf(y[8] - m2), e2 = expf(y[9] - m2), es = e0 + e1 + e2;
+        o.index_per_point[(size_t)r * 3 + 0] = e0 / es;
+        o.index_per_point[(size_t)r * 3 + 1] = e1 / es;
+        o.index_per_point[(size_t)r * 3 + 2] = e2 / es;
+    }
 }
 
 static TcLayer tc_layer(const ancsh_layer_t &l, int has_bias_step = 0)

@@ -118,8 +118,8 @@ template <bool RELU>
 __device__ __forceinline__ uint32_t pack_f16x2(float upper, float lower)
 {
     uint32_t d;
-    if (RELU) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(upper), "f"(lower));
-    else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(upper), "f"(lower));
+    if (RELU) asm("cvt.rn.satfinite.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(upper), "f"(lower));
+    else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(upper), "f"(lower));
     return d;
 }
 // 8 consecutive k of one row -> one 16-byte piece each of the hi and lo operand images

@@ -127,10 +127,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
 }
 
 // ---- fp16 hi/lo split ---------------------------------------------------------------------------------
+// Range contract: |v| < 65504.  Larger magnitudes saturate (hi = +-65504, lo = the clamped remainder) instead of turning
+// into inf - inf = NaN: the element is clipped, the rest of the row stays exact.
+__device__ __forceinline__ __half f2h_sat(float v)
+{
+    unsigned short h;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+    return __ushort_as_half(h);
+}
 __device__ __forceinline__ void split_f16(float v, __half &hi, __half &lo)
 {
-    hi = __float2half_rn(v);
-    lo = __float2half_rn(v - __half2float(hi));
+    hi = f2h_sat(v);
+    lo = f2h_sat(v - __half2float(hi));
 }
 // 8 consecutive k of one row -> one 16-byte piece each for the hi and lo operand images (fp16)
 __device__ __forceinline__ void store_split8(const float (&v)[8], uint4 *dst_hi, uint4 *dst_lo)

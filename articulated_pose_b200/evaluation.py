@@ -73,9 +73,8 @@ def solver_ransac_nonlinear(s_ind, e_ind, test_exp, baseline_exp, choose_thresho
                                 inlier_th=choose_threshold, seed=seed, device=device)
         results = solver.solve(np.stack(P), np.stack(nocs), np.stack(mask), np.stack(axis), np.stack(jcls))
         for base, res in zip(chunk, results):
-            entry = rts_all[base]                                          # updated in place like the reference, :346-352
-            entry.update(_rts_entry(res, entry["rt"]["gt"], entry["scale"]["gt"]))
-            all_rts[base] = entry
+            gt = rts_all[base]                                             # read only: the reference builds a fresh rts_dict (:346-352)
+            all_rts[base] = _rts_entry(res, gt["rt"]["gt"], gt["scale"]["gt"])
     if file_name is not None:
         os.makedirs(os.path.dirname(os.path.abspath(file_name)), exist_ok=True)
         with open(file_name, "wb") as fh:

@@ -132,9 +132,12 @@ class AncshNet:
         pred.net = net_out.data_ptr() if net_out is not None else None     # optional (B,N,128) trunk feature
         ev = stage_events.arr if stage_events is not None else None
         if geometry_from is not None:
-            gws, _, gB = geometry_from.last_workspace
-            if gB != B:
-                raise ValueError("geometry_from ran on a different batch size")
+            if geometry_from.last_workspace is None:
+                raise ValueError("geometry_from has not run a forward yet")
+            gws, _, gB, gN, gP = geometry_from.last_workspace
+            if (gB, gN) != (B, N) or gP != P.data_ptr():
+                raise ValueError("geometry_from's last forward ran on a different batch (shape %r / another tensor): its FPS, "
+                                 "ball-query and three_nn tables do not belong to this P" % ((gB, gN),))
             rc = _lib.ancsh_net_forward_shared(ctypes.byref(self._net), B, N, P.data_ptr(), ws.data_ptr(), lay.total_bytes,
                                                ctypes.byref(geometry_from._net), gws.data_ptr(), ctypes.byref(pred), ev,
                                                torch.cuda.current_stream().cuda_stream)
@@ -142,7 +145,7 @@ class AncshNet:
             rc = _lib.ancsh_net_forward(ctypes.byref(self._net), B, N, P.data_ptr(), ws.data_ptr(), lay.total_bytes,
                                         ctypes.byref(pred), ev, torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "ancsh_net_forward")
-        self.last_workspace = (ws, lay, B)
+        self.last_workspace = (ws, lay, B, N, P.data_ptr())
         return out
 
     def forward(self, P, copy=True):
@@ -179,7 +182,7 @@ class AncshNet:
 
     def intermediates(self):
         """Views of the last forward's workspace (indices and per-level features), for parity tests."""
-        ws, lay, B = self.last_workspace
+        ws, lay, B = self.last_workspace[:3]
         out = {}
         for name, (dt, shp) in _WS_VIEWS.items():
             shape = shp(self, B)
