@@ -116,6 +116,7 @@ struct LmTick {
     // ---- control state of lmder ----
     double x[6], fnorm, par, delta, xnorm;
     int iter, nfev, njev;
+    int nlm;           // lmpar iterations so far (statistics only: feeds the FLOP model of bench.py's roofline)
     int info;          // 0 while the solve is running, MINPACK's info code afterwards
     int need_jac;      // the next tick starts with a Jacobian evaluation (the previous step was accepted)
     // ---- products of the Jacobian phase, valid while need_jac == 0 ----
@@ -132,7 +133,7 @@ PM_HD void lm_tick_init(LmTick &s, const double *x0, double fnorm0)
 #pragma unroll
     for (int j = 0; j < 6; ++j) s.x[j] = x0[j];
     s.fnorm = fnorm0; s.par = 0.0; s.delta = 0.0; s.xnorm = 0.0;
-    s.iter = 1; s.nfev = 1; s.njev = 0; s.info = 0; s.need_jac = 1;
+    s.iter = 1; s.nfev = 1; s.njev = 0; s.nlm = 0; s.info = 0; s.need_jac = 1;
     s.dxn = 0.0; s.gnt = 0.0; s.gnorm = 0.0;
 }
 
@@ -221,6 +222,7 @@ PM_HD void lm_tick(const Prob &prob, LmTick &s, double ftol, double xtol, double
             if (par == 0.0) par = gradnorm / dxnorm;
             for (int it = 1;; ++it) {
                 if (par == 0.0) par = fmax(DWARF, 0.001 * paru);
+                ++s.nlm;
                 double S[21], rinv[6], w[6];
                 chol6p(s.A, par, 0.0, S, rinv);                    // S^T S = J^T J + par I
                 solve_lower6p(S, rinv, s.g, w);

@@ -12,6 +12,7 @@
 //   joint_refit_kernel     first-max hypothesis, masks, block-cooperative LM refit on all inliers
 //   umeyama_kernel         lib/aligning.py:580-622 (GT poses, compute_gt_pose.py:87)
 #include <stdlib.h>
+#include <cstdio>
 #include <cstdlib>
 #include "common.cuh"
 #include "pose_math.cuh"
@@ -508,6 +509,8 @@ constexpr int LM_PHASE_SHARE[LM_PHASES] = {1, 4, 32};         // phase p is size
 // measured 8.5 -> 6.9 ms for the joint stage alone; the pipelined throughput moves by 2% only, see DESIGN.md "overlap")
 constexpr int LM_BLOCKS_PER_SM = 4;
 constexpr int LM_SLOTS = 39;     // doubles per lane in shared memory: 36 point coordinates + joint direction
+// statistics slots inside the 64-int counter block of the workspace (joint_tail): totals over all solves of a call
+constexpr int LM_STAT_NJEV = 60, LM_STAT_NLM = 61;
 
 // objective_eval over one lane's 3+3 points; element e of the lane lives at pts[e * LMT] (conflict-free)
 struct LaneProb {
@@ -565,6 +568,7 @@ __global__ void __launch_bounds__(LMT, LM_BLOCKS_PER_SM) joint_lm_kernel(const J
     P.pts = my;
     pm::LmTick s;
     int t = -1;             // record this lane is solving
+    int njev0 = 0;          // Jacobian evaluations the record had when this lane took it
     bool more = true;       // unclaimed work may remain
     for (;;) {
         const bool want = t < 0 && more;
@@ -592,6 +596,7 @@ __global__ void __launch_bounds__(LMT, LM_BLOCKS_PER_SM) joint_lm_kernel(const J
                             s.par = r.par; s.delta = r.delta; s.xnorm = r.xnorm;
                             s.iter = r.iter; s.nfev = r.nfev; s.njev = r.njev;
                         }
+                        njev0 = s.njev;
                     }
                 }
             }
@@ -607,8 +612,12 @@ __global__ void __launch_bounds__(LMT, LM_BLOCKS_PER_SM) joint_lm_kernel(const J
 #pragma unroll
                 for (int j = 0; j < 6; ++j) r.x[j] = s.x[j];
                 a.nfev[t] = s.nfev;
+                atomicAdd(a.tail_count + LM_STAT_NJEV, s.njev - njev0);
+                atomicAdd(a.tail_count + LM_STAT_NLM, s.nlm);
                 t = -1;
             } else if (s.need_jac && s.nfev >= budget) {      // out of budget: hand the solve to the next phase
+                atomicAdd(a.tail_count + LM_STAT_NJEV, s.njev - njev0);
+                atomicAdd(a.tail_count + LM_STAT_NLM, s.nlm);
                 JointRec &r = recs[t];
 #pragma unroll
                 for (int j = 0; j < 6; ++j) r.x[j] = s.x[j];
@@ -1318,6 +1327,10 @@ extern "C" int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in
             static const int lm_cap = getenv("ANCSH_LM_BLOCKS_PER_SM") ? atoi(getenv("ANCSH_LM_BLOCKS_PER_SM")) : 1;
             const long cap = (long)sms * (lm_cap >= 1 && lm_cap <= LM_BLOCKS_PER_SM ? lm_cap : 1);
             int *lists = (int *)(recs + nsolves);              // 2 x nsolves work-list entries behind the records
+            // debugging aid: ANCSH_LM_TRACE=1 prints the duration of every LM phase (synchronises the stream)
+            static const bool lm_trace = getenv("ANCSH_LM_TRACE") != nullptr;
+            cudaEvent_t tev[LM_PHASES + 1];
+            if (lm_trace) { for (auto &e : tev) cudaEventCreate(&e); cudaEventRecord(tev[0], st); }
             for (int ph = 0; ph < LM_PHASES; ++ph) {
                 const long items = ph == 0 ? nsolves : nsolves / LM_PHASE_SHARE[ph] + 1;
                 const long per_lane = ph == 0 ? LM_SOLVES_PER_LANE : 1;     // later phases: few, long solves -> one lane each
@@ -1327,6 +1340,20 @@ extern "C" int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in
                                                                  ph == 0 ? nullptr : lists + (size_t)((ph - 1) & 1) * nsolves,
                                                                  lists + (size_t)(ph & 1) * nsolves);
                 ANCSH_CHECK_LAUNCH();
+                if (lm_trace) cudaEventRecord(tev[ph + 1], st);
+            }
+            if (lm_trace) {
+                cudaStreamSynchronize(st);
+                int h_tail[64];
+                cudaMemcpy(h_tail, a.tail_count, sizeof h_tail, cudaMemcpyDeviceToHost);
+                fprintf(stderr, "[lm trace] solves %ld:", nsolves);
+                for (int ph = 0; ph < LM_PHASES; ++ph) {
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, tev[ph], tev[ph + 1]);
+                    fprintf(stderr, "  phase %d: %d items %.3f ms", ph, ph == 0 ? (int)nsolves : h_tail[2 * ph + 1], ms);
+                }
+                fprintf(stderr, "  njev %d lmpar iterations %d\n", h_tail[LM_STAT_NJEV], h_tail[LM_STAT_NLM]);
+                for (auto &e : tev) cudaEventDestroy(e);
             }
         }
         joint_model_kernel<<<gsolve, JIT, 0, st>>>(a, recs);

@@ -126,6 +126,8 @@ class PoseSolver:
             nbytes = int(np.prod(shape)) * _ESIZE[dt]
             off = getattr(lay, name)
             res[name] = ws[off:off + nbytes].view(dt).view(shape)
+        cnt = ws[lay.joint_tail:lay.joint_tail + 256].view(torch.int32)
+        res["lm_njev_total"], res["lm_lmpar_total"] = cnt[60], cnt[61]      # totals over all LM solves of the call
         return res
 
     def solve(self, P, nocs, mask, joint_axis=None, joint_cls=None, idx_single=None, idx_joint0=None, idx_joint1=None):

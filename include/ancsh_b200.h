@@ -256,7 +256,9 @@ typedef struct {
     size_t joint_best;     /* int32 (B,K-1) */
     size_t joint_nfev;     /* int32 (B,K-1,niter_joint) residual evaluations each hypothesis' LM solve took */
     size_t joint_models;   /* f64 (B,K-1,niter_joint,26) per-hypothesis {R0[9],s0,t0[3],R1[9],s1,t1[3]} */
-    size_t joint_tail;     /* internal: work list of LM solves suspended after their first-phase budget */
+    size_t joint_tail;     /* internal: 64 int32 counters, then the LM solve records and the work lists of suspended solves.
+                              Counters [60] / [61] = Jacobian evaluations / lmpar iterations summed over all LM solves of the
+                              call (statistics for the FLOP model of the joint stage) */
     size_t total_bytes;
 } ancsh_pose_ws_t;
 
