@@ -76,6 +76,7 @@ def _sig(name, argtypes, restype=c_int):
 vp = ctypes.c_void_p
 ancsh_version = _sig("ancsh_version", [], ctypes.c_char_p)
 ancsh_launch_count = _sig("ancsh_launch_count", [], ctypes.c_ulonglong)
+ancsh_diag_fp64_fma = _sig("ancsh_diag_fp64_fma", [c_int, c_int, vp, vp])
 ancsh_fps = _sig("ancsh_fps", [c_int, c_int, c_int, vp, vp, vp, vp])
 ancsh_fps_two_level = _sig("ancsh_fps_two_level", [c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp])
 ancsh_gather_point = _sig("ancsh_gather_point", [c_int, c_int, c_int, vp, vp, vp, vp])

@@ -308,8 +308,8 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
     uint64_t *bar_acc = bar_empty + MAX_STAGES;                               // MMA thread -> workers: accumulators complete
     uint64_t *bar_ready = bar_acc + 1;                                        // workers -> MMA thread: operand written / TMEM drained
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bar_ready + 1);
-    int *s_cnt = reinterpret_cast<int *>(s_tmem + 4);                         // [8] hits found by each ball-query warp
-    int *s_idx = s_cnt + 8;                                                   // [8 warps][S] ball-query hit lists
+    int *s_cnt = reinterpret_cast<int *>(s_tmem + 4);                         // [2][8] hits found by each ball-query warp
+    int *s_idx = s_cnt + 16;                                                  // [2][8 warps][S] ball-query hit lists (double buffered)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) tc::tmem_alloc(s_tmem, TMEM_COLS);
@@ -399,76 +399,82 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_ready);
         };
-        for (int t = 0; t < ntiles; ++t) {
-            const int tile = blockIdx.x * ntiles + t;
-            const int tb = (warp == 0 ? 0 : 32);                  // trace base (warps 0 and 4 record)
-            if (warp == 0 || warp == 4) LEAN_TRACE(tb, 0);
-            const long R = (long)tile * TM + r;                   // row inside the cloud = centroid * S + sample
-            const int g = (int)(R / S);
-            int id;
-            if (BALL) {
-                // query_ball_point (tf_grouping_g.cu:3-36): first S points in index order with max(sqrt(d2), 1e-20) < radius,
-                // row padded with the first hit (all zeros when the ball is empty).  WPC warps per centroid, each scans a
-                // contiguous range of the points and keeps an ordered hit list; the lists are concatenated in range order.
-                {
-                    const int cl = warp / WPC, part = warp % WPC;          // centroid of the tile, range of this warp
-                    const int cen = tile * CPT + cl;
-                    const float *c3 = a.new_xyz + ((size_t)b * a.m + cen) * 3;
-                    const float x2 = __ldg(c3), y2 = __ldg(c3 + 1), z2 = __ldg(c3 + 2);
-                    const float *p1 = a.xyz + (size_t)b * a.n * 3;
-                    const int per = ((a.n + WPC - 1) / WPC + 31) & ~31;
-                    const int k_beg = part * per, k_end = min(a.n, k_beg + per);
-                    int *row = s_idx + warp * S;
-                    int cnt = 0;
-                    for (int base = k_beg; base < k_end && cnt < S; base += 64) {
-                        bool in[2];
+        // query_ball_point of one tile (tf_grouping_g.cu:3-36): first S points in index order with max(sqrt(d2), 1e-20) < radius,
+        // row padded with the first hit (all zeros when the ball is empty).  WPC warps per centroid, each scans a contiguous
+        // range of the points (128 per trip, 4 per lane) and keeps an ordered hit list; fetch_id() concatenates the lists in
+        // range order.  Runs in the shadow of the previous tile's first MMA unit (the workers would only wait there).
+        auto ball_tile = [&](int tile, int buf) {
+            const int cl = warp / WPC, part = warp % WPC;              // centroid of the tile, range of this warp
+            const int cen = tile * CPT + cl;
+            const float *c3 = a.new_xyz + ((size_t)b * a.m + cen) * 3;
+            const float x2 = __ldg(c3), y2 = __ldg(c3 + 1), z2 = __ldg(c3 + 2);
+            const float *p1 = a.xyz + (size_t)b * a.n * 3;
+            const int per = ((a.n + WPC - 1) / WPC + 31) & ~31;
+            const int k_beg = part * per, k_end = min(a.n, k_beg + per);
+            int *row = s_idx + (buf * 8 + warp) * S;
+            int cnt = 0;
+            for (int base = k_beg; base < k_end && cnt < S; base += 128) {
+                bool in[4];
 #pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const int k = base + u * 32 + lane;
-                            in[u] = false;
-                            if (k < k_end) {
-                                const float dx = x2 - __ldg(p1 + k * 3 + 0);
-                                const float dy = y2 - __ldg(p1 + k * 3 + 1);
-                                const float dz = z2 - __ldg(p1 + k * 3 + 2);
-                                float d = __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))));
-                                d = fmaxf(d, 1e-20f);
-                                in[u] = d < a.radius;
-                            }
-                        }
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const unsigned mask = __ballot_sync(0xFFFFFFFFu, in[u]);
-                            const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
-                            if (in[u] && pos < S) row[pos] = base + u * 32 + lane;
-                            cnt += __popc(mask);
-                        }
+                for (int u = 0; u < 4; ++u) {
+                    const int k = base + u * 32 + lane;
+                    in[u] = false;
+                    if (k < k_end) {
+                        const float dx = x2 - __ldg(p1 + k * 3 + 0);
+                        const float dy = y2 - __ldg(p1 + k * 3 + 1);
+                        const float dz = z2 - __ldg(p1 + k * 3 + 2);
+                        float d = __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))));
+                        d = fmaxf(d, 1e-20f);
+                        in[u] = d < a.radius;
                     }
-                    if (lane == 0) s_cnt[warp] = min(cnt, S);
                 }
-                gather_sync();
-                if (warp == 0 || warp == 4) LEAN_TRACE(tb, 1);
-                {
-                    const int cl = r / S;
-                    int j = r - cl * S, total = 0, first = 0, found = -1;
-                    bool have_first = false;
 #pragma unroll
-                    for (int p = 0; p < WPC; ++p) {
-                        const int w = cl * WPC + p, cp = s_cnt[w];
-                        if (!have_first && cp > 0) { first = s_idx[w * S]; have_first = true; }
-                        if (found < 0 && j < cp) found = s_idx[w * S + j];
-                        j -= cp; total += cp;
-                    }
-                    id = found >= 0 ? found : first;
-                    if (a.idx_out && h == 0) a.idx_out[(size_t)b * a.m * S + R] = id;
-                    if (a.cnt_out && h == 0 && r % S == 0) a.cnt_out[(size_t)b * a.m + g] = min(total, S);
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned mask = __ballot_sync(0xFFFFFFFFu, in[u]);
+                    const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+                    if (in[u] && pos < S) row[pos] = base + u * 32 + lane;
+                    cnt += __popc(mask);
                 }
-            } else {
-                id = __ldg(a.idx_in + (size_t)b * a.m * S + R);
             }
-            float rel[3];
+            if (lane == 0) s_cnt[buf * 8 + warp] = min(cnt, S);
+        };
+        // index of this thread's row (after a gather_sync that follows ball_tile of the same buffer)
+        auto fetch_id = [&](int tile, int buf) -> int {
+            const long R = (long)tile * TM + r;                        // row inside the cloud = centroid * S + sample
+            if (!BALL) return __ldg(a.idx_in + (size_t)b * a.m * S + R);
+            const int cl = r / S;
+            int j = r - cl * S, total = 0, first = 0, found = -1;
+            bool have_first = false;
+#pragma unroll
+            for (int p = 0; p < WPC; ++p) {
+                const int w = buf * 8 + cl * WPC + p, cp = s_cnt[w];
+                if (!have_first && cp > 0) { first = s_idx[w * S]; have_first = true; }
+                if (found < 0 && j < cp) found = s_idx[w * S + j];
+                j -= cp; total += cp;
+            }
+            const int id = found >= 0 ? found : first;
+            if (a.idx_out && h == 0) a.idx_out[(size_t)b * a.m * S + R] = id;
+            if (a.cnt_out && h == 0 && r % S == 0) a.cnt_out[(size_t)b * a.m + R / S] = min(total, S);
+            return id;
+        };
+        auto load_rel = [&](int tile, int id, float (&rel)[3]) {
+            const int g = (int)(((long)tile * TM + r) / S);
 #pragma unroll
             for (int c = 0; c < 3; ++c)
                 rel[c] = __fsub_rn(__ldg(a.xyz + ((size_t)b * a.n + id) * 3 + c), __ldg(a.new_xyz + ((size_t)b * a.m + g) * 3 + c));
+        };
+
+        const int tile0 = blockIdx.x * ntiles;
+        int id;
+        float rel[3];
+        if (BALL) { ball_tile(tile0, 0); gather_sync(); }
+        id = fetch_id(tile0, 0);
+        load_rel(tile0, id, rel);
+        for (int t = 0; t < ntiles; ++t) {
+            const int tile = tile0 + t;
+            const bool has_next = t + 1 < ntiles;
+            const int tb = (warp == 0 ? 0 : 32);                  // trace base (warps 0 and 4 record)
+            if (warp == 0 || warp == 4) LEAN_TRACE(tb, 0);
             if (C == 0) {
                 if (h == 0) conv0_xyz<0>(a, rel, r, A_hi, A_lo);
                 else conv0_xyz<32>(a, rel, r, A_hi, A_lo);
@@ -503,6 +509,9 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
             }
             if (warp == 0 || warp == 4) LEAN_TRACE(tb, 2);
             ready();                                              // operand gathered
+            // ball query of the NEXT tile while the tensor pipe runs this tile's first unit
+            if (BALL && has_next) ball_tile(tile + 1, (t + 1) & 1);
+            if (warp == 0 || warp == 4) LEAN_TRACE(tb, 3);
             // ---- in-place layers ----
             if (NSTD == 2) {
                 tc::mbar_wait(bar_acc, uc & 1u); ++uc;
@@ -520,6 +529,14 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
                 if (warp == 0 || warp == 4) LEAN_TRACE(tb, 7);
                 ready();
             }
+            // index + relative coordinate of this thread's row of the NEXT tile: the loads fly under the pooled units
+            int id_n = 0;
+            float rel_n[3] = {0.f, 0.f, 0.f};
+            if (has_next) {
+                if (BALL) gather_sync();                          // every warp's hit list of the next tile is complete
+                id_n = fetch_id(tile + 1, (t + 1) & 1);
+                load_rel(tile + 1, id_n, rel_n);
+            }
             // ---- pooled layer, transposed: lane = output channel ----
 #pragma unroll
             for (int blk = 0; blk < NTB; ++blk) {
@@ -532,6 +549,8 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
                 if (warp == 0 || warp == 4) LEAN_TRACE(tb, 10 + 3 * blk);
                 ready();
             }
+            id = id_n;
+            rel[0] = rel_n[0]; rel[1] = rel_n[1]; rel[2] = rel_n[2];
         }
         // the last ready() was consumed by the MMA thread before it left its loop; TMEM is idle
         asm volatile("bar.sync 3, %0;" ::"n"(NWORK) : "memory");
@@ -554,7 +573,7 @@ int launch(const SaLeanArgs &a, dim3 grid, cudaStream_t st)
 {
     using P = Plan<C, N0, N1, N2>;
     const size_t smem = (size_t)2 * P::K8 * 2048 + 4096 + (size_t)P::NST * P::SLOT_BYTES + (2 * MAX_STAGES + 2) * sizeof(uint64_t) + 16 +
-                        8 * sizeof(int) + 8 * S * sizeof(int);
+                        16 * sizeof(int) + 16 * S * sizeof(int);
     auto k = sa_lean_kernel<C, N0, N1, N2, S, BALL, ACC1>;
     ANCSH_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ANCSH_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include "../../include/ancsh_b200.h"
 
 struct TcLayer {
     const __half *Wimg;   // [K/8][2 (hi,lo)][N][8] fp16: W^T pre-split and pre-tiled (weights.tc_image)
@@ -42,11 +43,16 @@ int sa_lean_launch(const SaLeanArgs2 &a, int B, cudaStream_t st);
 // ---- generic row-tile chain (feature propagation / heads) ------------------------------------------------------
 enum { TC_DST_INPLACE = 0, TC_DST_GLOBAL = 1 };
 
+enum { TC_ACT_NONE = 0, TC_ACT_NOCS_HEADS = 1, TC_ACT_JOINT_HEADS = 2 };
+
 struct ChainStep {
     TcLayer L;
     int dst;        // TC_DST_INPLACE: output becomes the next step's operand; TC_DST_GLOBAL: rows go to `out`, operand kept
     float *out;     // [rows_total][ldo] f32; with TC_DST_INPLACE and out != NULL the rows are written as well
     int ldo;
+    int act;        // TC_DST_GLOBAL only: TC_ACT_*_HEADS = the step is a packed head layer; its activations
+                    // (lib/architecture.py:122-139, 150-157) run in the epilogue and the results go straight to
+                    // ChainTcArgs::pred (out may be NULL)
 };
 
 struct ChainTcArgs {
@@ -60,6 +66,20 @@ struct ChainTcArgs {
     int nsteps;
     int pool_S;               // > 0 (warp-specialised kernel only): the last step is max-pooled over groups of pool_S consecutive
                               // rows (multiple of 32, ReLU output) into S[last].out = [rows_total / pool_S][N]
+    // Fused feature propagation (pointnet_util.py:206-236; warp-specialised kernel only): with fp_points2 != NULL the X1 part
+    // of a row is three_interpolate(fp_points2, idx, weight) evaluated in the gather (X1 itself is ignored), where
+    // (idx, weight) = three_nn(fp_xyz1, fp_xyz2) + the inverse-distance weights are computed by the tile (or read from the
+    // tables of an earlier forward over the same clouds: shared geometry).
+    const float *fp_points2;  // [clouds][fp_m2][C1]
+    const float *fp_xyz1;     // [clouds][rows_per_cloud][3] query points
+    const float *fp_xyz2;     // [clouds][fp_m2][3] known points
+    int fp_m2;
+    const int *fp_idx_in;     // [rows_total][3] or NULL
+    const float *fp_w_in;     // [rows_total][3] or NULL
+    int *fp_idx_out;          // optional copies of the tables computed here
+    float *fp_w_out;
+    ancsh_pred_t pred;        // destination of the TC_ACT_* steps
+    int n_parts, mixed;
     int kmax8;                // filled by the launcher
     uint32_t tmem_cols;
 };

@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "net_tc.cuh"
+#include "ops.cuh"
 
 namespace {
 
@@ -48,6 +49,7 @@ struct Unit {
     int ksl;               // k16 steps per ring stage
     int nsl;               // ring stages (slices) per chunk
     int relu, inplace, pool, ldo;
+    int act;               // TC_ACT_*: head activations in the epilogue
 };
 
 struct Chain2Args {
@@ -61,6 +63,15 @@ struct Chain2Args {
     int n, m, S, C;
     const float *W0, *b0;  // xyz-only set abstraction: f32 weights [>=3][N0] / bias of the first conv, evaluated in the gather
     int N0, relu0;         // (N0 == 0: disabled)
+    // fused feature propagation (FP kernels): X1 part of a row = blend of three rows of fp_points2
+    const float *fp_points2, *fp_xyz1, *fp_xyz2;
+    const int *fp_idx_in;
+    const float *fp_w_in;
+    int *fp_idx_out;
+    float *fp_w_out;
+    int fp_m2;
+    ancsh_pred_t pred;     // outputs of the head units
+    int n_parts, mixed;
     int K0;                // operand width of the first tensor-core layer (multiple of 16)
     int kmax8;             // operand image width / 8
     int nst;               // ring stages
@@ -184,7 +195,49 @@ __device__ __forceinline__ void pool_store2(float *orow, int S, int lane, const 
     }
 }
 
-template <bool SA, int MINB>
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// Head activations of one row (lib/architecture.py:122-139, 150-157) on the 32 leading columns of a packed head layer:
+//   nocs_net  [W(K) | nocs(3K) | scale(K) | trans(3K) | confi(1)]  (mixed)  /  [W(K) | nocs(3K) | confi(1)]
+//   joint_net [joint_axis(3) | unitvec(3) | heatmap(1) | index(3)]
+// c0 = first column held in v (0 or 32); every output pointer may be NULL (not requested).
+__device__ __forceinline__ void head_activations(int act, int c0, float (&x)[32], long r, int K, int mixed, const ancsh_pred_t &o)
+{
+    if (act == TC_ACT_NOCS_HEADS) {
+        const int confi_col = mixed ? 8 * K : 4 * K;
+        if (c0 == 0) {
+            float mx = x[0];
+            for (int k = 1; k < K; ++k) mx = fmaxf(mx, x[k]);
+            float sum = 0.f;
+            for (int k = 0; k < K; ++k) { x[k] = expf(x[k] - mx); sum += x[k]; }
+            if (o.W) for (int k = 0; k < K; ++k) o.W[(size_t)r * K + k] = x[k] / sum;
+            for (int k = K; k < 4 * K; ++k) { x[k] = sigmoidf_(x[k]); if (o.nocs_per_point) o.nocs_per_point[(size_t)r * 3 * K + (k - K)] = x[k]; }
+            if (mixed) {
+                for (int k = 4 * K; k < 5 * K; ++k) { x[k] = sigmoidf_(x[k]); if (o.global_scale) o.global_scale[(size_t)r * K + (k - 4 * K)] = x[k]; }
+                for (int k = 5 * K; k < 8 * K; ++k) { x[k] = tanhf(x[k]); if (o.global_translation) o.global_translation[(size_t)r * 3 * K + (k - 5 * K)] = x[k]; }
+                if (o.gocs_per_point)
+                    for (int k = 0; k < 3 * K; ++k)
+                        o.gocs_per_point[(size_t)r * 3 * K + k] = __fadd_rn(__fmul_rn(x[K + k], x[4 * K + k / 3]), x[5 * K + k]);
+            }
+        }
+        if (confi_col >= c0 && confi_col < c0 + 32 && o.confi_per_point) o.confi_per_point[r] = sigmoidf_(x[confi_col - c0]);
+    } else if (c0 == 0) {
+        if (o.joint_axis_per_point) for (int k = 0; k < 3; ++k) o.joint_axis_per_point[(size_t)r * 3 + k] = tanhf(x[k]);
+        if (o.unitvec_per_point) for (int k = 0; k < 3; ++k) o.unitvec_per_point[(size_t)r * 3 + k] = tanhf(x[3 + k]);
+        if (o.heatmap_per_point) o.heatmap_per_point[r] = sigmoidf_(x[6]);
+        if (o.index_per_point) {
+            const float m2 = fmaxf(x[7], fmaxf(x[8], x[9]));
+            const float e0 = expf(x[7] - m2), e1 = expf(x[8] - m2), e2 = expf(x[9] - m2), es = e0 + e1 + e2;
+            o.index_per_point[(size_t)r * 3 + 0] = e0 / es;
+            o.index_per_point[(size_t)r * 3 + 1] = e1 / es;
+            o.index_per_point[(size_t)r * 3 + 2] = e2 / es;
+        }
+    }
+}
+
+// SA: set-abstraction gather (ball-query indices).  FP: feature-propagation gather (three_nn + three_interpolate built into
+// the rows) and head activations in the epilogue.
+template <bool SA, int MINB, bool FP>
 __global__ void __launch_bounds__(NTHR, MINB) chain2_kernel(const __grid_constant__ Chain2Args a)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -195,8 +248,11 @@ __global__ void __launch_bounds__(NTHR, MINB) chain2_kernel(const __grid_constan
     uint64_t *bar_empty = bar_full + MAX_STAGES;
     uint64_t *bar_acc = bar_empty + MAX_STAGES;
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bar_acc + 1);
+    int *s_nni = reinterpret_cast<int *>(s_tmem + 4);          // FP: [128][3] three_nn indices of the tile's rows
+    float *s_nnw = reinterpret_cast<float *>(s_nni + TM * 3);  // FP: [128][3] interpolation weights
 
     constexpr int CW = MINB >= 3 ? 16 : 32;   // columns a worker handles at a time (register budget)
+    static_assert(!FP || (!SA && MINB == 2), "the FP variant is a 2-CTA rows kernel");
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) tc::tmem_alloc(s_tmem, a.tmem_cols);
     if (tid == NWORK) {
@@ -336,6 +392,94 @@ __global__ void __launch_bounds__(NTHR, MINB) chain2_kernel(const __grid_constan
                 }
                 split8(v, reinterpret_cast<uint4 *>(A_hi + (size_t)kc * 2048 + r * 16), reinterpret_cast<uint4 *>(A_lo + (size_t)kc * 2048 + r * 16));
             }
+        } else if (FP) {
+            // ---- three_nn + inverse-distance weights of the tile's rows (tf_interpolate.cpp:60-105, pointnet_util.py:217-222):
+            // two adjacent lanes per row, each scans half of the known points in index order; exact un-fused f32 ----
+            const long row0 = (long)blockIdx.x * TM;
+            const long cloud = row0 / a.rows_per_cloud;
+            if (a.fp_idx_in) {
+                for (int i = tid; i < TM * 3; i += NWORK) {
+                    s_nni[i] = __ldg(a.fp_idx_in + (size_t)row0 * 3 + i);
+                    s_nnw[i] = __ldg(a.fp_w_in + (size_t)row0 * 3 + i);
+                }
+            } else {
+                const int row = tid >> 1, part = tid & 1;
+                const float *q = a.fp_xyz1 + (size_t)(row0 + row) * 3;
+                const float x1 = __ldg(q), y1 = __ldg(q + 1), z1 = __ldg(q + 2);
+                const float *kn = a.fp_xyz2 + (size_t)cloud * a.fp_m2 * 3;
+                const int chunk = (a.fp_m2 + 1) / 2;
+                const int k0 = part * chunk, k1 = min(a.fp_m2, k0 + chunk);
+                Best3 best;
+                best.init();
+                for (int k = k0; k < k1; ++k)
+                    best.insert(nn_dist_unfused(__ldg(kn + k * 3), __ldg(kn + k * 3 + 1), __ldg(kn + k * 3 + 2), x1, y1, z1), k);
+                Best3 o;
+                o.d1 = __shfl_xor_sync(0xFFFFFFFFu, best.d1, 1); o.i1 = __shfl_xor_sync(0xFFFFFFFFu, best.i1, 1);
+                o.d2 = __shfl_xor_sync(0xFFFFFFFFu, best.d2, 1); o.i2 = __shfl_xor_sync(0xFFFFFFFFu, best.i2, 1);
+                o.d3 = __shfl_xor_sync(0xFFFFFFFFu, best.d3, 1); o.i3 = __shfl_xor_sync(0xFFFFFFFFu, best.i3, 1);
+                if (part == 0) {
+                    best.merge_higher(o);
+                    float w1, w2, w3;
+                    three_weights(best.d1, best.d2, best.d3, w1, w2, w3);
+                    s_nnw[row * 3 + 0] = w1; s_nnw[row * 3 + 1] = w2; s_nnw[row * 3 + 2] = w3;
+                    s_nni[row * 3 + 0] = best.i1; s_nni[row * 3 + 1] = best.i2; s_nni[row * 3 + 2] = best.i3;
+                    if (a.fp_idx_out) {                              // geometry tables for a second network over the same clouds
+                        const size_t g = (size_t)(row0 + row) * 3;
+                        a.fp_w_out[g] = w1; a.fp_w_out[g + 1] = w2; a.fp_w_out[g + 2] = w3;
+                        a.fp_idx_out[g] = best.i1; a.fp_idx_out[g + 1] = best.i2; a.fp_idx_out[g + 2] = best.i3;
+                    }
+                }
+            }
+            asm volatile("bar.sync 2, %0;" ::"n"(NWORK) : "memory");
+            // ---- rows: [three_interpolate(points2) (C1) | X2 (C2) | zero pad] (pointnet_util.py:223-228) ----
+            R = row0 + r;
+            const float w1 = s_nnw[r * 3], w2 = s_nnw[r * 3 + 1], w3 = s_nnw[r * 3 + 2];
+            const float *p1 = a.fp_points2 + ((size_t)cloud * a.fp_m2 + s_nni[r * 3 + 0]) * a.C1;
+            const float *p2 = a.fp_points2 + ((size_t)cloud * a.fp_m2 + s_nni[r * 3 + 1]) * a.C1;
+            const float *p3 = a.fp_points2 + ((size_t)cloud * a.fp_m2 + s_nni[r * 3 + 2]) * a.C1;
+            const float *r2 = a.X2 ? a.X2 + (size_t)R * a.C2 : nullptr;
+            const int nkc1 = a.C1 / 8;                                // C1 % 8 == 0 (launcher)
+            for (int kc = h; kc < nkc1; kc += 4) {                    // two 8-channel pieces per trip: 12 loads in flight
+                const int kb = kc + 2;
+                float4 u[4], v[4], w[4];
+                u[0] = ldg4(p1 + kc * 8); u[1] = ldg4(p1 + kc * 8 + 4);
+                v[0] = ldg4(p2 + kc * 8); v[1] = ldg4(p2 + kc * 8 + 4);
+                w[0] = ldg4(p3 + kc * 8); w[1] = ldg4(p3 + kc * 8 + 4);
+                if (kb < nkc1) {
+                    u[2] = ldg4(p1 + kb * 8); u[3] = ldg4(p1 + kb * 8 + 4);
+                    v[2] = ldg4(p2 + kb * 8); v[3] = ldg4(p2 + kb * 8 + 4);
+                    w[2] = ldg4(p3 + kb * 8); w[3] = ldg4(p3 + kb * 8 + 4);
+                }
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const int kk = kc + 2 * t;
+                    if (kk >= nkc1) break;
+                    float x[8];
+                    x[0] = interp3_unfused(u[2 * t].x, v[2 * t].x, w[2 * t].x, w1, w2, w3);
+                    x[1] = interp3_unfused(u[2 * t].y, v[2 * t].y, w[2 * t].y, w1, w2, w3);
+                    x[2] = interp3_unfused(u[2 * t].z, v[2 * t].z, w[2 * t].z, w1, w2, w3);
+                    x[3] = interp3_unfused(u[2 * t].w, v[2 * t].w, w[2 * t].w, w1, w2, w3);
+                    x[4] = interp3_unfused(u[2 * t + 1].x, v[2 * t + 1].x, w[2 * t + 1].x, w1, w2, w3);
+                    x[5] = interp3_unfused(u[2 * t + 1].y, v[2 * t + 1].y, w[2 * t + 1].y, w1, w2, w3);
+                    x[6] = interp3_unfused(u[2 * t + 1].z, v[2 * t + 1].z, w[2 * t + 1].z, w1, w2, w3);
+                    x[7] = interp3_unfused(u[2 * t + 1].w, v[2 * t + 1].w, w[2 * t + 1].w, w1, w2, w3);
+                    split8(x, reinterpret_cast<uint4 *>(A_hi + (size_t)kk * 2048 + r * 16), reinterpret_cast<uint4 *>(A_lo + (size_t)kk * 2048 + r * 16));
+                }
+            }
+            for (int kc = nkc1 + h; kc < a.K0 / 8; kc += 2) {        // skip features and the zero padding
+                float x[8];
+                if (r2 && (a.C2 & 7) == 0 && kc * 8 + 8 <= a.C1 + a.C2) {
+                    const float4 q0 = ldg4(r2 + (kc * 8 - a.C1)), q1 = ldg4(r2 + (kc * 8 - a.C1) + 4);
+                    x[0] = q0.x; x[1] = q0.y; x[2] = q0.z; x[3] = q0.w; x[4] = q1.x; x[5] = q1.y; x[6] = q1.z; x[7] = q1.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int c = kc * 8 + i;
+                        x[i] = (r2 && c < a.C1 + a.C2) ? __ldg(r2 + (c - a.C1)) : 0.f;
+                    }
+                }
+                split8(x, reinterpret_cast<uint4 *>(A_hi + (size_t)kc * 2048 + r * 16), reinterpret_cast<uint4 *>(A_lo + (size_t)kc * 2048 + r * 16));
+            }
         } else {
             R = (long)blockIdx.x * TM + r;
             const float *r1 = a.X1 + (size_t)R * a.C1;
@@ -384,7 +528,9 @@ __global__ void __launch_bounds__(NTHR, MINB) chain2_kernel(const __grid_constan
 #pragma unroll
                         for (int i = 0; i < CW; ++i) v[i] = fmaxf(v[i], 0.f);
                     }
-                    if (U.pool) {
+                    if (FP && U.act) {
+                        if constexpr (FP) head_activations(U.act, col, v, R, a.n_parts, a.mixed, a.pred);
+                    } else if (U.pool) {
                         const long g = ((long)blockIdx.x * TM + wq * 32) / a.S;
                         pool_store2<CW>(U.out + ((size_t)b * a.m + g) * U.Nfull + col, a.S, lane, v);
                     } else if (U.out) {
@@ -412,6 +558,7 @@ struct LayerSpec {
     int ldo;
     const float *bias_override;
     long bias_stride;
+    int act;
 };
 
 int build_units(Chain2Args &a, const LayerSpec *spec, int nspec, size_t *smem_out, int *minb_out)
@@ -429,7 +576,7 @@ int build_units(Chain2Args &a, const LayerSpec *spec, int nspec, size_t *smem_ou
     }
     a.kmax8 = kmax / 8;
     const size_t opbytes = (size_t)2 * a.kmax8 * 2048;
-    const size_t tail = (2 * MAX_STAGES + 1) * sizeof(uint64_t) + 16;
+    const size_t tail = (2 * MAX_STAGES + 1) * sizeof(uint64_t) + 16 + (a.fp_points2 ? (size_t)TM * 3 * 8 : 0);
     size_t limit = 113 * 1024;                                 // two CTAs per SM when the operand is small enough
     a.tmem_cols = 256;
     a.nst = MAX_STAGES;
@@ -473,7 +620,7 @@ int build_units(Chain2Args &a, const LayerSpec *spec, int nspec, size_t *smem_ou
             U.G = 1;                                           // filled below (needs the final tmem_cols)
             U.ksl = STAGE_BYTES / (64 * nc);
             U.nsl = (L.K / 16 + U.ksl - 1) / U.ksl;
-            U.relu = L.relu; U.inplace = spec[i].inplace; U.pool = spec[i].pool;
+            U.relu = L.relu; U.inplace = spec[i].inplace; U.pool = spec[i].pool; U.act = spec[i].act;
         }
     }
     for (int u = 0; u < a.nunits; ++u) {
@@ -484,12 +631,12 @@ int build_units(Chain2Args &a, const LayerSpec *spec, int nspec, size_t *smem_ou
     return ANCSH_OK;
 }
 
-template <bool SA, int MINB>
+template <bool SA, int MINB, bool FP = false>
 int launch_chain2(const Chain2Args &a, dim3 grid, size_t smem, cudaStream_t st)
 {
-    ANCSH_CUDA(cudaFuncSetAttribute(chain2_kernel<SA, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ANCSH_CUDA(cudaFuncSetAttribute(chain2_kernel<SA, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    chain2_kernel<SA, MINB><<<grid, NTHR, smem, st>>>(a);
+    ANCSH_CUDA(cudaFuncSetAttribute(chain2_kernel<SA, MINB, FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ANCSH_CUDA(cudaFuncSetAttribute(chain2_kernel<SA, MINB, FP>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    chain2_kernel<SA, MINB, FP><<<grid, NTHR, smem, st>>>(a);
     ANCSH_CHECK_LAUNCH();
     return ANCSH_OK;
 }
@@ -531,12 +678,30 @@ int chain_tc2_launch(const ChainTcArgs &c, long rows_total, cudaStream_t st)
     a.X1 = c.X1; a.X2 = c.X2; a.C1 = c.C1; a.C2 = c.C2;
     a.rows_per_cloud = c.rows_per_cloud > 0 ? c.rows_per_cloud : 1;
     a.K0 = c.S[0].L.K;
+    const bool fp = c.fp_points2 != nullptr;
+    bool heads = false;
+    for (int i = 0; i < c.nsteps; ++i) heads = heads || c.S[i].act != TC_ACT_NONE;
+    if (fp) {
+        // a tile must not straddle clouds; the three_nn tables come in pairs
+        if (a.rows_per_cloud % TM != 0 || !c.fp_xyz1 || !c.fp_xyz2 || c.fp_m2 < 1 || (c.fp_idx_in == nullptr) != (c.fp_w_in == nullptr) ||
+            (c.fp_idx_out == nullptr) != (c.fp_w_out == nullptr))
+            return ANCSH_ERR_INVALID_ARG;
+        a.fp_points2 = c.fp_points2; a.fp_xyz1 = c.fp_xyz1; a.fp_xyz2 = c.fp_xyz2; a.fp_m2 = c.fp_m2;
+        a.fp_idx_in = c.fp_idx_in; a.fp_w_in = c.fp_w_in; a.fp_idx_out = c.fp_idx_out; a.fp_w_out = c.fp_w_out;
+    }
+    if (heads) {
+        // the epilogue keeps W | nocs | scale | trans of a row in one 32-column group (gocs = nocs * scale + trans)
+        if (!fp || c.n_parts < 1 || (c.mixed ? 8 * c.n_parts : 4 * c.n_parts) > 32) return ANCSH_ERR_UNSUPPORTED;
+        a.pred = c.pred; a.n_parts = c.n_parts; a.mixed = c.mixed;
+    }
     LayerSpec spec[8] = {};
     for (int i = 0; i < c.nsteps; ++i) {
         spec[i].L = c.S[i].L;
         spec[i].inplace = c.S[i].dst == TC_DST_INPLACE;
         spec[i].out = c.S[i].out; spec[i].ldo = c.S[i].ldo;
-        if (c.S[i].dst == TC_DST_GLOBAL && !c.S[i].out) return ANCSH_ERR_INVALID_ARG;
+        spec[i].act = c.S[i].act;
+        if (c.S[i].act != TC_ACT_NONE && (c.S[i].dst != TC_DST_GLOBAL || c.S[i].L.N != 64 || c.S[i].L.relu)) return ANCSH_ERR_INVALID_ARG;
+        if (c.S[i].dst == TC_DST_GLOBAL && !c.S[i].out && c.S[i].act == TC_ACT_NONE) return ANCSH_ERR_INVALID_ARG;
         const bool pooled = c.pool_S > 0 && i == c.nsteps - 1;
         if (!pooled && c.S[i].out && (c.S[i].ldo < c.S[i].L.N || c.S[i].ldo % 4 != 0)) return ANCSH_ERR_INVALID_ARG;
     }
@@ -555,6 +720,10 @@ int chain_tc2_launch(const ChainTcArgs &c, long rows_total, cudaStream_t st)
     int minb = 2;
     int rc = build_units(a, spec, c.nsteps, &smem, &minb);
     if (rc) return rc;
+    if (fp) {
+        if (minb != 2) return ANCSH_ERR_UNSUPPORTED;
+        return launch_chain2<false, 2, true>(a, dim3((unsigned)(rows_total / TM)), smem, st);
+    }
     if (minb == 3) return launch_chain2<false, 3>(a, dim3((unsigned)(rows_total / TM)), smem, st);
     return launch_chain2<false, 2>(a, dim3((unsigned)(rows_total / TM)), smem, st);
 }

@@ -290,10 +290,36 @@ __global__ void __launch_bounds__(256) three_interp_kernel(int m, int c, long ro
         dst[l] = interp3_unfused(__ldg(p1 + l), __ldg(p2 + l), __ldg(p3 + l), w1, w2, w3);
 }
 
+// Peak probe of the FP64 pipe (the roofline denominator of the f64 pose kernels; MEASURED_PEAKS.json has no FP64 figure):
+// 8 independent DFMA chains per thread, enough resident warps to cover the pipe latency.
+__global__ void __launch_bounds__(256) fp64_fma_probe_kernel(int iters, double *sink)
+{
+    double a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = 1.0 + (double)(threadIdx.x + i) * 1e-9;
+    const double m = 1.0 - 1e-12, c = 1e-13;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = fma(a[i], m, c);
+    }
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += a[i];
+    if (t == 123.456) sink[0] = t;            // never true: keeps the chains alive
+}
+
 // =====================================================================================================
 // C ABI
 // =====================================================================================================
 extern "C" {
+
+int ancsh_diag_fp64_fma(int blocks, int iters, double *sink, void *stream)
+{
+    if (blocks <= 0 || iters <= 0 || !sink) return ANCSH_ERR_INVALID_ARG;
+    fp64_fma_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, sink);
+    ANCSH_CHECK_LAUNCH();
+    return ANCSH_OK;
+}
 
 const char *ancsh_version(void) { return "ancsh_b200 0.2 sm_100a"; }
 

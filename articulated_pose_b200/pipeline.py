@@ -48,8 +48,9 @@ class AncshPipeline:
             self._buf[key] = d
         return self._buf[key]
 
-    def run_device(self, P, joint_cls, net_events=None, net_b_events=None, pose_events=None):
-        """P (B,N,3) f32 CUDA, joint_cls (B,N) int32 CUDA -> dict of CUDA pose tensors (ancsh_pose_out_t)."""
+    def run_device(self, P, joint_cls, net_events=None, net_b_events=None, pose_events=None, seed=None):
+        """P (B,N,3) f32 CUDA, joint_cls (B,N) int32 CUDA -> dict of CUDA pose tensors (ancsh_pose_out_t).
+        seed: Philox key of this batch's RANSAC draws (default: the pipeline's)."""
         B, N, _ = P.shape
         buf = self._buffers(B, N)
         pred = self.net.forward_device(P, buf["pred"], stage_events=net_events)
@@ -57,7 +58,7 @@ class AncshPipeline:
         if self.net_npcs is not None:
             src = self.net_npcs.forward_device(P, buf["pred_b"], stage_events=net_b_events, geometry_from=self.net)
         return self.pose.solve_device(P, src["nocs_per_point"], src["W"], pred["joint_axis_per_point"], joint_cls,
-                                      out=buf["pose"], stage_events=pose_events)
+                                      out=buf["pose"], stage_events=pose_events, seed=seed)
 
     # ---- stream-pipelined submission: the pose stage of batch i overlaps the forwards of batch i+1 ----------
     def _slot(self, B, N, slot):
@@ -70,7 +71,7 @@ class AncshPipeline:
             self._slots[key] = d
         return self._slots[key]
 
-    def submit(self, P, joint_cls, slot=0, net_events=None, net_b_events=None, pose_events=None):
+    def submit(self, P, joint_cls, slot=0, net_events=None, net_b_events=None, pose_events=None, seed=None):
         """Asynchronous run_device: the forwards are enqueued on the current stream, the pose stage on an
         internal side stream (one per slot) that waits for them; buffers are per `slot` (cycle through
         N_SLOTS slots).  The slow tail
@@ -96,7 +97,7 @@ class AncshPipeline:
         with torch.cuda.stream(ps):
             ps.wait_event(sl["fwd_done"])
             out = self.pose.solve_device(P, src["nocs_per_point"], src["W"], pred["joint_axis_per_point"], joint_cls,
-                                         out=sl["pose"], stage_events=pose_events, ws_slot=slot)
+                                         out=sl["pose"], stage_events=pose_events, ws_slot=slot, seed=seed)
             sl["pose_done"].record(ps)
         sl["used"] = True
         return out
@@ -108,9 +109,10 @@ class AncshPipeline:
             if sl["used"]:
                 main.wait_event(sl["pose_done"])
 
-    def run_many(self, batches, unpack=False):
+    def run_many(self, batches, unpack=False, seeds=None):
         """Host API for a stream of batches [(P, joint_cls), ...] (all the same shape): pinned H2D, forwards and
-        pose stages pipelined over two slots, D2H of the pose records.  Returns one result per batch."""
+        pose stages pipelined over N_SLOTS slots, D2H of the pose records.  Returns one result per batch.
+        seeds: optional Philox key per batch."""
         if not batches:
             return []
         B, N, _ = batches[0][0].shape
@@ -155,7 +157,8 @@ class AncshPipeline:
                 bufs[slot]["hjc"].numpy()[...] = jc
                 bufs[slot]["P"].copy_(bufs[slot]["hP"], non_blocking=True)
                 bufs[slot]["jc"].copy_(bufs[slot]["hjc"], non_blocking=True)
-                pending[slot] = (i, self.submit(bufs[slot]["P"], bufs[slot]["jc"], slot=slot))
+                pending[slot] = (i, self.submit(bufs[slot]["P"], bufs[slot]["jc"], slot=slot,
+                                                seed=None if seeds is None else seeds[i]))
             for k in range(self.N_SLOTS):              # oldest first
                 drain((len(batches) + k) % self.N_SLOTS)
         return results

@@ -77,10 +77,11 @@ class PoseSolver:
         return {k: torch.empty(shp(B, self.K, N, J), dtype=dt, device=self.device) for k, (dt, shp) in _OUT_SPEC.items()}
 
     def solve_device(self, P, nocs, mask, joint_axis=None, joint_cls=None, idx_single=None, idx_joint0=None,
-                     idx_joint1=None, out=None, stage_events=None, ws_slot=0):
+                     idx_joint1=None, out=None, stage_events=None, ws_slot=0, seed=None):
         """P (B,N,3) f32, nocs (B,N,3K) f32, mask (B,N,K) f32, joint_axis (B,N,3) f32, joint_cls (B,N) int32;
         optional idx_single (B,K,niter_single,3), idx_joint0/1 (B,K-1,niter_joint,3) int32.  Launches on torch's
-        current stream and returns a dict of CUDA tensors (see include/ancsh_b200.h: ancsh_pose_out_t)."""
+        current stream and returns a dict of CUDA tensors (see include/ancsh_b200.h: ancsh_pose_out_t).
+        seed: Philox key of this call (default: the solver's), so that successive batches draw different hypotheses."""
         B, N, _ = P.shape
         K = self.K
 
@@ -110,7 +111,9 @@ class PoseSolver:
         pout = _lib.PoseOut()
         for k in _lib.POSE_OUT_FIELDS:
             setattr(pout, k, out[k].data_ptr())
-        rc = _lib.ancsh_pose_solve(ctypes.byref(self.cfg), ctypes.byref(pin), B, N, ws.data_ptr(), lay.total_bytes,
+        cfg = self.cfg if seed is None else _lib.PoseCfg(self.K, self.cfg.niter_single, self.cfg.niter_joint,
+                                                         self.cfg.inlier_th, int(seed))
+        rc = _lib.ancsh_pose_solve(ctypes.byref(cfg), ctypes.byref(pin), B, N, ws.data_ptr(), lay.total_bytes,
                                    ctypes.byref(pout), stage_events.arr if stage_events is not None else None,
                                    torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "ancsh_pose_solve")

@@ -35,6 +35,11 @@ const char *ancsh_version(void);
  * memsets / copies are not counted).  bench.py reports the difference over its timed region as `gpu_launches`. */
 unsigned long long ancsh_launch_count(void);
 
+/* Diagnostic: FP64 peak probe.  Launches `blocks` blocks of 256 threads that each run 8 independent chains of `iters`
+ * DFMAs (= blocks * 256 * 8 * iters * 2 FLOP); time it with events on `stream`.  bench.py uses the result as the roofline
+ * denominator of the f64 pose kernels.  sink: one device double (never written in practice). */
+int ancsh_diag_fp64_fma(int blocks, int iters, double *sink, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Op level -- one entry point per native op on the path.
  * ---------------------------------------------------------------------------------------------- */

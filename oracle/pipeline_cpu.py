@@ -90,6 +90,45 @@ def solve_cloud_parallel(P, nocs, mask, joint_axis, joint_cls, K, th, niter_sing
     return res
 
 
+def _solve_cloud_serial(args):
+    P, nocs, mask, axis, jc, K, th, ns, nj, seed = args
+    rng = np.random.default_rng(seed)
+    cnt = np.bincount(np.argmax(mask, axis=1), minlength=K)
+    if (cnt == 0).any():
+        return 0                                   # the reference's worker would raise in np.random.randint(0)
+    idx_s = [rng.integers(0, cnt[j], size=(ns, 3)) for j in range(K)]
+    idx_0 = [rng.integers(0, cnt[0], size=(nj, 3)) for _ in range(1, K)]
+    idx_1 = [rng.integers(0, cnt[j], size=(nj, 3)) for j in range(1, K)]
+    pose_np.solve_cloud(P, nocs, mask, axis, jc, K, th, idx_s, idx_0, idx_1)
+    return 1
+
+
+def run_clouds_fanout(P, joint_cls, w_ancsh, w_npcs, K, nsample, th, niter_single, niter_joint, seed=0):
+    """BASELINE configs[0] as the reference runs it: `main.py --test` over all clouds (both networks; the native ops use all
+    cores), then ONE `pose_multi_process.py`: the clouds are cut into contiguous slices, one per forked worker
+    (cpu_count - 2 of them, evaluation/pose_multi_process.py:54-67), and every worker solves its clouds serially
+    (parallel_ancsh_pose.py:214-352).  Returns #clouds done."""
+    pnpp.set_threads(os.cpu_count() or 1)
+    B = P.shape[0]
+    jobs = []
+    for b in range(B):
+        pred = pnpp.forward(P[b:b + 1], w_ancsh, K, nsample=nsample)
+        src = pred
+        if w_npcs is not None:
+            src = pnpp.forward(P[b:b + 1], w_npcs, K, nsample=nsample, mixed_pred=False, early_split_nocs=False)
+        jobs.append((P[b], src["nocs_per_point"][0], src["W"][0], pred["joint_axis_per_point"][0], joint_cls[b], K, th,
+                     niter_single, niter_joint, seed * 100003 + b))
+    W = workers()
+    num_per = int(B / W) + 1                                       # pose_multi_process.py:55
+    slices = [jobs[k * num_per:(k + 1) * num_per] for k in range(W) if jobs[k * num_per:(k + 1) * num_per]]
+    pool().map(_run_slice, slices)
+    return B
+
+
+def _run_slice(jobs):
+    return sum(_solve_cloud_serial(j) for j in jobs)
+
+
 def run_clouds(P, joint_cls, w_ancsh, w_npcs, K, nsample, th, niter_single, niter_joint, stages="full", seed=0):
     """Full CPU path for a batch of clouds (sequentially; every stage uses all cores).  Returns #clouds done."""
     rng = np.random.default_rng(seed)
