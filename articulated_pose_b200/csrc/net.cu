@@ -121,13 +121,6 @@ static int sa_launch(const SaArgs &a0, int B, cudaStream_t st)
     return ANCSH_OK;
 }
 
-// TEMPORARY development switch: ANCSH_TC_V1=1 selects the first-generation tensor-core kernels (net_tc.cu)
-static bool tc_v1()
-{
-    static const bool v = getenv("ANCSH_TC_V1") != nullptr;
-    return v;
-}
-
 // A/B switches for profiling (read once): ANCSH_SA_LEAN_OFF = generic chain kernel for layer1 / layer2,
 // ANCSH_BALL_FUSED_OFF = separate ball-query kernel in front of the lean kernel
 static bool sa_lean_off()
@@ -161,7 +154,7 @@ static int sa_tc_from(const ancsh_net_t *net, const SaArgs &s, int B, float radi
         L[l].has_bias_step = net->tc_bias_step;
     }
     int rc;
-    if (!sa_lean_off() && !tc_v1() && idx_rw) {
+    if (!sa_lean_off() && idx_rw) {
         SaLeanArgs2 t{};
         t.xyz = s.xyz; t.points = s.points; t.new_xyz = s.new_xyz; t.out = s.out;
         t.n = s.n; t.m = s.m; t.S = s.S; t.C = s.C; t.radius = radius;
@@ -183,7 +176,7 @@ static int sa_tc_from(const ancsh_net_t *net, const SaArgs &s, int B, float radi
     t.n = s.n; t.m = s.m; t.S = s.S; t.C = s.C;
     t.W0 = s.L[0].W;
     for (int l = 0; l < 3; ++l) t.L[l] = L[l];
-    return tc_v1() ? sa_tc_launch(t, B, st) : sa_tc2_launch(t, B, st);
+    return sa_tc2_launch(t, B, st);
 }
 
 // ================================================================================================
@@ -427,158 +420,6 @@ static int fp_launch(const FpArgs &a0, int B, cudaStream_t st)
     return ANCSH_OK;
 }
 
-// ================================================================================================
-// Tensor-core path of the point-wise stages: interpolation and head activations as light kernels around
-// chain_tc_kernel (net_tc.cu)
-// ================================================================================================
-// three_nn + inverse-distance weights + three_interpolate -> (B,n1,C2) in global memory (pointnet_util.py:217-223);
-// the (idx, weight) tables are pure geometry and are also written out for the second network of the pipeline
-__global__ void __launch_bounds__(NT) fp_interp_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2,
-                                                       const float *__restrict__ points2, int n1, int m2, int C2,
-                                                       float *__restrict__ out, int *__restrict__ idx_out,
-                                                       float *__restrict__ w_out)
-{
-    constexpr int TMI = 64, PARTS = NT / TMI;
-    extern __shared__ __align__(16) float s_known[];   // m2*3
-    __shared__ float s_w[TMI * 3];
-    __shared__ int s_i[TMI * 3];
-    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long row0 = (long)blockIdx.x * TMI;
-    for (int i = tid; i < m2 * 3; i += NT) s_known[i] = __ldg(xyz2 + (size_t)b * m2 * 3 + i);
-    __syncthreads();
-    {
-        const int row = tid / PARTS, part = tid % PARTS;
-        const float *q = xyz1 + ((size_t)b * n1 + row0 + row) * 3;
-        const float x1 = __ldg(q), y1 = __ldg(q + 1), z1 = __ldg(q + 2);
-        const int chunk = (m2 + PARTS - 1) / PARTS;
-        const int k0 = part * chunk, k1 = min(m2, k0 + chunk);
-        Best3 best;
-        best.init();
-        for (int k = k0; k < k1; ++k)
-            best.insert(nn_dist_unfused(s_known[k * 3], s_known[k * 3 + 1], s_known[k * 3 + 2], x1, y1, z1), k);
-#pragma unroll
-        for (int off = 1; off < PARTS; off <<= 1) {
-            Best3 o;
-            o.d1 = __shfl_xor_sync(0xFFFFFFFFu, best.d1, off); o.i1 = __shfl_xor_sync(0xFFFFFFFFu, best.i1, off);
-            o.d2 = __shfl_xor_sync(0xFFFFFFFFu, best.d2, off); o.i2 = __shfl_xor_sync(0xFFFFFFFFu, best.i2, off);
-            o.d3 = __shfl_xor_sync(0xFFFFFFFFu, best.d3, off); o.i3 = __shfl_xor_sync(0xFFFFFFFFu, best.i3, off);
-            if ((part & off) == 0) {
-                best.merge_higher(o);
-            } else {
-                o.merge_higher(best);
-                best = o;
-            }
-        }
-        if (part == 0) {
-            float w1, w2, w3;
-            three_weights(best.d1, best.d2, best.d3, w1, w2, w3);
-            s_w[row * 3 + 0] = w1; s_w[row * 3 + 1] = w2; s_w[row * 3 + 2] = w3;
-            s_i[row * 3 + 0] = best.i1; s_i[row * 3 + 1] = best.i2; s_i[row * 3 + 2] = best.i3;
-            const size_t o = ((size_t)b * n1 + row0 + row) * 3;          // geometry tables for a second network (fp_blend_kernel)
-            w_out[o] = w1; w_out[o + 1] = w2; w_out[o + 2] = w3;
-            idx_out[o] = best.i1; idx_out[o + 1] = best.i2; idx_out[o + 2] = best.i3;
-        }
-    }
-    __syncthreads();
-    for (int r = warp; r < TMI; r += NT / 32) {
-        const float w1 = s_w[r * 3], w2 = s_w[r * 3 + 1], w3 = s_w[r * 3 + 2];
-        const float *p1 = points2 + ((size_t)b * m2 + s_i[r * 3 + 0]) * C2;
-        const float *p2 = points2 + ((size_t)b * m2 + s_i[r * 3 + 1]) * C2;
-        const float *p3 = points2 + ((size_t)b * m2 + s_i[r * 3 + 2]) * C2;
-        float *o = out + ((size_t)b * n1 + row0 + r) * C2;
-        for (int c4 = lane; c4 < C2 / 4; c4 += 32) {
-            const float4 u = ldg4(p1 + c4 * 4), v = ldg4(p2 + c4 * 4), w = ldg4(p3 + c4 * 4);
-            float4 x;
-            x.x = interp3_unfused(u.x, v.x, w.x, w1, w2, w3);
-            x.y = interp3_unfused(u.y, v.y, w.y, w1, w2, w3);
-            x.z = interp3_unfused(u.z, v.z, w.z, w1, w2, w3);
-            x.w = interp3_unfused(u.w, v.w, w.w, w1, w2, w3);
-            *reinterpret_cast<float4 *>(o + c4 * 4) = x;
-        }
-    }
-}
-
-// three_interpolate (tf_interpolate.cpp:107-127) -> (B,n1,C2) rows in global memory.  One warp per row, RB rows per pass
-// so that 3 * RB 16-byte loads are in flight per lane before the first blend.
-__global__ void __launch_bounds__(NT) fp_blend_kernel(const float *__restrict__ points2, const int *__restrict__ idx,
-                                                      const float *__restrict__ wgt, int n1, int m2, int C2,
-                                                      float *__restrict__ out)
-{
-    constexpr int TMI = 64, RB = 4;
-    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long row0 = (long)blockIdx.x * TMI;
-    const float *src = points2 + (size_t)b * m2 * C2;
-    for (int r = warp * RB; r < TMI; r += (NT / 32) * RB) {
-        const size_t g = ((size_t)b * n1 + row0 + r) * 3;
-        int id[RB][3];
-        float w[RB][3];
-#pragma unroll
-        for (int j = 0; j < RB; ++j)
-#pragma unroll
-            for (int t = 0; t < 3; ++t) { id[j][t] = __ldg(idx + g + 3 * j + t); w[j][t] = __ldg(wgt + g + 3 * j + t); }
-        for (int c4 = lane; c4 < C2 / 4; c4 += 32) {
-            float4 u[RB], v[RB], x[RB];
-#pragma unroll
-            for (int j = 0; j < RB; ++j) {
-                u[j] = ldg4(src + (size_t)id[j][0] * C2 + c4 * 4);
-                v[j] = ldg4(src + (size_t)id[j][1] * C2 + c4 * 4);
-                x[j] = ldg4(src + (size_t)id[j][2] * C2 + c4 * 4);
-            }
-#pragma unroll
-            for (int j = 0; j < RB; ++j) {
-                float4 y;
-                y.x = interp3_unfused(u[j].x, v[j].x, x[j].x, w[j][0], w[j][1], w[j][2]);
-                y.y = interp3_unfused(u[j].y, v[j].y, x[j].y, w[j][0], w[j][1], w[j][2]);
-                y.z = interp3_unfused(u[j].z, v[j].z, x[j].z, w[j][0], w[j][1], w[j][2]);
-                y.w = interp3_unfused(u[j].w, v[j].w, x[j].w, w[j][0], w[j][1], w[j][2]);
-                *reinterpret_cast<float4 *>(out + ((size_t)b * n1 + row0 + r + j) * C2 + c4 * 4) = y;
-            }
-        }
-    }
-}
-
-// activations of all heads (lib/architecture.py:122-139, 150-157) from the raw linear outputs, one thread per point
-__global__ void __launch_bounds__(256) heads_act_kernel(const float *__restrict__ raw1, const float *__restrict__ raw2,
-                                                        long rows, int K, int mixed, const ancsh_pred_t o)
-{
-    const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= rows) return;
-    float x[64];
-    const float4 *s1 = reinterpret_cast<const float4 *>(raw1 + (size_t)r * 64);
-#pragma unroll
-    for (int q = 0; q < 16; ++q) { const float4 t = __ldg(s1 + q); x[4 * q] = t.x; x[4 * q + 1] = t.y; x[4 * q + 2] = t.z; x[4 * q + 3] = t.w; }
-    float mx = x[0];
-    for (int k = 1; k < K; ++k) mx = fmaxf(mx, x[k]);
-    float sum = 0.f;
-    for (int k = 0; k < K; ++k) { x[k] = expf(x[k] - mx); sum += x[k]; }
-    // every output is optional (NULL = not requested), like copy_tile_out of the f32 path
-    if (o.W) for (int k = 0; k < K; ++k) o.W[(size_t)r * K + k] = x[k] / sum;
-    for (int k = K; k < 4 * K; ++k) { x[k] = sigmoidf_(x[k]); if (o.nocs_per_point) o.nocs_per_point[(size_t)r * 3 * K + (k - K)] = x[k]; }
-    if (mixed) {
-        for (int k = 4 * K; k < 5 * K; ++k) { x[k] = sigmoidf_(x[k]); if (o.global_scale) o.global_scale[(size_t)r * K + (k - 4 * K)] = x[k]; }
-        for (int k = 5 * K; k < 8 * K; ++k) { x[k] = tanhf(x[k]); if (o.global_translation) o.global_translation[(size_t)r * 3 * K + (k - 5 * K)] = x[k]; }
-        if (o.confi_per_point) o.confi_per_point[r] = sigmoidf_(x[8 * K]);
-        if (o.gocs_per_point)
-            for (int k = 0; k < 3 * K; ++k)
-                o.gocs_per_point[(size_t)r * 3 * K + k] = __fadd_rn(__fmul_rn(x[K + k], x[4 * K + k / 3]), x[5 * K + k]);
-    } else if (o.confi_per_point) {
-        o.confi_per_point[r] = sigmoidf_(x[4 * K]);
-    }
-    const float4 *s2 = reinterpret_cast<const float4 *>(raw2 + (size_t)r * 64);
-    const float4 j0 = __ldg(s2), j1 = __ldg(s2 + 1), j2 = __ldg(s2 + 2);
-    const float y[10] = {j0.x, j0.y, j0.z, j0.w, j1.x, j1.y, j1.z, j1.w, j2.x, j2.y};
-    if (o.joint_axis_per_point) for (int k = 0; k < 3; ++k) o.joint_axis_per_point[(size_t)r * 3 + k] = tanhf(y[k]);
-    if (o.unitvec_per_point) for (int k = 0; k < 3; ++k) o.unitvec_per_point[(size_t)r * 3 + k] = tanhf(y[3 + k]);
-    if (o.heatmap_per_point) o.heatmap_per_point[r] = sigmoidf_(y[6]);
-    if (o.index_per_point) {
-        const float m2 = fmaxf(y[7], fmaxf(y[8], y[9]));
-        const float e0 = expf(y[7] - m2), e1 = expf(y[8] - m2), e2 = expf(y[9] - m2), es = e0 + e1 + e2;
-        o.index_per_point[(size_t)r * 3 + 0] = e0 / es;
-        o.index_per_point[(size_t)r * 3 + 1] = e1 / es;
-        o.index_per_point[(size_t)r * 3 + 2] = e2 / es;
-    }
-}
-
 static TcLayer tc_layer(const ancsh_layer_t &l, int has_bias_step = 0)
 {
     TcLayer t;
@@ -614,8 +455,8 @@ extern "C" int ancsh_net_plan(const ancsh_net_t *net, int B, int N, ancsh_ws_lay
     L->fp1_bias = take(b * net->fp1_global.cout_pad * 4);
     L->l2_points_fp = take(b * m2 * net->fp1[1].cout * 4);
     L->l1_points_fp = take(b * m1 * net->fp2[1].cout * 4);
-    L->interp3 = take(net->use_tensor_cores ? b * N * net->fp2[1].cout * 4 : 0);
-    L->raw_heads = take(net->use_tensor_cores ? b * N * 64 * 4 * 2 : 0);
+    L->interp3 = take(net->use_tensor_cores ? b * m2 * net->sa3[1].cout_pad * 4 : 0);
+    L->raw_heads = take(0);
     L->nn_idx2 = take(net->use_tensor_cores ? b * m1 * 3 * 4 : 0);
     L->nn_w2 = take(net->use_tensor_cores ? b * m1 * 3 * 4 : 0);
     L->nn_idx3 = take(net->use_tensor_cores ? b * N * 3 * 4 : 0);
@@ -704,39 +545,23 @@ static int net_forward_impl(const ancsh_net_t *net, int B, int N, const float *P
         a.L[0] = net->sa3[0]; a.L[1] = net->sa3[1]; a.L[2] = net->sa3[2];
         a.n = m2; a.m = 1; a.S = m2; a.C = net->sa2[2].cout;
         if (net->use_tensor_cores && net->sa3[0].W_tc && net->sa3[2].W_tc) {
-            // group_all: three streaming GEMMs over the B*npoint2 rows; temporaries live in the fa_layer3 scratch
-            float *t1 = (float *)(ws + L.interp3);
-            float *t2 = t1 + (size_t)B * m2 * net->sa3[0].cout_pad;
-            if ((size_t)m2 * (net->sa3[0].cout_pad + net->sa3[1].cout_pad) > (size_t)N * net->fp2[1].cout || m2 % 32 != 0 ||
-                net->sa3[2].cout != net->sa3[2].cout_pad)
-                return ANCSH_ERR_UNSUPPORTED;
-            if (!tc_v1()) {
-                // conv0 (in place) + conv1 -> t2 as one warp-specialised chain: each 128-row CTA converts its operand once
-                // and streams the weights through the TMA ring (the streaming GEMM re-converts the rows for every
-                // 128-column chunk and serialises load / MMA).  conv2 (K = 512: its operand images would need 256 KB of
-                // shared memory) stays a streaming GEMM with the max over the cloud's npoint2 rows in its epilogue.
-                ChainTcArgs c{};
-                c.X1 = l2_points; c.C1 = net->sa2[2].cout; c.X2 = l2_xyz; c.C2 = 3; c.rows_per_cloud = m2;
-                c.S[0].L = tc_layer(net->sa3[0]); c.S[0].dst = TC_DST_INPLACE;
-                c.S[1].L = tc_layer(net->sa3[1]); c.S[1].dst = TC_DST_GLOBAL; c.S[1].out = t2; c.S[1].ldo = net->sa3[1].cout_pad;
-                c.nsteps = 2;
-                if ((rc = chain_tc2_launch(c, (long)B * m2, st))) return rc;
-                GemmTcArgs g{};
-                g.X1 = t2; g.C1 = net->sa3[1].cout_pad; g.X2 = nullptr; g.C2 = 0; g.L = tc_layer(net->sa3[2]);
-                g.out = l3_points; g.ldo = 0; g.pool_S = m2;
-                if ((rc = gemm_tc_launch(g, (long)B * m2, st))) return rc;
-            } else {
+            // group_all over the B*npoint2 rows; conv1's output is the only temporary (workspace slot `interp3`)
+            float *t2 = (float *)(ws + L.interp3);
+            if (m2 % 32 != 0 || net->sa3[2].cout != net->sa3[2].cout_pad) return ANCSH_ERR_UNSUPPORTED;
+            // conv0 (in place) + conv1 -> t2 as one warp-specialised chain: each 128-row CTA converts its operand once
+            // and streams the weights through the TMA ring (the streaming GEMM re-converts the rows for every
+            // 128-column chunk and serialises load / MMA).  conv2 (K = 512: its operand images would need 256 KB of
+            // shared memory) stays a streaming GEMM with the max over the cloud's npoint2 rows in its epilogue.
+            ChainTcArgs c{};
+            c.X1 = l2_points; c.C1 = net->sa2[2].cout; c.X2 = l2_xyz; c.C2 = 3; c.rows_per_cloud = m2;
+            c.S[0].L = tc_layer(net->sa3[0]); c.S[0].dst = TC_DST_INPLACE;
+            c.S[1].L = tc_layer(net->sa3[1]); c.S[1].dst = TC_DST_GLOBAL; c.S[1].out = t2; c.S[1].ldo = net->sa3[1].cout_pad;
+            c.nsteps = 2;
+            if ((rc = chain_tc2_launch(c, (long)B * m2, st))) return rc;
             GemmTcArgs g{};
-            g.X1 = l2_points; g.C1 = net->sa2[2].cout; g.X2 = l2_xyz; g.C2 = 3; g.L = tc_layer(net->sa3[0]);
-            g.out = t1; g.ldo = net->sa3[0].cout_pad; g.pool_S = 0;
-            if ((rc = gemm_tc_launch(g, (long)B * m2, st))) return rc;
-            g.X1 = t1; g.C1 = net->sa3[0].cout_pad; g.X2 = nullptr; g.C2 = 0; g.L = tc_layer(net->sa3[1]);
-            g.out = t2; g.ldo = net->sa3[1].cout_pad;
-            if ((rc = gemm_tc_launch(g, (long)B * m2, st))) return rc;
-            g.X1 = t2; g.C1 = net->sa3[1].cout_pad; g.L = tc_layer(net->sa3[2]);
+            g.X1 = t2; g.C1 = net->sa3[1].cout_pad; g.X2 = nullptr; g.C2 = 0; g.L = tc_layer(net->sa3[2]);
             g.out = l3_points; g.ldo = 0; g.pool_S = m2;
             if ((rc = gemm_tc_launch(g, (long)B * m2, st))) return rc;
-            }
         } else if ((rc = sa_launch<64>(a, B, st))) return rc;
     }
     // fa_layer1
@@ -760,7 +585,7 @@ static int net_forward_impl(const ancsh_net_t *net, int B, int N, const float *P
             c.S[1].L = tc_layer(net->fp1[1]); c.S[1].dst = TC_DST_GLOBAL; c.S[1].out = l2_fp; c.S[1].ldo = net->fp1[1].cout;
             c.nsteps = 2;
             if (net->fp1[1].cout != net->fp1[1].cout_pad) return ANCSH_ERR_INVALID_ARG;
-            if ((rc = (tc_v1() ? chain_tc_launch : chain_tc2_launch)(c, (long)B * m2, st))) return rc;
+            if ((rc = chain_tc2_launch(c, (long)B * m2, st))) return rc;
         } else if ((rc = fp_launch<64, false>(a, B, st))) return rc;
     }
     // fa_layer2
@@ -773,26 +598,22 @@ static int net_forward_impl(const ancsh_net_t *net, int B, int N, const float *P
         a.bias0 = net->fp2[0].b; a.bias0_stride = 0;
         a.out = l1_fp;
         if (net->use_tensor_cores && net->fp2[0].W_tc && net->fp2[1].W_tc) {
-            // interpolate into the (not yet used) fa_layer3 buffer, then [interp(256) | l1_points(128)] -> 256 -> 128
-            float *interp2 = (float *)(ws + L.interp3);
+            // rows [three_interpolate(l2_fp)(256) | l1_points(128)] are built inside the chain kernel's gather from the
+            // stage's (idx, weight) tables (24 bytes per row): no interpolated tensor in HBM
             const int C2 = net->fp1[1].cout;
-            if (m1 % 64 != 0 || (size_t)m1 * C2 > (size_t)N * net->fp2[1].cout) return ANCSH_ERR_UNSUPPORTED;
+            if (m1 % 128 != 0 || C2 % 8 != 0) return ANCSH_ERR_UNSUPPORTED;
             int *nn_i = (int *)(gws + GL.nn_idx2);
             float *nn_w = (float *)(gws + GL.nn_w2);
-            if (!shared)
-                fp_interp_kernel<<<dim3(m1 / 64, B), NT, (size_t)m2 * 3 * sizeof(float), st>>>(l1_xyz, l2_xyz, l2_fp, m1, m2, C2,
-                                                                                            interp2, nn_i, nn_w);
-            else
-                fp_blend_kernel<<<dim3(m1 / 64, B), NT, 0, st>>>(l2_fp, nn_i, nn_w, m1, m2, C2, interp2);
-            ANCSH_CHECK_LAUNCH();
             ChainTcArgs c{};
-            c.X1 = interp2; c.C1 = C2; c.X2 = l1_points; c.C2 = net->sa1[2].cout; c.rows_per_cloud = m1;
+            c.X1 = nullptr; c.C1 = C2; c.X2 = l1_points; c.C2 = net->sa1[2].cout; c.rows_per_cloud = m1;
             c.bias0 = nullptr; c.bias0_stride = 0;
+            c.fp_points2 = l2_fp; c.fp_m2 = m2; c.fp_idx = nn_i; c.fp_w = nn_w;
+            if (!shared && (rc = ancsh_three_nn_tables_impl(B, m1, m2, l1_xyz, l2_xyz, nn_i, nn_w, st))) return rc;
             c.S[0].L = tc_layer(net->fp2[0]); c.S[0].dst = TC_DST_INPLACE; c.S[0].out = nullptr; c.S[0].ldo = 0;
             c.S[1].L = tc_layer(net->fp2[1]); c.S[1].dst = TC_DST_GLOBAL; c.S[1].out = l1_fp; c.S[1].ldo = net->fp2[1].cout;
             c.nsteps = 2;
             if (net->fp2[1].cout != net->fp2[1].cout_pad) return ANCSH_ERR_INVALID_ARG;
-            if ((rc = (tc_v1() ? chain_tc_launch : chain_tc2_launch)(c, (long)B * m1, st))) return rc;
+            if ((rc = chain_tc2_launch(c, (long)B * m1, st))) return rc;
         } else if ((rc = fp_launch<64, false>(a, B, st))) return rc;
     }
     // fa_layer3 + fc1 + heads
@@ -807,22 +628,19 @@ static int net_forward_impl(const ancsh_net_t *net, int B, int N, const float *P
         a.joint_heads = net->joint_heads;
         a.pred = *pred; a.K = net->n_parts; a.mixed = net->mixed_pred;
         if (net->use_tensor_cores && net->fp3[0].W_tc && net->joint_heads.W_tc) {
-            float *interp3 = (float *)(ws + L.interp3);
-            float *raw1 = (float *)(ws + L.raw_heads), *raw2 = raw1 + (size_t)B * N * 64;
+            // fa_layer3 + fc1 + both head stacks as ONE launch: the rows [three_interpolate(l1_fp)(128) | xyz(3)] are built in
+            // the gather, the head activations and gocs run in the epilogues of the two head layers, the predictions are
+            // written once (no interpolated / raw-head tensors in HBM)
             const int C2 = net->fp2[1].cout;
-            if (N % 64 != 0 || C2 % 8 != 0 || net->nocs_heads.cout_pad != 64 || net->joint_heads.cout_pad != 64 ||
-                11 * net->n_parts + 1 > 64)
+            if (N % 128 != 0 || C2 % 8 != 0 || net->nocs_heads.cout_pad != 64 || net->joint_heads.cout_pad != 64)
                 return ANCSH_ERR_UNSUPPORTED;
             int *nn_i = (int *)(gws + GL.nn_idx3);
             float *nn_w = (float *)(gws + GL.nn_w3);
-            if (!shared)
-                fp_interp_kernel<<<dim3(N / 64, B), NT, (size_t)m1 * 3 * sizeof(float), st>>>(P, l1_xyz, l1_fp, N, m1, C2, interp3,
-                                                                                           nn_i, nn_w);
-            else
-                fp_blend_kernel<<<dim3(N / 64, B), NT, 0, st>>>(l1_fp, nn_i, nn_w, N, m1, C2, interp3);
-            ANCSH_CHECK_LAUNCH();
             ChainTcArgs c{};
-            c.X1 = interp3; c.C1 = C2; c.X2 = P; c.C2 = 3; c.rows_per_cloud = N; c.bias0 = nullptr; c.bias0_stride = 0;
+            c.X1 = nullptr; c.C1 = C2; c.X2 = P; c.C2 = 3; c.rows_per_cloud = N; c.bias0 = nullptr; c.bias0_stride = 0;
+            c.fp_points2 = l1_fp; c.fp_m2 = m1; c.fp_idx = nn_i; c.fp_w = nn_w;
+            if (!shared && (rc = ancsh_three_nn_tables_impl(B, N, m1, P, l1_xyz, nn_i, nn_w, st))) return rc;
+            c.pred = *pred; c.n_parts = net->n_parts; c.mixed = net->mixed_pred;
             const ancsh_layer_t *seq[8] = {&net->fp3[0], &net->fp3[1], &net->fp3[2], &net->fc1, &net->nocs_heads,
                                            &net->fc3[0], &net->fc3[1], &net->joint_heads};
             for (int i = 0; i < 8; ++i) {
@@ -830,13 +648,10 @@ static int net_forward_impl(const ancsh_net_t *net, int B, int N, const float *P
                 c.S[i].dst = TC_DST_INPLACE; c.S[i].out = nullptr; c.S[i].ldo = 0;
             }
             c.S[3].out = pred->net; c.S[3].ldo = net->fc1.cout;                       // optional copy of the trunk feature
-            c.S[4].dst = TC_DST_GLOBAL; c.S[4].out = raw1; c.S[4].ldo = 64;           // raw nocs_net outputs (net kept)
-            c.S[7].dst = TC_DST_GLOBAL; c.S[7].out = raw2; c.S[7].ldo = 64;           // raw joint_net outputs
+            c.S[4].dst = TC_DST_GLOBAL; c.S[4].act = TC_ACT_NOCS_HEADS;               // nocs_net heads (operand `net` kept)
+            c.S[7].dst = TC_DST_GLOBAL; c.S[7].act = TC_ACT_JOINT_HEADS;              // joint_net heads
             c.nsteps = 8;
-            if ((rc = (tc_v1() ? chain_tc_launch : chain_tc2_launch)(c, (long)B * N, st))) return rc;
-            const long rows = (long)B * N;
-            heads_act_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(raw1, raw2, rows, net->n_parts, net->mixed_pred, *pred);
-            ANCSH_CHECK_LAUNCH();
+            if ((rc = chain_tc2_launch(c, (long)B * N, st))) return rc;
         } else if ((rc = fp_launch<128, true>(a, B, st))) return rc;
     }
     STAGE_MARK();

@@ -22,6 +22,7 @@
 //     tf_grouping_g.cu:3-36: first nsample in index order, padded with the first hit), indices handed to the gathering
 //     threads through shared memory.
 // Numerics: unchanged from net_tc2.cu (hi*hi and cross terms in separate f32 TMEM accumulators, summed in the epilogue).
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -62,6 +63,11 @@ struct Plan {
     __host__ __device__ static constexpr int max_unit_bytes() { int t = 0; for (int u = 0; u < NU; ++u) t = unit_bytes(u) > t ? unit_bytes(u) : t; return t; }
     static constexpr int SLOT_BYTES = RESIDENT ? max_unit_bytes() : 8192;
     static constexpr int NST = RESIDENT ? NU : 4;
+    // resident plans: every unit has a slot of exactly its size (slot_off); streamed plans: NST stages of SLOT_BYTES
+    __host__ __device__ static constexpr int slot_off(int u) { int t = 0; for (int v = 0; v < u; ++v) t += unit_bytes(v); return t; }
+    static constexpr int RING_BYTES = RESIDENT ? all_bytes() : NST * SLOT_BYTES;
+    // xyz-only stages stage the cloud's coordinates in shared memory for the ball query (n <= XYZ_MAX points)
+    static constexpr int XYZ_MAX = C == 0 ? 1024 : 0;
     static_assert(N2 % 128 == 0 && NU <= MAXU && NST <= MAX_STAGES, "layer widths");
     static_assert(C % 8 == 0 && N0 % 64 == 0 && N1 % 64 == 0, "layer widths");
 };
@@ -83,6 +89,7 @@ struct SaLeanArgs {
     const float *bias_last;   // [N2] bias of the pooled layer
     int n, m;
     float radius;
+    float d2_below;           // smallest f32 t with sqrt_rn(t) >= radius: max(sqrt(d2), 1e-20) < radius  <=>  d2 < t (sqrt_rn is monotonic)
     int tiles_per_cta;
     LUnit U[MAXU];
     long long *trace;         // profiling aid (ANCSH_LEAN_TRACE): per-CTA clock64() stamps of the phase boundaries, or NULL
@@ -233,7 +240,7 @@ __device__ __forceinline__ void issue_unit(MmaCtx &c, bool first_tile)
     if (ACC1) {
         // cross terms first, hi*hi products on top: the small products are summed among themselves before the
         // (truncating) accumulator grows large
-        const uint32_t st = c.ring0 + (uint32_t)U * P::SLOT_BYTES;
+        const uint32_t st = c.ring0 + (uint32_t)P::slot_off(U);
         if (first_tile) tc::mbar_wait(c.bar_full + U, 0u);
         const uint64_t wh0 = tc::smem_desc(st, 2u * NC * 16u, 128u), wl0 = wh0 + (uint64_t)NC;
 #pragma unroll
@@ -257,7 +264,7 @@ __device__ __forceinline__ void issue_unit(MmaCtx &c, bool first_tile)
     for (int s0 = 0; s0 < NK; s0 += KPS) {
         uint32_t st;
         if (P::RESIDENT) {
-            st = c.ring0 + (uint32_t)U * P::SLOT_BYTES;
+            st = c.ring0 + (uint32_t)P::slot_off(U);
             if (first_tile) tc::mbar_wait(c.bar_full + U, 0u);
         } else {
             st = c.ring0 + (uint32_t)c.slot * P::SLOT_BYTES;
@@ -303,13 +310,14 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
     uint8_t *A_lo = A_hi + (size_t)K8 * 2048;
     uint8_t *ones = A_lo + (size_t)K8 * 2048;                                 // [2 kc][128 rows][8] fp16: (1, 1, 0 ...)
     uint8_t *ring = ones + 4096;
-    uint64_t *bar_full = reinterpret_cast<uint64_t *>(ring + (size_t)P::NST * P::SLOT_BYTES);
+    uint64_t *bar_full = reinterpret_cast<uint64_t *>(ring + (size_t)P::RING_BYTES);
     uint64_t *bar_empty = bar_full + MAX_STAGES;
     uint64_t *bar_acc = bar_empty + MAX_STAGES;                               // MMA thread -> workers: accumulators complete
     uint64_t *bar_ready = bar_acc + 1;                                        // workers -> MMA thread: operand written / TMEM drained
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bar_ready + 1);
     int *s_cnt = reinterpret_cast<int *>(s_tmem + 4);                         // [2][8] hits found by each ball-query warp
     int *s_idx = s_cnt + 16;                                                  // [2][8 warps][S] ball-query hit lists (double buffered)
+    float *s_xyz = reinterpret_cast<float *>(s_idx + 16 * S);                 // [XYZ_MAX][3] the cloud's coordinates (xyz-only stages)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) tc::tmem_alloc(s_tmem, TMEM_COLS);
@@ -344,7 +352,7 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
                         if (!P::RESIDENT && round > 0) tc::mbar_wait(bar_empty + slot, (uint32_t)((round - 1) & 1));
                         mbar_expect_tx(bar_full + slot, (uint32_t)P::kps(u) * 4u * piece);
                         for (int j = 0; j < P::kps(u); ++j) {
-                            const uint32_t dst = ring0 + (uint32_t)slot * P::SLOT_BYTES + (uint32_t)j * 4u * piece;
+                            const uint32_t dst = ring0 + (uint32_t)(P::RESIDENT ? P::slot_off(u) : slot * P::SLOT_BYTES) + (uint32_t)j * 4u * piece;
                             const uint8_t *src = U.img + (size_t)(s0 + j) * U.kstep_stride;
                             if (U.piece_stride == piece) {
                                 bulk_g2s(dst, src, 4u * piece, bar_full + slot);
@@ -399,6 +407,8 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_ready);
         };
+        // clouds of up to XYZ_MAX points are scanned from shared memory, larger ones through L1 (generic loads either way)
+        const bool USE_SXYZ = BALL && P::XYZ_MAX > 0 && a.n <= P::XYZ_MAX;
         // query_ball_point of one tile (tf_grouping_g.cu:3-36): first S points in index order with max(sqrt(d2), 1e-20) < radius,
         // row padded with the first hit (all zeros when the ball is empty).  WPC warps per centroid, each scans a contiguous
         // range of the points (128 per trip, 4 per lane) and keeps an ordered hit list; fetch_id() concatenates the lists in
@@ -408,7 +418,7 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
             const int cen = tile * CPT + cl;
             const float *c3 = a.new_xyz + ((size_t)b * a.m + cen) * 3;
             const float x2 = __ldg(c3), y2 = __ldg(c3 + 1), z2 = __ldg(c3 + 2);
-            const float *p1 = a.xyz + (size_t)b * a.n * 3;
+            const float *p1 = USE_SXYZ ? s_xyz : a.xyz + (size_t)b * a.n * 3;
             const int per = ((a.n + WPC - 1) / WPC + 31) & ~31;
             const int k_beg = part * per, k_end = min(a.n, k_beg + per);
             int *row = s_idx + (buf * 8 + warp) * S;
@@ -420,12 +430,11 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
                     const int k = base + u * 32 + lane;
                     in[u] = false;
                     if (k < k_end) {
-                        const float dx = x2 - __ldg(p1 + k * 3 + 0);
-                        const float dy = y2 - __ldg(p1 + k * 3 + 1);
-                        const float dz = z2 - __ldg(p1 + k * 3 + 2);
-                        float d = __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))));
-                        d = fmaxf(d, 1e-20f);
-                        in[u] = d < a.radius;
+                        const float dx = x2 - p1[k * 3 + 0];
+                        const float dy = y2 - p1[k * 3 + 1];
+                        const float dz = z2 - p1[k * 3 + 2];
+                        // tf_grouping_g.cu:21: d = max(sqrtf(dx*dx + dy*dy + dz*dz), 1e-20f) < radius, evaluated on d2 (see d2_below)
+                        in[u] = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))) < a.d2_below;
                     }
                 }
 #pragma unroll
@@ -467,6 +476,12 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
         const int tile0 = blockIdx.x * ntiles;
         int id;
         float rel[3];
+        if (USE_SXYZ) {
+            // the CTA's tiles all belong to cloud b: stage its coordinates once (AoS, stride 3: conflict-free for consecutive k)
+            const float *src = a.xyz + (size_t)b * a.n * 3;
+            for (int i = tid; i < a.n * 3; i += NWORK) s_xyz[i] = __ldg(src + i);
+            gather_sync();
+        }
         if (BALL) { ball_tile(tile0, 0); gather_sync(); }
         id = fetch_id(tile0, 0);
         load_rel(tile0, id, rel);
@@ -572,8 +587,8 @@ template <int C, int N0, int N1, int N2, int S, bool BALL, bool ACC1>
 int launch(const SaLeanArgs &a, dim3 grid, cudaStream_t st)
 {
     using P = Plan<C, N0, N1, N2>;
-    const size_t smem = (size_t)2 * P::K8 * 2048 + 4096 + (size_t)P::NST * P::SLOT_BYTES + (2 * MAX_STAGES + 2) * sizeof(uint64_t) + 16 +
-                        16 * sizeof(int) + 16 * S * sizeof(int);
+    const size_t smem = (size_t)2 * P::K8 * 2048 + 4096 + (size_t)P::RING_BYTES + (2 * MAX_STAGES + 2) * sizeof(uint64_t) + 16 +
+                        16 * sizeof(int) + 16 * S * sizeof(int) + (size_t)P::XYZ_MAX * 3 * sizeof(float);
     auto k = sa_lean_kernel<C, N0, N1, N2, S, BALL, ACC1>;
     ANCSH_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ANCSH_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -608,6 +623,14 @@ int sa_lean_launch(const SaLeanArgs2 &s, int B, cudaStream_t st)
     SaLeanArgs a{};
     a.xyz = s.xyz; a.points = s.points; a.new_xyz = s.new_xyz; a.idx_in = s.idx_in; a.idx_out = s.idx_out; a.cnt_out = s.cnt_out;
     a.out = s.out; a.bias_last = s.L[2].bias; a.n = s.n; a.m = s.m; a.radius = s.radius;
+    {
+        // threshold on the squared distance that reproduces the reference's test on the rounded square root bit for bit
+        if (!(s.radius > 1e-20f) || !std::isfinite(s.radius)) return ANCSH_ERR_UNSUPPORTED;
+        float t = s.radius * s.radius;
+        while (t > 0.f && sqrtf(t) >= s.radius) t = nextafterf(t, 0.f);
+        while (sqrtf(t) < s.radius) t = nextafterf(t, INFINITY);
+        a.d2_below = t;
+    }
     const int tiles = (int)(rows / TM);
     // resident weights (layer1): long-lived CTAs amortise the one-time weight load; streamed weights: 4 tiles per CTA
     int tpc = sa1 ? 16 : 4;

@@ -1,15 +1,8 @@
-// net_tc.cu -- the network's dense layers on the Blackwell tensor cores (tcgen05 + TMEM).
-//
-//   sa_tc_kernel     set abstraction (layer1/layer2): ball-query indices -> gather(features, xyz - centroid) -> 3 x
-//                    (1x1 conv + folded BN + ReLU) -> max over nsample, the grouped tensor never leaving the SM
-//   chain_tc_kernel  point-wise stages (fa_layer1/2/3, fc1, all heads): rows from global memory, a chain of layers
-//                    whose operand stays in shared memory, rows written out where needed
-//   gemm_tc_kernel   streaming GEMM for layer3 (group_all: K up to 512, N up to 1024)
-//
-// Common scheme: one CTA = 128 threads = 128 rows (thread t owns row t for the gather, TMEM lane t in the epilogue
-// and the write-back of the next layer's operand).  Activations live in shared memory as fp16 hi/lo operand images
-// (tc_common.cuh) and are overwritten in place by each layer's epilogue; weights are pre-split / pre-tiled on the host
-// and streamed from L2 in 32-wide k slices with cp.async.  Outputs are produced in chunks of <= 128 columns.
+// net_tc.cu -- streaming tcgen05 GEMM for the one layer whose operand does not fit the operand-resident chains
+// (net_tc2.cu / net_lean.cu): layer3 conv_2 (group_all, K = 512, N = 1024) with the max over the cloud's rows in its
+// epilogue.  One CTA = 128 threads = 128 rows (thread t owns row t for the loads and TMEM lane t in the epilogue); the
+// operand is converted slice by slice (32 k) into fp16 hi/lo images, the pre-tiled weights are streamed from L2 with
+// cp.async, outputs are produced in chunks of <= 128 columns.
 //
 // Numerics.  x = hi + lo with fp16 pieces (22 bits).  The tensor core adds into its f32 accumulator with TRUNCATION, so
 // the error grows linearly with the number of MMAs chained into one accumulator (measured).  Therefore
@@ -17,8 +10,6 @@
 //     split over up to 3 A accumulators when TMEM allows;
 //   * the small cross terms hi*lo + lo*hi go to a separate accumulator B (their truncation error is 2^-11 smaller);
 //   * the epilogue adds A.. + B in round-to-nearest f32.
-// Two CTAs per SM (<= 113 KB shared memory, <= 256 TMEM columns each) overlap one CTA's epilogue / weight fetch with
-// the other's MMAs wherever the operand fits.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "net_tc.cuh"
@@ -26,7 +17,6 @@
 namespace {
 
 constexpr int TM = 128;      // rows per CTA == threads per CTA
-constexpr int KSLICE = 64;   // k elements per weight slice (4 MMA k-steps)
 constexpr int NCH = 128;     // default output columns per chunk = TMEM columns per accumulator (layer1 uses 64)
 
 struct Engine {
@@ -79,29 +69,6 @@ __device__ __forceinline__ void issue_slice(uint32_t tmemA, uint32_t tmemB, int 
     }
 }
 
-// all MMAs of one layer for one 128-column chunk, operand RESIDENT in shared memory (images at a_hi0 / a_lo0)
-__device__ __forceinline__ void mma_chunk_resident(Engine &e, const TcLayer &L, int n0, int NC, uint32_t tbase, int G,
-                                                   uint32_t a_hi0, uint32_t a_lo0)
-{
-    const int nk16 = L.K / 16;
-    uint32_t startedA = 0, startedB = 0;
-    for (int k16 = 0; k16 < nk16; k16 += KSLICE / 16) {
-        const int steps = min(KSLICE / 16, nk16 - k16);
-        stage_weights(e, L.Wimg, L.N, n0, NC, k16 * 2, steps * 2);
-        cp_async_wait<0>();
-        tc::fence_proxy_async();
-        __syncthreads();
-        if (e.tid == 0) {
-            tc::fence_after_sync();
-            issue_slice(tbase, tbase + (uint32_t)(G * e.nch), G, nk16, k16, steps, a_hi0 + (uint32_t)(2 * k16) * 2048u,
-                        a_lo0 + (uint32_t)(2 * k16) * 2048u, e.w0, NC, startedA, startedB, e.nch);
-            tc::mma_commit(e.bar);
-        }
-        tc::mbar_wait(e.bar, e.phase);       // slice buffer free again / accumulators complete
-        e.phase ^= 1;
-    }
-}
-
 // 32 accumulator columns of this thread's row: sum of the A accumulators and B, in round-to-nearest f32
 __device__ __forceinline__ void load_acc(uint32_t trow, int G, int c0, float (&v)[32], int nch)
 {
@@ -120,19 +87,6 @@ __device__ __forceinline__ void load_acc(uint32_t trow, int G, int c0, float (&v
         tc::tmem_ld32(trow + (uint32_t)(g * nch) + c0, u);
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] += u[i];
-    }
-}
-
-__device__ __forceinline__ void store_operand(uint8_t *A_hi, uint8_t *A_lo, int tid, int col0, const float (&v)[32])
-{
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        float w[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) w[i] = v[q * 8 + i];
-        const int kc = (col0 >> 3) + q;
-        tc::store_split8(w, reinterpret_cast<uint4 *>(A_hi + (size_t)kc * 2048 + tid * 16),
-                         reinterpret_cast<uint4 *>(A_lo + (size_t)kc * 2048 + tid * 16));
     }
 }
 
@@ -163,161 +117,6 @@ __device__ __forceinline__ Engine engine_setup(uint8_t *Wst, uint64_t *bar, uint
     return e;
 }
 
-// ============================================================================================================
-__global__ void __launch_bounds__(TM) sa_tc_kernel(const SaTcArgs a)
-{
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t *A_hi = smem;
-    uint8_t *A_lo = A_hi + (size_t)a.kmax8 * 2048;
-    uint8_t *Wst = A_lo + (size_t)a.kmax8 * 2048;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(Wst + (size_t)(KSLICE / 8) * 2 * a.nch * 16);
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bar + 1);
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tile = blockIdx.x, b = blockIdx.y;
-    const long row0 = (long)tile * TM;
-    Engine e = engine_setup(Wst, bar, s_tmem, a.tmem_cols, a.nch);
-
-    // ---- gather row `tid` of the tile: channel order [features(C), xyz(3), zero pad] (pointnet_util.py:52-57) ----
-    {
-        const long R = row0 + tid;
-        const int g = (int)(R / a.S);
-        const int id = a.idx ? __ldg(a.idx + (size_t)b * a.m * a.S + R) : (int)R;
-        const float *prow = a.points ? a.points + ((size_t)b * a.n + id) * a.C : nullptr;
-        float rel[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float v = __ldg(a.xyz + ((size_t)b * a.n + id) * 3 + c);
-            if (a.new_xyz) v = __fsub_rn(v, __ldg(a.new_xyz + ((size_t)b * a.m + g) * 3 + c));
-            rel[c] = v;
-        }
-        const int K0 = a.L[0].K;
-        for (int kc = 0; kc < K0 / 8; ++kc) {
-            float v[8];
-            if (kc * 8 + 8 <= a.C) {
-                const float4 p0 = ldg4(prow + kc * 8), p1 = ldg4(prow + kc * 8 + 4);
-                v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int c = kc * 8 + i;
-                    v[i] = c < a.C ? __ldg(prow + c) : (c < a.C + 3 ? rel[c - a.C] : 0.f);
-                }
-            }
-            tc::store_split8(v, reinterpret_cast<uint4 *>(A_hi + (size_t)kc * 2048 + tid * 16),
-                             reinterpret_cast<uint4 *>(A_lo + (size_t)kc * 2048 + tid * 16));
-        }
-    }
-    tc::fence_proxy_async();
-    const uint32_t a_hi0 = tc::smem_u32(A_hi), a_lo0 = tc::smem_u32(A_lo);
-    const uint32_t trow = e.tmem + ((uint32_t)(warp * 32) << 16);
-
-    for (int l = 0; l < 3; ++l) {
-        const TcLayer &L = a.L[l];
-        for (int n0 = 0; n0 < L.N; n0 += a.nch) {               // in-place layers have N <= nch: a single chunk
-            const int NC = min(a.nch, L.N - n0);
-            mma_chunk_resident(e, L, n0, NC, e.tmem, 1, a_hi0, a_lo0);
-            tc::fence_after_sync();
-            for (int c0 = 0; c0 < NC; c0 += 32) {
-                float v[32];
-                load_acc(trow, 1, c0, v, a.nch);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float x = v[i] + __ldg(L.bias + n0 + c0 + i);
-                    v[i] = L.relu ? fmaxf(x, 0.f) : x;
-                }
-                if (l < 2) {
-                    store_operand(A_hi, A_lo, tid, n0 + c0, v);      // next layer's operand, in place
-                } else {
-                    const long g = (row0 + warp * 32) / a.S;
-                    pool_store(a.out + ((size_t)b * a.m + g) * L.N + n0 + c0, a.S, lane, v);
-                }
-            }
-            tc::fence_proxy_async();
-            tc::fence_before_sync();
-            __syncthreads();
-        }
-    }
-    if (warp == 0) tc::tmem_dealloc(e.tmem, a.tmem_cols);
-}
-
-// ============================================================================================================
-__global__ void __launch_bounds__(TM) chain_tc_kernel(const ChainTcArgs a)
-{
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t *A_hi = smem;
-    uint8_t *A_lo = A_hi + (size_t)a.kmax8 * 2048;
-    uint8_t *Wst = A_lo + (size_t)a.kmax8 * 2048;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(Wst + (size_t)(KSLICE / 8) * 2 * NCH * 16);
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bar + 1);
-
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const long R = (long)blockIdx.x * TM + tid;
-    Engine e = engine_setup(Wst, bar, s_tmem, a.tmem_cols, NCH);
-
-    {
-        const float *r1 = a.X1 + (size_t)R * a.C1;
-        const float *r2 = a.X2 ? a.X2 + (size_t)R * a.C2 : nullptr;
-        const int K0 = a.S[0].L.K;
-        for (int kc = 0; kc < K0 / 8; ++kc) {
-            float v[8];
-            if (kc * 8 + 8 <= a.C1) {
-                const float4 p0 = ldg4(r1 + kc * 8), p1 = ldg4(r1 + kc * 8 + 4);
-                v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
-            } else if (r2 && (a.C2 & 7) == 0 && kc * 8 >= a.C1 && kc * 8 + 8 <= a.C1 + a.C2) {
-                const float4 p0 = ldg4(r2 + (kc * 8 - a.C1)), p1 = ldg4(r2 + (kc * 8 - a.C1) + 4);
-                v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int c = kc * 8 + i;
-                    v[i] = c < a.C1 ? __ldg(r1 + c) : (r2 && c < a.C1 + a.C2 ? __ldg(r2 + (c - a.C1)) : 0.f);
-                }
-            }
-            tc::store_split8(v, reinterpret_cast<uint4 *>(A_hi + (size_t)kc * 2048 + tid * 16),
-                             reinterpret_cast<uint4 *>(A_lo + (size_t)kc * 2048 + tid * 16));
-        }
-    }
-    tc::fence_proxy_async();
-    const uint32_t a_hi0 = tc::smem_u32(A_hi), a_lo0 = tc::smem_u32(A_lo);
-    const uint32_t trow = e.tmem + ((uint32_t)(warp * 32) << 16);
-
-    for (int st = 0; st < a.nsteps; ++st) {
-        const ChainStep &S = a.S[st];
-        const TcLayer &L = S.L;
-        const int nch = (L.N + NCH - 1) / NCH;
-        // accumulators per chunk: G for hi*hi (k range split) + 1 for the cross terms; every chunk of the layer gets
-        // its own set, so the in-place epilogue only starts after ALL MMAs of the layer have read the operand
-        const int G = tc_num_acc(L.K, (int)a.tmem_cols / (NCH * nch) - 1);
-        for (int j = 0; j < nch; ++j)
-            mma_chunk_resident(e, L, j * NCH, min(NCH, L.N - j * NCH), e.tmem + (uint32_t)(j * (G + 1) * NCH), G, a_hi0, a_lo0);
-        tc::fence_after_sync();
-        const float *bias = (st == 0 && a.bias0) ? a.bias0 + (size_t)(R / a.rows_per_cloud) * a.bias0_stride : L.bias;
-        for (int j = 0; j < nch; ++j) {
-            const int NC = min(NCH, L.N - j * NCH);
-            for (int c0 = 0; c0 < NC; c0 += 32) {
-                float v[32];
-                load_acc(trow + (uint32_t)(j * (G + 1) * NCH), G, c0, v, NCH);
-                const int col = j * NCH + c0;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float x = v[i] + __ldg(bias + col + i);
-                    v[i] = L.relu ? fmaxf(x, 0.f) : x;
-                }
-                if (S.out) {
-                    float4 *o = reinterpret_cast<float4 *>(S.out + (size_t)R * S.ldo + col);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                }
-                if (S.dst == TC_DST_INPLACE) store_operand(A_hi, A_lo, tid, col, v);
-            }
-        }
-        tc::fence_proxy_async();
-        tc::fence_before_sync();
-        __syncthreads();
-    }
-    if (warp == 0) tc::tmem_dealloc(e.tmem, a.tmem_cols);
-}
 
 // ============================================================================================================
 // Streaming GEMM: neither operand is resident.  Per GK-wide k slice every thread converts its row's GK f32 inputs to
@@ -419,66 +218,8 @@ __global__ void __launch_bounds__(TM) gemm_tc_kernel(const GemmTcArgs a)
 }
 
 inline uint32_t pow2_cols(int cols) { return cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512; }
-constexpr size_t kStageBytes = (size_t)(KSLICE / 8) * 2 * NCH * 16 + 16;
 
 }  // namespace
-
-int sa_tc_launch(const SaTcArgs &a0, int B, cudaStream_t st)
-{
-    SaTcArgs a = a0;
-    const long rows = (long)a.m * a.S;
-    if (rows % TM != 0 || a.S % 32 != 0 || a.C % 8 != 0) return ANCSH_ERR_UNSUPPORTED;
-    int kmax = 0, nin = 0;
-    for (int l = 0; l < 3; ++l) {
-        if (!a.L[l].Wimg || a.L[l].K % 16 != 0 || a.L[l].N % 32 != 0) return ANCSH_ERR_INVALID_ARG;
-        if (l > 0 && a.L[l].K != a.L[l - 1].N) return ANCSH_ERR_INVALID_ARG;
-        if (l < 2 && a.L[l].N > nin) nin = a.L[l].N;
-        kmax = a.L[l].K > kmax ? a.L[l].K : kmax;
-    }
-    if (nin > NCH) return ANCSH_ERR_UNSUPPORTED;                            // in-place layers: a single column chunk
-    if (a.L[0].K < a.C + 3 || !a.L[2].relu) return ANCSH_ERR_INVALID_ARG;
-    a.kmax8 = kmax / 8;
-    a.nch = nin <= 64 ? 64 : NCH;                                           // layer1 (64-wide): 128 TMEM columns -> 4 CTAs per SM
-    a.tmem_cols = 2 * a.nch;                                                // accumulators A and B
-    const size_t smem = (size_t)2 * a.kmax8 * 2048 + (size_t)(KSLICE / 8) * 2 * a.nch * 16 + 16;
-    if (smem > 113 * 1024) return ANCSH_ERR_UNSUPPORTED;
-    ANCSH_CUDA(cudaFuncSetAttribute(sa_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ANCSH_CUDA(cudaFuncSetAttribute(sa_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    if (a.S != 32) ANCSH_CUDA(cudaMemsetAsync(a.out, 0, (size_t)B * a.m * a.L[2].N * sizeof(float), st));
-    dim3 grid((unsigned)(rows / TM), B);
-    sa_tc_kernel<<<grid, TM, smem, st>>>(a);
-    ANCSH_CHECK_LAUNCH();
-    return ANCSH_OK;
-}
-
-int chain_tc_launch(const ChainTcArgs &a0, long rows_total, cudaStream_t st)
-{
-    ChainTcArgs a = a0;
-    if (rows_total % TM != 0 || a.C1 % 8 != 0 || a.nsteps < 1 || a.nsteps > 8) return ANCSH_ERR_UNSUPPORTED;
-    int kmax = 0, nchmax = 1;
-    for (int i = 0; i < a.nsteps; ++i) {
-        const TcLayer &L = a.S[i].L;
-        if (!L.Wimg || L.K % 16 != 0 || L.N % 32 != 0 || L.N > 2 * NCH) return ANCSH_ERR_INVALID_ARG;
-        if (a.S[i].dst == TC_DST_GLOBAL && !a.S[i].out) return ANCSH_ERR_INVALID_ARG;
-        if (a.S[i].out && (a.S[i].ldo < L.N || a.S[i].ldo % 4 != 0)) return ANCSH_ERR_INVALID_ARG;
-        kmax = L.K > kmax ? L.K : kmax;
-        if (a.S[i].dst == TC_DST_INPLACE && L.N > kmax) kmax = L.N;
-        const int nch = (L.N + NCH - 1) / NCH;
-        nchmax = nch > nchmax ? nch : nchmax;
-    }
-    if (a.S[0].L.K < a.C1 + (a.X2 ? a.C2 : 0)) return ANCSH_ERR_INVALID_ARG;
-    a.kmax8 = kmax / 8;
-    const size_t smem = (size_t)2 * a.kmax8 * 2048 + kStageBytes;
-    if (smem > 227 * 1024) return ANCSH_ERR_UNSUPPORTED;
-    // two CTAs per SM (256 columns each) while shared memory allows it and 2 accumulators per chunk fit, else all 512
-    a.tmem_cols = (smem <= 113 * 1024 && nchmax * 2 * NCH <= 256) ? 256 : 512;
-    if (nchmax * 2 * NCH > (int)a.tmem_cols) return ANCSH_ERR_UNSUPPORTED;
-    ANCSH_CUDA(cudaFuncSetAttribute(chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ANCSH_CUDA(cudaFuncSetAttribute(chain_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    chain_tc_kernel<<<(unsigned)(rows_total / TM), TM, smem, st>>>(a);
-    ANCSH_CHECK_LAUNCH();
-    return ANCSH_OK;
-}
 
 int gemm_tc_launch(const GemmTcArgs &a0, long rows_total, cudaStream_t st)
 {

@@ -23,8 +23,7 @@ struct SaTcArgs {
     uint32_t tmem_cols;
 };
 
-int sa_tc_launch(const SaTcArgs &a, int B, cudaStream_t st);
-int sa_tc2_launch(const SaTcArgs &a, int B, cudaStream_t st);    // warp-specialised version (net_tc2.cu)
+int sa_tc2_launch(const SaTcArgs &a, int B, cudaStream_t st);    // generic warp-specialised chain (net_tc2.cu)
 
 // ---- layer-specialised set abstraction with fused ball query (net_lean.cu) --------------------------------------
 struct SaLeanArgs2 {
@@ -66,18 +65,13 @@ struct ChainTcArgs {
     int nsteps;
     int pool_S;               // > 0 (warp-specialised kernel only): the last step is max-pooled over groups of pool_S consecutive
                               // rows (multiple of 32, ReLU output) into S[last].out = [rows_total / pool_S][N]
-    // Fused feature propagation (pointnet_util.py:206-236; warp-specialised kernel only): with fp_points2 != NULL the X1 part
-    // of a row is three_interpolate(fp_points2, idx, weight) evaluated in the gather (X1 itself is ignored), where
-    // (idx, weight) = three_nn(fp_xyz1, fp_xyz2) + the inverse-distance weights are computed by the tile (or read from the
-    // tables of an earlier forward over the same clouds: shared geometry).
+    // Fused feature propagation (pointnet_util.py:206-236): with fp_points2 != NULL the X1 part of a row is
+    // three_interpolate(fp_points2, fp_idx, fp_w) evaluated in the gather (X1 itself is ignored); (fp_idx, fp_w) are the
+    // stage's three_nn indices and inverse-distance weights (ancsh_three_nn_tables_impl).
     const float *fp_points2;  // [clouds][fp_m2][C1]
-    const float *fp_xyz1;     // [clouds][rows_per_cloud][3] query points
-    const float *fp_xyz2;     // [clouds][fp_m2][3] known points
     int fp_m2;
-    const int *fp_idx_in;     // [rows_total][3] or NULL
-    const float *fp_w_in;     // [rows_total][3] or NULL
-    int *fp_idx_out;          // optional copies of the tables computed here
-    float *fp_w_out;
+    const int *fp_idx;        // [rows_total][3]
+    const float *fp_w;        // [rows_total][3]
     ancsh_pred_t pred;        // destination of the TC_ACT_* steps
     int n_parts, mixed;
     int kmax8;                // filled by the launcher
@@ -91,8 +85,7 @@ __host__ __device__ inline int tc_num_acc(int K, int max_acc)
     return g < max_acc ? (g < 1 ? 1 : g) : max_acc;
 }
 
-int chain_tc_launch(const ChainTcArgs &a, long rows_total, cudaStream_t st);
-int chain_tc2_launch(const ChainTcArgs &a, long rows_total, cudaStream_t st);   // warp-specialised version (net_tc2.cu)
+int chain_tc2_launch(const ChainTcArgs &a, long rows_total, cudaStream_t st);   // net_tc2.cu
 
 // ---- streaming GEMM (layers whose K or N do not fit the operand-resident chain: layer3 / group_all) -------------
 struct GemmTcArgs {

@@ -64,11 +64,9 @@ struct Chain2Args {
     const float *W0, *b0;  // xyz-only set abstraction: f32 weights [>=3][N0] / bias of the first conv, evaluated in the gather
     int N0, relu0;         // (N0 == 0: disabled)
     // fused feature propagation (FP kernels): X1 part of a row = blend of three rows of fp_points2
-    const float *fp_points2, *fp_xyz1, *fp_xyz2;
-    const int *fp_idx_in;
-    const float *fp_w_in;
-    int *fp_idx_out;
-    float *fp_w_out;
+    const float *fp_points2;
+    const int *fp_idx;     // [rows][3] three_nn indices into the cloud's fp_m2 known points
+    const float *fp_w;     // [rows][3] interpolation weights
     int fp_m2;
     ancsh_pred_t pred;     // outputs of the head units
     int n_parts, mixed;
@@ -197,41 +195,95 @@ __device__ __forceinline__ void pool_store2(float *orow, int S, int lane, const 
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-// Head activations of one row (lib/architecture.py:122-139, 150-157) on the 32 leading columns of a packed head layer:
-//   nocs_net  [W(K) | nocs(3K) | scale(K) | trans(3K) | confi(1)]  (mixed)  /  [W(K) | nocs(3K) | confi(1)]
+// Head activations of one row (lib/architecture.py:122-139, 150-157) on a 32-column group of a packed head layer:
+//   nocs_net  [W(K) | nocs(3K) | scale(K) | trans(3K) | confi(1)]  (MIXED)  /  [W(K) | nocs(3K) | confi(1)]
 //   joint_net [joint_axis(3) | unitvec(3) | heatmap(1) | index(3)]
-// c0 = first column held in v (0 or 32); every output pointer may be NULL (not requested).
-__device__ __forceinline__ void head_activations(int act, int c0, float (&x)[32], long r, int K, int mixed, const ancsh_pred_t &o)
+// c0 = first column held in x (0 or 32); every output pointer may be NULL (not requested).  K and MIXED are compile-time
+// so that every index into x is static (a dynamically indexed x would push the accumulator rows of ALL epilogues of the
+// kernel into local memory: measured 0.61 -> 0.87 ms for fa_layer3 + heads).
+template <int K, bool MIXED>
+__device__ __forceinline__ void nocs_head_act(int c0, const float (&x)[32], long r, const ancsh_pred_t &o)
 {
-    if (act == TC_ACT_NOCS_HEADS) {
-        const int confi_col = mixed ? 8 * K : 4 * K;
-        if (c0 == 0) {
-            float mx = x[0];
-            for (int k = 1; k < K; ++k) mx = fmaxf(mx, x[k]);
-            float sum = 0.f;
-            for (int k = 0; k < K; ++k) { x[k] = expf(x[k] - mx); sum += x[k]; }
-            if (o.W) for (int k = 0; k < K; ++k) o.W[(size_t)r * K + k] = x[k] / sum;
-            for (int k = K; k < 4 * K; ++k) { x[k] = sigmoidf_(x[k]); if (o.nocs_per_point) o.nocs_per_point[(size_t)r * 3 * K + (k - K)] = x[k]; }
-            if (mixed) {
-                for (int k = 4 * K; k < 5 * K; ++k) { x[k] = sigmoidf_(x[k]); if (o.global_scale) o.global_scale[(size_t)r * K + (k - 4 * K)] = x[k]; }
-                for (int k = 5 * K; k < 8 * K; ++k) { x[k] = tanhf(x[k]); if (o.global_translation) o.global_translation[(size_t)r * 3 * K + (k - 5 * K)] = x[k]; }
-                if (o.gocs_per_point)
-                    for (int k = 0; k < 3 * K; ++k)
-                        o.gocs_per_point[(size_t)r * 3 * K + k] = __fadd_rn(__fmul_rn(x[K + k], x[4 * K + k / 3]), x[5 * K + k]);
+    constexpr int CONFI = MIXED ? 8 * K : 4 * K;
+    static_assert((MIXED ? 8 * K : 4 * K) <= 32, "W | nocs | scale | trans of a row must share one 32-column group");
+    if (c0 == 0) {
+        float e[K], mx = x[0], sum = 0.f;
+#pragma unroll
+        for (int k = 1; k < K; ++k) mx = fmaxf(mx, x[k]);
+#pragma unroll
+        for (int k = 0; k < K; ++k) { e[k] = expf(x[k] - mx); sum += e[k]; }
+        if (o.W) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) o.W[(size_t)r * K + k] = e[k] / sum;
+        }
+        float nocs[3 * K];
+#pragma unroll
+        for (int k = 0; k < 3 * K; ++k) nocs[k] = sigmoidf_(x[K + k]);
+        if (o.nocs_per_point) {
+#pragma unroll
+            for (int k = 0; k < 3 * K; ++k) o.nocs_per_point[(size_t)r * 3 * K + k] = nocs[k];
+        }
+        if (MIXED) {
+            float sc[K], tr[3 * K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) sc[k] = sigmoidf_(x[4 * K + k]);
+#pragma unroll
+            for (int k = 0; k < 3 * K; ++k) tr[k] = tanhf(x[5 * K + k]);
+            if (o.global_scale) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) o.global_scale[(size_t)r * K + k] = sc[k];
+            }
+            if (o.global_translation) {
+#pragma unroll
+                for (int k = 0; k < 3 * K; ++k) o.global_translation[(size_t)r * 3 * K + k] = tr[k];
+            }
+            if (o.gocs_per_point) {
+#pragma unroll
+                for (int k = 0; k < 3 * K; ++k) o.gocs_per_point[(size_t)r * 3 * K + k] = __fadd_rn(__fmul_rn(nocs[k], sc[k / 3]), tr[k]);
             }
         }
-        if (confi_col >= c0 && confi_col < c0 + 32 && o.confi_per_point) o.confi_per_point[r] = sigmoidf_(x[confi_col - c0]);
-    } else if (c0 == 0) {
-        if (o.joint_axis_per_point) for (int k = 0; k < 3; ++k) o.joint_axis_per_point[(size_t)r * 3 + k] = tanhf(x[k]);
-        if (o.unitvec_per_point) for (int k = 0; k < 3; ++k) o.unitvec_per_point[(size_t)r * 3 + k] = tanhf(x[3 + k]);
-        if (o.heatmap_per_point) o.heatmap_per_point[r] = sigmoidf_(x[6]);
-        if (o.index_per_point) {
-            const float m2 = fmaxf(x[7], fmaxf(x[8], x[9]));
-            const float e0 = expf(x[7] - m2), e1 = expf(x[8] - m2), e2 = expf(x[9] - m2), es = e0 + e1 + e2;
-            o.index_per_point[(size_t)r * 3 + 0] = e0 / es;
-            o.index_per_point[(size_t)r * 3 + 1] = e1 / es;
-            o.index_per_point[(size_t)r * 3 + 2] = e2 / es;
-        }
+    }
+    if (CONFI >= 32 ? c0 == 32 : c0 == 0) {
+        if (o.confi_per_point) o.confi_per_point[r] = sigmoidf_(x[CONFI & 31]);
+    }
+}
+
+__device__ __forceinline__ void joint_head_act(int c0, const float (&x)[32], long r, const ancsh_pred_t &o)
+{
+    if (c0 != 0) return;
+    if (o.joint_axis_per_point) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) o.joint_axis_per_point[(size_t)r * 3 + k] = tanhf(x[k]);
+    }
+    if (o.unitvec_per_point) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) o.unitvec_per_point[(size_t)r * 3 + k] = tanhf(x[3 + k]);
+    }
+    if (o.heatmap_per_point) o.heatmap_per_point[r] = sigmoidf_(x[6]);
+    if (o.index_per_point) {
+        const float m2 = fmaxf(x[7], fmaxf(x[8], x[9]));
+        const float e0 = expf(x[7] - m2), e1 = expf(x[8] - m2), e2 = expf(x[9] - m2), es = e0 + e1 + e2;
+        o.index_per_point[(size_t)r * 3 + 0] = e0 / es;
+        o.index_per_point[(size_t)r * 3 + 1] = e1 / es;
+        o.index_per_point[(size_t)r * 3 + 2] = e2 / es;
+    }
+}
+
+// Out of line on purpose: the transcendental-heavy head code must not share the register budget (96) of the epilogue loop.
+__device__ __noinline__ void head_activations(int act, int c0, const float (&x)[32], long r, int K, int mixed, const ancsh_pred_t &o)
+{
+    if (act == TC_ACT_JOINT_HEADS) { joint_head_act(c0, x, r, o); return; }
+    if (mixed) {
+        if (K == 2) nocs_head_act<2, true>(c0, x, r, o);
+        else if (K == 3) nocs_head_act<3, true>(c0, x, r, o);
+        else nocs_head_act<4, true>(c0, x, r, o);
+    } else {
+        if (K == 2) nocs_head_act<2, false>(c0, x, r, o);
+        else if (K == 3) nocs_head_act<3, false>(c0, x, r, o);
+        else if (K == 4) nocs_head_act<4, false>(c0, x, r, o);
+        else if (K == 5) nocs_head_act<5, false>(c0, x, r, o);
+        else if (K == 6) nocs_head_act<6, false>(c0, x, r, o);
+        else nocs_head_act<7, false>(c0, x, r, o);
     }
 }
 
@@ -393,42 +445,14 @@ __global__ void __launch_bounds__(NTHR, MINB) chain2_kernel(const __grid_constan
                 split8(v, reinterpret_cast<uint4 *>(A_hi + (size_t)kc * 2048 + r * 16), reinterpret_cast<uint4 *>(A_lo + (size_t)kc * 2048 + r * 16));
             }
         } else if (FP) {
-            // ---- three_nn + inverse-distance weights of the tile's rows (tf_interpolate.cpp:60-105, pointnet_util.py:217-222):
-            // two adjacent lanes per row, each scans half of the known points in index order; exact un-fused f32 ----
+            // ---- (idx, weight) of the tile's rows: three_nn + inverse-distance weights (tf_interpolate.cpp:60-105,
+            // pointnet_util.py:217-222) come from the stage's 24-byte-per-row tables (ops.cu three_nn_kernel; evaluating
+            // them here put a 256-candidate insertion chain in front of every tile: +0.26 ms for fa_layer3) ----
             const long row0 = (long)blockIdx.x * TM;
             const long cloud = row0 / a.rows_per_cloud;
-            if (a.fp_idx_in) {
-                for (int i = tid; i < TM * 3; i += NWORK) {
-                    s_nni[i] = __ldg(a.fp_idx_in + (size_t)row0 * 3 + i);
-                    s_nnw[i] = __ldg(a.fp_w_in + (size_t)row0 * 3 + i);
-                }
-            } else {
-                const int row = tid >> 1, part = tid & 1;
-                const float *q = a.fp_xyz1 + (size_t)(row0 + row) * 3;
-                const float x1 = __ldg(q), y1 = __ldg(q + 1), z1 = __ldg(q + 2);
-                const float *kn = a.fp_xyz2 + (size_t)cloud * a.fp_m2 * 3;
-                const int chunk = (a.fp_m2 + 1) / 2;
-                const int k0 = part * chunk, k1 = min(a.fp_m2, k0 + chunk);
-                Best3 best;
-                best.init();
-                for (int k = k0; k < k1; ++k)
-                    best.insert(nn_dist_unfused(__ldg(kn + k * 3), __ldg(kn + k * 3 + 1), __ldg(kn + k * 3 + 2), x1, y1, z1), k);
-                Best3 o;
-                o.d1 = __shfl_xor_sync(0xFFFFFFFFu, best.d1, 1); o.i1 = __shfl_xor_sync(0xFFFFFFFFu, best.i1, 1);
-                o.d2 = __shfl_xor_sync(0xFFFFFFFFu, best.d2, 1); o.i2 = __shfl_xor_sync(0xFFFFFFFFu, best.i2, 1);
-                o.d3 = __shfl_xor_sync(0xFFFFFFFFu, best.d3, 1); o.i3 = __shfl_xor_sync(0xFFFFFFFFu, best.i3, 1);
-                if (part == 0) {
-                    best.merge_higher(o);
-                    float w1, w2, w3;
-                    three_weights(best.d1, best.d2, best.d3, w1, w2, w3);
-                    s_nnw[row * 3 + 0] = w1; s_nnw[row * 3 + 1] = w2; s_nnw[row * 3 + 2] = w3;
-                    s_nni[row * 3 + 0] = best.i1; s_nni[row * 3 + 1] = best.i2; s_nni[row * 3 + 2] = best.i3;
-                    if (a.fp_idx_out) {                              // geometry tables for a second network over the same clouds
-                        const size_t g = (size_t)(row0 + row) * 3;
-                        a.fp_w_out[g] = w1; a.fp_w_out[g + 1] = w2; a.fp_w_out[g + 2] = w3;
-                        a.fp_idx_out[g] = best.i1; a.fp_idx_out[g + 1] = best.i2; a.fp_idx_out[g + 2] = best.i3;
-                    }
-                }
+            for (int i = tid; i < TM * 3; i += NWORK) {
+                s_nni[i] = __ldg(a.fp_idx + (size_t)row0 * 3 + i);
+                s_nnw[i] = __ldg(a.fp_w + (size_t)row0 * 3 + i);
             }
             asm volatile("bar.sync 2, %0;" ::"n"(NWORK) : "memory");
             // ---- rows: [three_interpolate(points2) (C1) | X2 (C2) | zero pad] (pointnet_util.py:223-228) ----
@@ -529,7 +553,12 @@ __global__ void __launch_bounds__(NTHR, MINB) chain2_kernel(const __grid_constan
                         for (int i = 0; i < CW; ++i) v[i] = fmaxf(v[i], 0.f);
                     }
                     if (FP && U.act) {
-                        if constexpr (FP) head_activations(U.act, col, v, R, a.n_parts, a.mixed, a.pred);
+                        if constexpr (FP) {
+                            float x[32];                              // a copy: v itself must stay in registers (see nocs_head_act)
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) x[i] = v[i];
+                            head_activations(U.act, col, x, R, a.n_parts, a.mixed, a.pred);
+                        }
                     } else if (U.pool) {
                         const long g = ((long)blockIdx.x * TM + wq * 32) / a.S;
                         pool_store2<CW>(U.out + ((size_t)b * a.m + g) * U.Nfull + col, a.S, lane, v);
@@ -682,16 +711,13 @@ int chain_tc2_launch(const ChainTcArgs &c, long rows_total, cudaStream_t st)
     bool heads = false;
     for (int i = 0; i < c.nsteps; ++i) heads = heads || c.S[i].act != TC_ACT_NONE;
     if (fp) {
-        // a tile must not straddle clouds; the three_nn tables come in pairs
-        if (a.rows_per_cloud % TM != 0 || !c.fp_xyz1 || !c.fp_xyz2 || c.fp_m2 < 1 || (c.fp_idx_in == nullptr) != (c.fp_w_in == nullptr) ||
-            (c.fp_idx_out == nullptr) != (c.fp_w_out == nullptr))
-            return ANCSH_ERR_INVALID_ARG;
-        a.fp_points2 = c.fp_points2; a.fp_xyz1 = c.fp_xyz1; a.fp_xyz2 = c.fp_xyz2; a.fp_m2 = c.fp_m2;
-        a.fp_idx_in = c.fp_idx_in; a.fp_w_in = c.fp_w_in; a.fp_idx_out = c.fp_idx_out; a.fp_w_out = c.fp_w_out;
+        // a tile must not straddle clouds
+        if (a.rows_per_cloud % TM != 0 || c.fp_m2 < 1 || !c.fp_idx || !c.fp_w) return ANCSH_ERR_INVALID_ARG;
+        a.fp_points2 = c.fp_points2; a.fp_m2 = c.fp_m2; a.fp_idx = c.fp_idx; a.fp_w = c.fp_w;
     }
     if (heads) {
         // the epilogue keeps W | nocs | scale | trans of a row in one 32-column group (gocs = nocs * scale + trans)
-        if (!fp || c.n_parts < 1 || (c.mixed ? 8 * c.n_parts : 4 * c.n_parts) > 32) return ANCSH_ERR_UNSUPPORTED;
+        if (!fp || c.n_parts < 2 || (c.mixed ? 8 * c.n_parts : 4 * c.n_parts + 1) > 32) return ANCSH_ERR_UNSUPPORTED;
         a.pred = c.pred; a.n_parts = c.n_parts; a.mixed = c.mixed;
     }
     LayerSpec spec[8] = {};

@@ -246,9 +246,11 @@ __global__ void __launch_bounds__(256) group_point_kernel(int n, int c, long row
 // three_nn -- tf_interpolate.cpp:60-103 (a single CPU thread in the reference).  One thread per query,
 // known points staged through shared memory.  Un-fused f32 distance, strict '<' insertion chain.
 // =====================================================================================================
+// dist / weight: either may be NULL; weight = the inverse-distance weights of pointnet_util.py:219-222 (the fused
+// feature-propagation gather of net_tc2.cu reads the (idx, weight) tables).
 __global__ void __launch_bounds__(256) three_nn_kernel(int n, int m, const float *__restrict__ xyz1,
                                                        const float *__restrict__ xyz2, float *__restrict__ dist,
-                                                       int *__restrict__ idx)
+                                                       int *__restrict__ idx, float *__restrict__ weight)
 {
     __shared__ float s_k[512 * 3];
     const int b = blockIdx.y;
@@ -267,9 +269,22 @@ __global__ void __launch_bounds__(256) three_nn_kernel(int n, int m, const float
     }
     if (j < n) {
         size_t o = ((size_t)b * n + j) * 3;
-        dist[o + 0] = best.d1; dist[o + 1] = best.d2; dist[o + 2] = best.d3;
+        if (dist) { dist[o + 0] = best.d1; dist[o + 1] = best.d2; dist[o + 2] = best.d3; }
         idx[o + 0] = best.i1; idx[o + 1] = best.i2; idx[o + 2] = best.i3;
+        if (weight) {
+            float w1, w2, w3;
+            three_weights(best.d1, best.d2, best.d3, w1, w2, w3);
+            weight[o + 0] = w1; weight[o + 1] = w2; weight[o + 2] = w3;
+        }
     }
+}
+
+int ancsh_three_nn_tables_impl(int b, int n, int m, const float *xyz1, const float *xyz2, int *idx, float *weight, cudaStream_t st)
+{
+    if (b <= 0 || n <= 0 || m <= 0 || b > 65535) return ANCSH_ERR_INVALID_ARG;
+    three_nn_kernel<<<dim3(ancsh_cdiv(n, 256), b), 256, 0, st>>>(n, m, xyz1, xyz2, nullptr, idx, weight);
+    ANCSH_CHECK_LAUNCH();
+    return ANCSH_OK;
 }
 
 // three_interpolate -- tf_interpolate.cpp:107-127 (f32, left-to-right, no fma)
@@ -375,7 +390,7 @@ int ancsh_three_nn(int b, int n, int m, const float *xyz1, const float *xyz2, fl
     if (b == 0 || n == 0) return ANCSH_OK;
     if (b > 65535) return ANCSH_ERR_UNSUPPORTED;
     dim3 grid(ancsh_cdiv(n, 256), b);
-    three_nn_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, m, xyz1, xyz2, dist, idx);
+    three_nn_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, m, xyz1, xyz2, dist, idx, nullptr);
     ANCSH_CHECK_LAUNCH();
     return ANCSH_OK;
 }

@@ -62,3 +62,6 @@ int ancsh_fps2_impl(int b, int n, int m, const float *xyz, int *idx, float *new_
                     cudaStream_t st);
 int ancsh_ball_query_impl(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2, int *idx,
                           int *pts_cnt, cudaStream_t st);
+// (idx, weight) tables of a feature-propagation stage: three_nn(xyz1 queries (b,n,3), xyz2 known (b,m,3)) + the
+// inverse-distance weights, both (b,n,3)
+int ancsh_three_nn_tables_impl(int b, int n, int m, const float *xyz1, const float *xyz2, int *idx, float *weight, cudaStream_t st);
