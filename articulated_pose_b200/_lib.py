@@ -36,7 +36,7 @@ def check(rc, what):
 
 class Layer(ctypes.Structure):
     _fields_ = [("W", ctypes.c_void_p), ("b", ctypes.c_void_p), ("W_tc", ctypes.c_void_p), ("cin", c_int), ("cout", c_int),
-                ("cin_pad", c_int), ("cout_pad", c_int), ("relu", c_int)]
+                ("cin_pad", c_int), ("cout_pad", c_int), ("relu", c_int), ("tc_descale", ctypes.c_float)]
 
 
 class Net(ctypes.Structure):

@@ -152,6 +152,7 @@ static int sa_tc_from(const ancsh_net_t *net, const SaArgs &s, int B, float radi
         L[l].Wimg = reinterpret_cast<const __half *>(s.L[l].W_tc);
         L[l].bias = s.L[l].b; L[l].K = s.L[l].cin_pad; L[l].N = s.L[l].cout_pad; L[l].relu = s.L[l].relu;
         L[l].has_bias_step = net->tc_bias_step;
+        L[l].descale = s.L[l].tc_descale;
     }
     int rc;
     if (!sa_lean_off() && idx_rw) {
@@ -426,6 +427,7 @@ static TcLayer tc_layer(const ancsh_layer_t &l, int has_bias_step = 0)
     t.Wimg = reinterpret_cast<const __half *>(l.W_tc);
     t.bias = l.b; t.K = l.cin_pad; t.N = l.cout_pad; t.relu = l.relu;
     t.has_bias_step = has_bias_step;
+    t.descale = l.tc_descale;
     return t;
 }
 

@@ -21,7 +21,7 @@
 //   * ball query fused into the gather: one warp per centroid, ballot + popc ordered compaction (bit-exact with
 //     tf_grouping_g.cu:3-36: first nsample in index order, padded with the first hit), indices handed to the gathering
 //     threads through shared memory.
-// Numerics: unchanged from net_tc2.cu (hi*hi and cross terms in separate f32 TMEM accumulators, summed in the epilogue).
+// Numerics: as net_tc2.cu (hi*hi and the 2^11-scaled cross terms in separate f32 TMEM accumulators, combined in the epilogue).
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -92,6 +92,7 @@ struct SaLeanArgs {
     float d2_below;           // smallest f32 t with sqrt_rn(t) >= radius: max(sqrt(d2), 1e-20) < radius  <=>  d2 < t (sqrt_rn is monotonic)
     int tiles_per_cta;
     LUnit U[MAXU];
+    float descale[3];         // per layer (conv0, conv1, conv2): accumulators * descale = layer output (TcLayer::descale)
     long long *trace;         // profiling aid (ANCSH_LEAN_TRACE): per-CTA clock64() stamps of the phase boundaries, or NULL
     float w0[4 * 64];         // xyz-only first conv: rows 0..2 = W[k][0..63], row 3 = bias
 };
@@ -139,7 +140,7 @@ __device__ __forceinline__ void split8_lean(const float (&v)[8], uint8_t *dst_hi
         const float a = v[2 * i], b = v[2 * i + 1];
         const float ha = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u), hb = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
         h[i] = pack_f16x2<RELU>(hb, ha);
-        l[i] = pack_f16x2<RELU>(b - hb, a - ha);
+        l[i] = pack_f16x2<RELU>((b - hb) * tc::LO_SCALE, (a - ha) * tc::LO_SCALE);        // lo piece stored * 2^11 (tc_common.cuh)
     }
     *reinterpret_cast<uint4 *>(dst_hi) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4 *>(dst_lo) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -152,24 +153,23 @@ __device__ __forceinline__ float max3(float a, float b, float c)
     return d;
 }
 
-// epilogue of an in-place layer: this thread's row, columns [h*N/2, (h+1)*N/2): (hi*hi + cross) -> ReLU -> split -> operand
-// ACC1: one accumulator holds both sums (cross terms issued first, see the MMA role)
-template <int N, bool ACC1>
-__device__ __forceinline__ void epi_inplace(uint32_t trow, int h, int r, uint8_t *A_hi, uint8_t *A_lo)
+// epilogue of an in-place layer: this thread's row, columns [h*N/2, (h+1)*N/2): (hi*hi + 2^-11 cross) * sc -> ReLU -> split -> operand
+template <int N>
+__device__ __forceinline__ void epi_inplace(uint32_t trow, int h, int r, float sc, uint8_t *A_hi, uint8_t *A_lo)
 {
+    const float sc_lo = sc * tc::LO_UNSCALE;
 #pragma unroll
     for (int cc = 0; cc < N / 2; cc += 32) {
         const int c0 = h * (N / 2) + cc;
         uint32_t ra[32], rb[32];
         tc::tmem_ld32_issue(trow + (uint32_t)c0, ra);
-        if (!ACC1) tc::tmem_ld32_issue(trow + (uint32_t)(N + c0), rb);
+        tc::tmem_ld32_issue(trow + (uint32_t)(N + c0), rb);
         tc::tmem_wait_ld();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             float v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                v[i] = ACC1 ? __uint_as_float(ra[q * 8 + i]) : __uint_as_float(ra[q * 8 + i]) + __uint_as_float(rb[q * 8 + i]);
+            for (int i = 0; i < 8; ++i) v[i] = fmaf(__uint_as_float(rb[q * 8 + i]), sc_lo, __uint_as_float(ra[q * 8 + i]) * sc);
             const int kc = (c0 >> 3) + q;
             split8_lean<true>(v, A_hi + (size_t)kc * 2048 + r * 16, A_lo + (size_t)kc * 2048 + r * 16);
         }
@@ -178,8 +178,8 @@ __device__ __forceinline__ void epi_inplace(uint32_t trow, int h, int r, uint8_t
 
 // epilogue of a transposed pooled block: this thread's TMEM lane = one output channel, columns [h*64, h*64+64) = rows of
 // 64 / S centroids.  out_c points at out[centroid 0 of the tile][channel of this lane]; ld = channels per centroid.
-template <int S, bool ACC1>
-__device__ __forceinline__ void epi_pool_T(uint32_t trow, int h, float bias, float *out_c, int ld)
+template <int S>
+__device__ __forceinline__ void epi_pool_T(uint32_t trow, int h, float sc, float bias, float *out_c, int ld)
 {
     static_assert(S == 32 || S == 64, "nsample 32 or 64");
 #pragma unroll
@@ -190,16 +190,15 @@ __device__ __forceinline__ void epi_pool_T(uint32_t trow, int h, float bias, flo
             const int c0 = h * 64 + g * S + cc;
             uint32_t ra[32], rb[32];
             tc::tmem_ld32_issue(trow + (uint32_t)c0, ra);
-            if (!ACC1) tc::tmem_ld32_issue(trow + (uint32_t)(TM + c0), rb);
+            tc::tmem_ld32_issue(trow + (uint32_t)(TM + c0), rb);
             tc::tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-                if (ACC1) mx = max3(mx, __uint_as_float(ra[i]), __uint_as_float(ra[i + 1]));
-                else mx = max3(mx, __uint_as_float(ra[i]) + __uint_as_float(rb[i]), __uint_as_float(ra[i + 1]) + __uint_as_float(rb[i + 1]));
-            }
+            for (int i = 0; i < 32; i += 2)
+                mx = max3(mx, fmaf(__uint_as_float(rb[i]), tc::LO_UNSCALE, __uint_as_float(ra[i])),
+                          fmaf(__uint_as_float(rb[i + 1]), tc::LO_UNSCALE, __uint_as_float(ra[i + 1])));
         }
         const int centroid = h * (64 / S) + g;
-        out_c[(size_t)centroid * ld] = fmaxf(mx + bias, 0.f);   // relu(max(x) + b) == max(relu(x + b))
+        out_c[(size_t)centroid * ld] = fmaxf(fmaf(mx, sc, bias), 0.f);   // relu(max(x) * sc + b) == max(relu(x * sc + b)), sc > 0
     }
 }
 
@@ -228,38 +227,14 @@ struct MmaCtx {
     int slot, round;                 // ring position (streaming plans)
 };
 
-template <class P, int U, bool ACC1>
+template <class P, int U>
 __device__ __forceinline__ void issue_unit(MmaCtx &c, bool first_tile)
 {
     constexpr bool T = P::transposed(U);
     constexpr int NC = P::nc(U), NK = P::nk(U), KPS = P::kps(U);
     constexpr uint32_t idesc = T ? tc::instr_desc_f16(128, TM) : tc::instr_desc_f16(TM, NC);
     constexpr bool BIAS = !T;
-    const uint32_t hh = c.tmem, cr = ACC1 ? c.tmem : c.tmem + (uint32_t)(T ? TM : NC);
-    static_assert(!ACC1 || P::RESIDENT, "one-accumulator order needs the unit's weights resident (two passes)");
-    if (ACC1) {
-        // cross terms first, hi*hi products on top: the small products are summed among themselves before the
-        // (truncating) accumulator grows large
-        const uint32_t st = c.ring0 + (uint32_t)P::slot_off(U);
-        if (first_tile) tc::mbar_wait(c.bar_full + U, 0u);
-        const uint64_t wh0 = tc::smem_desc(st, 2u * NC * 16u, 128u), wl0 = wh0 + (uint64_t)NC;
-#pragma unroll
-        for (int kk = 0; kk < NK - (BIAS ? 1 : 0); ++kk) {
-            const uint64_t wh = wh0 + (uint64_t)(kk * NC * 4), wl = wl0 + (uint64_t)(kk * NC * 4);       // k-step = NC * 64 B
-            const uint64_t ah = c.ah0 + (uint64_t)(kk * 256), al = c.al0 + (uint64_t)(kk * 256);
-            if (!T) { tc::mma_f16(cr, ah, wl, idesc, kk > 0); tc::mma_f16(cr, al, wh, idesc, 1u); }
-            else { tc::mma_f16(cr, wh, al, idesc, kk > 0); tc::mma_f16(cr, wl, ah, idesc, 1u); }
-        }
-#pragma unroll
-        for (int kk = 0; kk < NK; ++kk) {
-            const uint64_t wh = wh0 + (uint64_t)(kk * NC * 4);
-            const uint64_t ah = c.ah0 + (uint64_t)(kk * 256);
-            if (BIAS && kk == NK - 1) tc::mma_f16(hh, c.on0, wh, idesc, 1u);
-            else if (!T) tc::mma_f16(hh, ah, wh, idesc, 1u);
-            else tc::mma_f16(hh, wh, ah, idesc, 1u);
-        }
-        return;
-    }
+    const uint32_t hh = c.tmem, cr = c.tmem + (uint32_t)(T ? TM : NC);     // hi*hi accumulator, cross-term accumulator
 #pragma unroll
     for (int s0 = 0; s0 < NK; s0 += KPS) {
         uint32_t st;
@@ -296,8 +271,8 @@ __device__ __forceinline__ void issue_unit(MmaCtx &c, bool first_tile)
 }
 
 // C: feature channels of the dataset (0: xyz only, first conv on the CUDA cores).  N0/N1/N2: layer widths.
-// S: nsample (32 / 64).  BALL: ball query in the kernel.  ACC1: one TMEM accumulator per output (resident plans only).
-template <int C, int N0, int N1, int N2, int S, bool BALL, bool ACC1>
+// S: nsample (32 / 64).  BALL: ball query in the kernel.
+template <int C, int N0, int N1, int N2, int S, bool BALL>
 __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant__ SaLeanArgs a)
 {
     using P = Plan<C, N0, N1, N2>;
@@ -383,10 +358,10 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
                 LEAN_TRACE(64, 0);
 #pragma unroll
                 for (int u = 0; u < NU; ++u) {
-                    if (u == 0) issue_unit<P, 0, ACC1>(c, t == 0);
-                    if (u == 1) issue_unit<P, 1 < NU ? 1 : 0, ACC1>(c, t == 0);
-                    if (u == 2) issue_unit<P, 2 < NU ? 2 : 0, ACC1>(c, t == 0);
-                    if (u == 3) issue_unit<P, 3 < NU ? 3 : 0, ACC1>(c, t == 0);
+                    if (u == 0) issue_unit<P, 0>(c, t == 0);
+                    if (u == 1) issue_unit<P, 1 < NU ? 1 : 0>(c, t == 0);
+                    if (u == 2) issue_unit<P, 2 < NU ? 2 : 0>(c, t == 0);
+                    if (u == 3) issue_unit<P, 3 < NU ? 3 : 0>(c, t == 0);
                     tc::mma_commit(bar_acc);
                     LEAN_TRACE(64, 3 + 4 * u);
                     tc::mbar_wait(bar_ready, rp & 1u); ++rp;      // epilogue done: operand rewritten / TMEM drained
@@ -532,7 +507,7 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
                 tc::mbar_wait(bar_acc, uc & 1u); ++uc;
                 if (warp == 0 || warp == 4) LEAN_TRACE(tb, 4);
                 tc::fence_after_sync();
-                epi_inplace<N0, ACC1>(trow, h, r, A_hi, A_lo);
+                epi_inplace<N0>(trow, h, r, a.descale[0], A_hi, A_lo);
                 if (warp == 0 || warp == 4) LEAN_TRACE(tb, 5);
                 ready();
             }
@@ -540,7 +515,7 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
                 tc::mbar_wait(bar_acc, uc & 1u); ++uc;
                 if (warp == 0 || warp == 4) LEAN_TRACE(tb, 6);
                 tc::fence_after_sync();
-                epi_inplace<N1, ACC1>(trow, h, r, A_hi, A_lo);
+                epi_inplace<N1>(trow, h, r, a.descale[1], A_hi, A_lo);
                 if (warp == 0 || warp == 4) LEAN_TRACE(tb, 7);
                 ready();
             }
@@ -560,7 +535,7 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
                 tc::fence_after_sync();
                 const int ch = blk * 128 + wq * 32 + lane;
                 float *out_c = a.out + ((size_t)b * a.m + (size_t)tile * CPT) * N2 + ch;
-                epi_pool_T<S, ACC1>(trow, h, __ldg(a.bias_last + ch), out_c, N2);
+                epi_pool_T<S>(trow, h, a.descale[2], __ldg(a.bias_last + ch), out_c, N2);
                 if (warp == 0 || warp == 4) LEAN_TRACE(tb, 10 + 3 * blk);
                 ready();
             }
@@ -583,13 +558,13 @@ LUnit make_unit(const TcLayer &L, int n0)
     return U;
 }
 
-template <int C, int N0, int N1, int N2, int S, bool BALL, bool ACC1>
+template <int C, int N0, int N1, int N2, int S, bool BALL>
 int launch(const SaLeanArgs &a, dim3 grid, cudaStream_t st)
 {
     using P = Plan<C, N0, N1, N2>;
     const size_t smem = (size_t)2 * P::K8 * 2048 + 4096 + (size_t)P::RING_BYTES + (2 * MAX_STAGES + 2) * sizeof(uint64_t) + 16 +
                         16 * sizeof(int) + 16 * S * sizeof(int) + (size_t)P::XYZ_MAX * 3 * sizeof(float);
-    auto k = sa_lean_kernel<C, N0, N1, N2, S, BALL, ACC1>;
+    auto k = sa_lean_kernel<C, N0, N1, N2, S, BALL>;
     ANCSH_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ANCSH_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     k<<<grid, NTHR, smem, st>>>(a);
@@ -597,11 +572,11 @@ int launch(const SaLeanArgs &a, dim3 grid, cudaStream_t st)
     return ANCSH_OK;
 }
 
-template <int C, int N0, int N1, int N2, bool ACC1>
+template <int C, int N0, int N1, int N2>
 int dispatch(const SaLeanArgs &a, int S, bool ball, dim3 grid, cudaStream_t st)
 {
-    if (S == 32) return ball ? launch<C, N0, N1, N2, 32, true, ACC1>(a, grid, st) : launch<C, N0, N1, N2, 32, false, ACC1>(a, grid, st);
-    if (S == 64) return ball ? launch<C, N0, N1, N2, 64, true, ACC1>(a, grid, st) : launch<C, N0, N1, N2, 64, false, ACC1>(a, grid, st);
+    if (S == 32) return ball ? launch<C, N0, N1, N2, 32, true>(a, grid, st) : launch<C, N0, N1, N2, 32, false>(a, grid, st);
+    if (S == 64) return ball ? launch<C, N0, N1, N2, 64, true>(a, grid, st) : launch<C, N0, N1, N2, 64, false>(a, grid, st);
     return ANCSH_ERR_UNSUPPORTED;
 }
 
@@ -623,6 +598,7 @@ int sa_lean_launch(const SaLeanArgs2 &s, int B, cudaStream_t st)
     SaLeanArgs a{};
     a.xyz = s.xyz; a.points = s.points; a.new_xyz = s.new_xyz; a.idx_in = s.idx_in; a.idx_out = s.idx_out; a.cnt_out = s.cnt_out;
     a.out = s.out; a.bias_last = s.L[2].bias; a.n = s.n; a.m = s.m; a.radius = s.radius;
+    for (int l = 0; l < 3; ++l) a.descale[l] = s.L[l].descale;
     {
         // threshold on the squared distance that reproduces the reference's test on the rounded square root bit for bit
         if (!(s.radius > 1e-20f) || !std::isfinite(s.radius)) return ANCSH_ERR_UNSUPPORTED;
@@ -647,8 +623,6 @@ int sa_lean_launch(const SaLeanArgs2 &s, int B, cudaStream_t st)
         a.U[3] = make_unit(s.L[2], 128);
     }
     const dim3 grid((unsigned)(tiles / a.tiles_per_cta), (unsigned)B);
-    // A/B switch: ANCSH_LEAN_ACC1 = one TMEM accumulator per output for the resident plan (cross terms issued first)
-    static const bool acc1 = getenv("ANCSH_LEAN_ACC1") != nullptr;
     // profiling aid: ANCSH_LEAN_TRACE=<file prefix> dumps the phase time stamps of the 4th launch of each stage
     static const char *trace_path = getenv("ANCSH_LEAN_TRACE");
     static int trace_calls[2] = {0, 0};
@@ -659,8 +633,7 @@ int sa_lean_launch(const SaLeanArgs2 &s, int B, cudaStream_t st)
         else cudaMemsetAsync(trace_dev, 0, trace_n * sizeof(long long), st);
     }
     a.trace = trace_dev;
-    const int rc = sa1 ? (acc1 ? dispatch<0, 64, 64, 128, true>(a, s.S, ball, grid, st) : dispatch<0, 64, 64, 128, false>(a, s.S, ball, grid, st))
-                       : dispatch<128, 128, 128, 256, false>(a, s.S, ball, grid, st);
+    const int rc = sa1 ? dispatch<0, 64, 64, 128>(a, s.S, ball, grid, st) : dispatch<128, 128, 128, 256>(a, s.S, ball, grid, st);
     if (trace_dev) {
         std::vector<long long> h(trace_n);
         cudaStreamSynchronize(st);

@@ -78,15 +78,16 @@ __device__ __forceinline__ void load_acc(uint32_t trow, int G, int c0, float (&v
         tc::tmem_ld32_issue(trow + (uint32_t)nch + c0, rb);
         tc::tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ra[i]) + __uint_as_float(rb[i]);
+        for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(rb[i]), tc::LO_UNSCALE, __uint_as_float(ra[i]));
         return;
     }
     tc::tmem_ld32(trow + c0, v);
     for (int g = 1; g <= G; ++g) {           // g == G is the cross-term accumulator B
         float u[32];
         tc::tmem_ld32(trow + (uint32_t)(g * nch) + c0, u);
+        const float f = g == G ? tc::LO_UNSCALE : 1.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += u[i];
+        for (int i = 0; i < 32; ++i) v[i] = fmaf(u[i], f, v[i]);
     }
 }
 
@@ -200,7 +201,7 @@ __global__ void __launch_bounds__(TM) gemm_tc_kernel(const GemmTcArgs a)
         load_acc(trow, G, c0, v, NCH);
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-            const float x = v[i] + __ldg(a.L.bias + n0 + c0 + i);
+            const float x = fmaf(v[i], a.L.descale, __ldg(a.L.bias + n0 + c0 + i));
             v[i] = a.L.relu ? fmaxf(x, 0.f) : x;
         }
         if (a.pool_S == 0) {

@@ -9,6 +9,7 @@ struct TcLayer {
     const float *bias;           // [N] f32 (BN folded)
     int K, N, relu;              // K = cin_pad (multiple of 16), N = cout_pad (64 / 128 / 256)
     int has_bias_step;           // the image carries the extra bias k-step after K (ancsh_net_t::tc_bias_step)
+    float descale;               // the image holds W * 2^s: accumulators are multiplied by descale = 2^-s (ancsh_layer_t::tc_descale)
 };
 
 struct SaTcArgs {

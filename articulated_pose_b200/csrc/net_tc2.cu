@@ -50,6 +50,7 @@ struct Unit {
     int nsl;               // ring stages (slices) per chunk
     int relu, inplace, pool, ldo;
     int act;               // TC_ACT_*: head activations in the epilogue
+    float descale;         // accumulators * descale = the layer's output (TcLayer::descale)
 };
 
 struct Chain2Args {
@@ -118,12 +119,16 @@ __device__ __forceinline__ void load_acc2(uint32_t trow, int G, int c0, float (&
     tmem_ld16_issue(trow + (uint32_t)stride + c0, rb);
     tc::tmem_wait_ld();
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]) + __uint_as_float(rb[i]);
+    // accumulators 0 .. G-1: hi*hi parts; accumulator G: cross terms, scaled by 2^11 (tc_common.cuh)
+    const float f1 = G == 1 ? tc::LO_UNSCALE : 1.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fmaf(__uint_as_float(rb[i]), f1, __uint_as_float(ra[i]));
     for (int g = 2; g <= G; ++g) {
         tmem_ld16_issue(trow + (uint32_t)(g * stride) + c0, ra);
         tc::tmem_wait_ld();
+        const float f = g == G ? tc::LO_UNSCALE : 1.f;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(ra[i]);
+        for (int i = 0; i < 16; ++i) v[i] = fmaf(__uint_as_float(ra[i]), f, v[i]);
     }
 }
 
@@ -136,15 +141,16 @@ __device__ __forceinline__ void load_acc2(uint32_t trow, int G, int c0, float (&
         tc::tmem_ld32_issue(trow + (uint32_t)stride + c0, rb);
         tc::tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ra[i]) + __uint_as_float(rb[i]);
+        for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(rb[i]), tc::LO_UNSCALE, __uint_as_float(ra[i]));
         return;
     }
     tc::tmem_ld32(trow + c0, v);
     for (int g = 1; g <= G; ++g) {
         float u[32];
         tc::tmem_ld32(trow + (uint32_t)(g * stride) + c0, u);
+        const float f = g == G ? tc::LO_UNSCALE : 1.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += u[i];
+        for (int i = 0; i < 32; ++i) v[i] = fmaf(u[i], f, v[i]);
     }
 }
 
@@ -156,7 +162,7 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4 *dst_hi, uint4
     for (int i = 0; i < 4; ++i) {
         const __half2 hi = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
         const float2 back = __half22float2(hi);
-        const __half2 lo = __floats2half2_rn(v[2 * i] - back.x, v[2 * i + 1] - back.y);
+        const __half2 lo = __floats2half2_rn((v[2 * i] - back.x) * tc::LO_SCALE, (v[2 * i + 1] - back.y) * tc::LO_SCALE);
         h[i] = *reinterpret_cast<const uint32_t *>(&hi);
         l[i] = *reinterpret_cast<const uint32_t *>(&lo);
     }
@@ -546,7 +552,8 @@ __global__ void __launch_bounds__(NTHR, MINB) chain2_kernel(const __grid_constan
 #pragma unroll
                     for (int i = 0; i < CW / 4; ++i) {
                         const float4 bb = __ldg(b4 + i);
-                        v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+                        v[4 * i] = fmaf(v[4 * i], U.descale, bb.x); v[4 * i + 1] = fmaf(v[4 * i + 1], U.descale, bb.y);
+                        v[4 * i + 2] = fmaf(v[4 * i + 2], U.descale, bb.z); v[4 * i + 3] = fmaf(v[4 * i + 3], U.descale, bb.w);
                     }
                     if (U.relu) {
 #pragma unroll
@@ -650,6 +657,7 @@ int build_units(Chain2Args &a, const LayerSpec *spec, int nspec, size_t *smem_ou
             U.ksl = STAGE_BYTES / (64 * nc);
             U.nsl = (L.K / 16 + U.ksl - 1) / U.ksl;
             U.relu = L.relu; U.inplace = spec[i].inplace; U.pool = spec[i].pool; U.act = spec[i].act;
+            U.descale = L.descale;
         }
     }
     for (int u = 0; u < a.nunits; ++u) {

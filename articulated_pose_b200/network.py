@@ -82,6 +82,7 @@ class AncshNet:
             dst.W, dst.b = base + 4 * wo, base + 4 * bo
             dst.W_tc = tc_base + 2 * tc_offs[slot] if slot in tc_offs else None
             dst.cin, dst.cout, dst.cin_pad, dst.cout_pad, dst.relu = pl.cin, pl.cout, pl.cin_pad, pl.cout_pad, pl.relu
+            dst.tc_descale = float(np.ldexp(1.0, -pl.tc_exp))
         net.tc_bias_step = 1
         l0 = self.layers["sa1[0]"]
         self._sa1_conv0 = np.ascontiguousarray(np.concatenate([l0.W[:3, :64].ravel(), l0.b[:64]]).astype(np.float32)) \

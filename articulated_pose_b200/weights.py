@@ -112,6 +112,7 @@ class PackedLayer:
         self.W[:cin, :cout] = W
         self.b = np.zeros((self.cout_pad,), np.float32)
         self.b[:cout] = b
+        self.tc_exp = 0      # power-of-two scale of the tensor-core image (set by flatten_tc_images)
 
 
 def pack_network(weights, n_parts, mixed_pred=True, early_split_nocs=True, prefix="SPFN"):
@@ -180,19 +181,36 @@ def bf16_bits_to_f32(b):
     return (b.astype(np.uint32) << 16).view(np.float32)
 
 
-def tc_image(W, b=None):
-    """Tensor-core operand image of a padded weight matrix W [cin_pad][cout_pad] (f32): W^T split into
+def tc_scale_exp(W, b=None):
+    """Power-of-two scale exponent s of a layer's tensor-core image: W * 2^s (and b * 2^s) put the largest magnitude into
+    [2^13, 2^14).  fp16 pieces are exact to 11 bits only while normal (>= 6.1e-5): unscaled BN-folded weights of ~1e-3
+    lose the lo piece to subnormals (measured 1.7e-5 relative output error, 1.7e-4 at 1e-4); scaled, hi + lo keeps ~22 bits
+    for every weight down to 2^-17 of the layer's largest.  The kernels undo the scale on the f32 accumulators
+    (ancsh_layer_t::tc_descale = 2^-s, exact)."""
+    m = float(np.abs(np.asarray(W, np.float32)).max(initial=0.0))
+    if b is not None:
+        m = max(m, float(np.abs(np.asarray(b, np.float32)).max(initial=0.0)))
+    if not np.isfinite(m):
+        raise ValueError("non-finite weights")
+    if m == 0.0:
+        return 0
+    return int(np.clip(13 - np.floor(np.log2(m)), -100, 100))
+
+
+def tc_image(W, b=None, scale_exp=0):
+    """Tensor-core operand image of a padded weight matrix W [cin_pad][cout_pad] (f32), scaled by 2^scale_exp: W^T split into
     hi = fp16(w), lo = fp16(w - hi) (round to nearest even), tiled as [K/8][2][cout_pad][8] fp16 bit patterns
     (csrc/tc_common.cuh).  hi + lo carries ~22 significant bits of w.
     With a bias b [cout_pad], K = cin_pad + 16: the extra k-step holds the rows (fp16(b), fp16(b - fp16(b)), 0 ...), so
     that a GEMM whose operand has ones in those two columns adds the bias (csrc/net_lean.cu); kernels that use
     K = cin_pad never read it."""
+    W = np.ldexp(np.asarray(W, np.float32), int(scale_exp)).astype(np.float32)
     if b is not None:
-        b = np.asarray(b, np.float32)
+        b = np.ldexp(np.asarray(b, np.float32), int(scale_exp)).astype(np.float32)
         if np.abs(b).max(initial=0.0) >= 65504:
             raise ValueError("bias exceeds the fp16 range of the tensor-core path")
         b_hi = b.astype(np.float16).astype(np.float32)
-        b_lo = (b - b_hi).astype(np.float16).astype(np.float32)
+        b_lo = (b - b_hi).astype(np.float16).astype(np.float32)      # a K row of the hi image (times the ones slab): NOT scaled
         extra = np.zeros((16, W.shape[1]), np.float32)
         extra[0], extra[1] = b_hi, b_lo
         W = np.concatenate([np.asarray(W, np.float32), extra], axis=0)
@@ -201,7 +219,7 @@ def tc_image(W, b=None):
     if np.abs(Wt).max() >= 65504:
         raise ValueError("weights exceed the fp16 range of the tensor-core path")
     hi16 = Wt.astype(np.float16)
-    lo16 = (Wt - hi16.astype(np.float32)).astype(np.float16)
+    lo16 = ((Wt - hi16.astype(np.float32)) * np.float32(2048.0)).astype(np.float16)      # lo piece stored * 2^11 (tc_common.cuh)
     hi, lo = hi16.view(np.uint16), lo16.view(np.uint16)
     img = np.stack([hi.reshape(N, K // 8, 8), lo.reshape(N, K // 8, 8)], axis=0)   # [2][N][K/8][8]
     return np.ascontiguousarray(img.transpose(2, 0, 1, 3))          # [K/8][2][N][8]
@@ -212,10 +230,12 @@ TC_SLOTS = ("sa1[0]", "sa1[1]", "sa1[2]", "sa2[0]", "sa2[1]", "sa2[2]", "sa3[0]"
 
 
 def flatten_tc_images(layers):
-    """uint16 buffer with the tensor-core images of the layers that run on tcgen05, 256-byte aligned offsets."""
+    """uint16 buffer with the tensor-core images of the layers that run on tcgen05, 256-byte aligned offsets.
+    Sets layers[slot].tc_exp (the power-of-two scale of each image, tc_scale_exp)."""
     off, offs, parts = 0, {}, []
     for slot in TC_SLOTS:
-        img = tc_image(layers[slot].W, layers[slot].b).ravel()
+        layers[slot].tc_exp = tc_scale_exp(layers[slot].W, layers[slot].b)
+        img = tc_image(layers[slot].W, layers[slot].b, layers[slot].tc_exp).ravel()
         offs[slot] = off
         parts.append((off, img))
         off = (off + img.size + 127) // 128 * 128

@@ -102,6 +102,9 @@ typedef struct {
                          W^T split as hi = fp16(w), lo = fp16(w - hi) (weights.tc_image); used when use_tensor_cores */
     int cin, cout, cin_pad, cout_pad;
     int relu;
+    float tc_descale; /* W_tc holds W * 2^s (s = the layer's power-of-two scale, weights.tc_scale_exp: the largest |w| or |b|
+                         lands in [2^13, 2^14), so that BN-folded weights of any magnitude keep both fp16 pieces in the
+                         normal range); the kernels multiply the accumulators by tc_descale = 2^-s (exact).  1 if unscaled. */
 } ancsh_layer_t;
 
 typedef struct {

@@ -53,19 +53,30 @@ def test_pipeline_matches_stagewise_and_oracle():
     idx_s = solver.sample_indices(0, cnt.reshape(-1), 128).reshape(B, K, 128, 3)
     idx_0 = solver.sample_indices(1, np.repeat(cnt[:, :1], K - 1, 1).reshape(-1), 16).reshape(B, K - 1, 16, 3)
     idx_1 = solver.sample_indices(2, cnt[:, 1:].reshape(-1), 16).reshape(B, K - 1, 16, 3)
-    checked = 0
+    checked, checked_joint, clouds_compared = 0, 0, 0
     for b in range(B):
         if not np.array_equal(np.argmax(on["W"][b], 1), np.argmax(pn["W"][b], 1)):
             continue
+        clouds_compared += 1
         ref = pose_np.solve_cloud(P[b], on["nocs_per_point"][b], on["W"][b], oa["joint_axis_per_point"][b], jc[b], K, 0.1,
                                   idx_s[b], idx_0[b], idx_1[b])
         for j in range(K):
-            same = np.array_equal(res[b]["inliers_single"][j], ref["inliers_single"][j])
-            if same:       # identical inlier sets -> the refit differs only by the 1e-4 input differences
-                assert np.abs(res[b]["baseline"][j]["rotation"] - ref["baseline"][j]["rotation"]).max() < 5e-3
-                assert abs(res[b]["baseline"][j]["scale"] - ref["baseline"][j]["scale"]) < 5e-3
+            # EVERY part whose inlier set coincides must agree: the refit then differs only by the <= 1e-4 differences of
+            # the network outputs it is fed with
+            if np.array_equal(res[b]["inliers_single"][j], ref["inliers_single"][j]):
+                m, r = res[b]["baseline"][j], ref["baseline"][j]
+                assert np.abs(m["rotation"] - r["rotation"]).max() < 1e-3, (b, j)
+                assert abs(m["scale"] - r["scale"]) < 1e-3 and np.abs(m["translation"] - r["translation"]).max() < 1e-3, (b, j)
                 checked += 1
-    assert checked >= 3
+        for j in range(1, K):
+            gi, ri = res[b]["inliers_joint"][j - 1], ref["inliers_joint"][j - 1]
+            if np.array_equal(gi[0], ri[0]) and np.array_equal(gi[1], ri[1]):
+                m, r = res[b]["nonlinear"][j - 1], ref["nonlinear"][j - 1]
+                for f in ("rotation0", "rotation1", "translation0", "translation1"):
+                    assert np.abs(np.asarray(m[f]) - np.asarray(r[f])).max() < 1e-3, (b, j, f)
+                checked_joint += 1
+    # same partition on at least two of the three clouds, and most of their parts pick the same inlier set
+    assert clouds_compared >= 2 and checked >= 2 * clouds_compared and checked_joint >= 1, (clouds_compared, checked, checked_joint)
 
 
 def test_shared_geometry_forward_is_bit_identical():

@@ -197,3 +197,31 @@ def test_full_size_properties():
             assert np.abs(r3[b]["baseline"][j]["rotation"] - Q.astype(np.float64) @ r1[b]["baseline"][j]["rotation"]).max() < 2e-2
             assert abs(r3[b]["baseline"][j]["scale"] - r1[b]["baseline"][j]["scale"]) < 5e-3
         assert r1[b]["single_score"].min() > 50
+
+
+def test_reference_default_hypothesis_counts_match_oracle():
+    """One cloud at the reference's own settings -- 10000 single-part hypotheses (parallel_ancsh_pose.py:262) and 200 joint
+    hypotheses (:288) -- against the oracle replaying the same Philox draws: winners' inlier masks bit-exact, models 1e-6."""
+    from articulated_pose_b200 import synthetic
+    from articulated_pose_b200.pose import PoseSolver
+    from oracle import pose_np
+    cloud = synthetic.make_cloud(77, "eyeglasses")
+    pred = synthetic.teacher_predictions(cloud)
+    K, ns, nj = cloud["n_parts"], 10000, 200
+    solver = PoseSolver(K, niter_single=ns, niter_joint=nj, inlier_th=0.1, seed=2024)
+    args = _inputs(cloud, pred)
+    res = solver.solve(*args)[0]
+    cnt = res["part_count"]
+    idx_s = solver.sample_indices(0, cnt, ns).reshape(K, ns, 3)
+    idx_0 = solver.sample_indices(1, np.repeat(cnt[:1], K - 1), nj).reshape(K - 1, nj, 3)
+    idx_1 = solver.sample_indices(2, cnt[1:], nj).reshape(K - 1, nj, 3)
+    ref = pose_np.solve_cloud(args[0][0], args[1][0], args[2][0], args[3][0], args[4][0], K, 0.1, idx_s, idx_0, idx_1)
+    for j in range(K):
+        np.testing.assert_array_equal(res["inliers_single"][j], ref["inliers_single"][j])
+        for f in ("rotation", "scale", "translation"):
+            assert close(res["baseline"][j][f], ref["baseline"][j][f]), (j, f)
+    for j in range(1, K):
+        np.testing.assert_array_equal(res["inliers_joint"][j - 1][0], ref["inliers_joint"][j - 1][0])
+        np.testing.assert_array_equal(res["inliers_joint"][j - 1][1], ref["inliers_joint"][j - 1][1])
+        for f in ("rotation0", "scale0", "translation0", "rotation1", "scale1", "translation1"):
+            assert close(res["nonlinear"][j - 1][f], ref["nonlinear"][j - 1][f]), (j, f)

@@ -58,8 +58,8 @@ def test_tc_image_layout_and_split():
     assert img.shape == (4, 2, 64, 8) and img.dtype == np.uint16
     hi = img[:, 0].view(np.float16).astype(np.float32).transpose(1, 0, 2).reshape(64, 32)     # [N][K]
     lo = img[:, 1].view(np.float16).astype(np.float32).transpose(1, 0, 2).reshape(64, 32)
-    np.testing.assert_allclose(hi + lo, Wm.T, rtol=2 ** -20, atol=1e-7)       # hi + lo carries ~22 mantissa bits
-    assert np.abs(lo).max() <= np.abs(Wm).max() * 2 ** -10
+    np.testing.assert_allclose(hi + lo / 2048.0, Wm.T, rtol=2 ** -20, atol=1e-7)   # hi + lo * 2^-11 carries ~22 mantissa bits
+    assert np.abs(lo).max() <= np.abs(Wm).max() * 2.0                               # the lo piece is stored * 2^11
     flat, offs = W.flatten_tc_images(W.pack_network(W.synthetic_weights(3), 3))
     assert all(o % 128 == 0 for o in offs.values()) and set(offs) == set(W.TC_SLOTS)
 
@@ -77,3 +77,29 @@ def test_tc_image_bias_step():
     np.testing.assert_allclose(step[0, :, 0] + step[0, :, 1], b, rtol=2 ** -20, atol=1e-7)
     assert not step[0, :, 2:].any() and not step[1].any()
     assert not img[4:, 1].any()                                      # the lo image of the bias step is empty
+
+
+def test_tc_image_scaling_keeps_small_weights_exact():
+    """Per-layer power-of-two scale of the tensor-core images (the fp16 hi/lo split has a 5-bit exponent):
+    hi + lo must reproduce W * 2^s to ~2^-21 of each weight whatever the layer's magnitude; unscaled, weights of 1e-4 keep
+    ~12 bits only."""
+    rng = np.random.default_rng(5)
+    for mag in (1e-5, 1e-4, 1e-3, 0.3, 40.0, 3e3):
+        Wm = (rng.standard_normal((32, 64)) * mag).astype(np.float32)
+        b = (rng.standard_normal(64) * mag).astype(np.float32)
+        s = W.tc_scale_exp(Wm, b)
+        top = max(np.abs(Wm).max(), np.abs(b).max()) * 2.0 ** s
+        assert 2 ** 13 <= top < 2 ** 14
+        img = W.tc_image(Wm, b, s)                                   # [K/8][2][N][8], K = 32 + 16 (bias step)
+        assert img.shape == (6, 2, 64, 8)
+        hi = img[:, 0].view(np.float16).astype(np.float64).transpose(1, 0, 2).reshape(64, 48)
+        lo = img[:, 1].view(np.float16).astype(np.float64).transpose(1, 0, 2).reshape(64, 48)
+        rec = (hi + lo / 2048.0)[:, :32].T * 2.0 ** -s              # the lo piece is stored * 2^11 (csrc/tc_common.cuh)
+        big = np.abs(Wm) > np.abs(Wm).max() * 2.0 ** -10
+        assert np.abs(rec - Wm)[big].max() <= np.abs(Wm).max() * 2.0 ** -21
+        np.testing.assert_allclose((hi + lo)[:, 32] * 2.0 ** -s + (hi + lo)[:, 33] * 2.0 ** -s, b, rtol=0, atol=np.abs(b).max() * 2.0 ** -21)
+    # even an unscaled image of small weights is accurate now: the lo piece is stored * 2^11
+    Wm = (rng.standard_normal((16, 64)) * 1e-4).astype(np.float32)
+    img = W.tc_image(Wm, None, 0)
+    rec = (img[:, 0].view(np.float16).astype(np.float64) + img[:, 1].view(np.float16).astype(np.float64) / 2048.0).transpose(1, 0, 2).reshape(64, 16).T
+    assert np.abs(rec - Wm).max() <= np.abs(Wm).max() * 2.0 ** -20        # ... and so does the 2^11 scale of the lo piece alone
