@@ -77,6 +77,22 @@ vp = ctypes.c_void_p
 ancsh_version = _sig("ancsh_version", [], ctypes.c_char_p)
 ancsh_launch_count = _sig("ancsh_launch_count", [], ctypes.c_ulonglong)
 ancsh_diag_fp64_fma = _sig("ancsh_diag_fp64_fma", [c_int, c_int, vp, vp])
+ancsh_weights_pack = _sig("ancsh_weights_pack", [c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(vp), ctypes.POINTER(c_size_t),
+                                                 c_int, c_int, c_int, ctypes.c_char_p, ctypes.POINTER(vp)])
+ancsh_packed_destroy = _sig("ancsh_packed_destroy", [vp], None)
+ancsh_packed_flat = _sig("ancsh_packed_flat", [vp, ctypes.POINTER(c_size_t)], vp)
+ancsh_packed_tc = _sig("ancsh_packed_tc", [vp, ctypes.POINTER(c_size_t)], vp)
+ancsh_packed_layer = _sig("ancsh_packed_layer", [vp, ctypes.c_char_p, ctypes.POINTER(c_size_t), ctypes.POINTER(c_size_t),
+                                                 ctypes.POINTER(c_size_t), ctypes.POINTER(c_int), ctypes.POINTER(c_int)])
+ancsh_net_create = _sig("ancsh_net_create", [vp, c_int, c_int, ctypes.POINTER(vp)])
+ancsh_net_get = _sig("ancsh_net_get", [vp], vp)
+ancsh_net_destroy = _sig("ancsh_net_destroy", [vp], None)
+ancsh_ransac_workspace_bytes = _sig("ancsh_ransac_workspace_bytes", [c_int, c_int, c_int, ctypes.POINTER(c_size_t)])
+ancsh_ransac_single = _sig("ancsh_ransac_single", [c_int, vp, vp, ctypes.c_double, c_int, vp, ctypes.c_ulonglong, vp, c_size_t,
+                                                   vp, vp, vp, vp, vp, vp, vp])
+ancsh_ransac_joint = _sig("ancsh_ransac_joint", [c_int, vp, vp, c_int, vp, vp, ctypes.POINTER(ctypes.c_double), ctypes.c_double,
+                                                 c_int, vp, vp, ctypes.c_ulonglong, vp, c_size_t, vp, vp, vp, vp, vp, vp, vp, vp,
+                                                 vp, vp, vp])
 ancsh_fps = _sig("ancsh_fps", [c_int, c_int, c_int, vp, vp, vp, vp])
 ancsh_fps_two_level = _sig("ancsh_fps_two_level", [c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp])
 ancsh_gather_point = _sig("ancsh_gather_point", [c_int, c_int, c_int, vp, vp, vp, vp])

@@ -1376,6 +1376,121 @@ extern "C" int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in
     return ANCSH_OK;
 }
 
+// ---- ransac() on caller datasets (parallel_ancsh_pose.py:20) for hosts without the Python mirror ---------------------------
+// Both entries express the dataset as a one-cloud problem of ancsh_pose_solve: the dataset's points become the parts of a
+// cloud (part membership through a 0/1 mask), so the kernels, the sampling streams and the results are the ones of the
+// per-cloud path.
+namespace {
+__global__ void ransac_dataset_kernel(int n0, int n1, const float *__restrict__ s0, const float *__restrict__ t0,
+                                      const float *__restrict__ s1, const float *__restrict__ t1, double dx, double dy, double dz,
+                                      float *P, float *nocs, float *mask, float *axis, int *jcls)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, n = n0 + n1, K = n1 > 0 ? 2 : 1;
+    if (i >= n) return;
+    const bool first = i < n0;
+    const float *s = first ? s0 + 3 * i : s1 + 3 * (i - n0), *t = first ? t0 + 3 * i : t1 + 3 * (i - n0);
+    for (int c = 0; c < 3; ++c) P[3 * i + c] = t[c];
+    for (int c = 0; c < 3 * K; ++c) nocs[3 * K * i + c] = 0.f;
+    for (int c = 0; c < 3; ++c) nocs[3 * K * i + (first ? 0 : 3) + c] = s[c];
+    for (int k = 0; k < K; ++k) mask[K * i + k] = (k == (first ? 0 : 1)) ? 1.f : 0.f;
+    if (K == 2) { axis[3 * i] = (float)dx; axis[3 * i + 1] = (float)dy; axis[3 * i + 2] = (float)dz; jcls[i] = 1; }
+}
+
+struct DatasetLayout { size_t P, nocs, mask, axis, jcls, out, pose_ws, total; };
+
+int dataset_layout(int n, int K, int niter_single, int niter_joint, DatasetLayout *L, ancsh_pose_ws_t *pw)
+{
+    ancsh_pose_cfg_t cfg{K, niter_single, niter_joint, 0.1, 0ull};
+    int rc = ancsh_pose_plan(&cfg, 1, n, pw);
+    if (rc) return rc;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align256(off + bytes); return o; };
+    L->P = take((size_t)n * 3 * 4); L->nocs = take((size_t)n * 3 * K * 4); L->mask = take((size_t)n * K * 4);
+    L->axis = take((size_t)n * 3 * 4); L->jcls = take((size_t)n * 4);
+    L->out = take(4096 + (size_t)3 * n);                 // scratch for the outputs the caller did not ask for
+    L->pose_ws = take(pw->total_bytes);
+    L->total = off;
+    return ANCSH_OK;
+}
+}  // namespace
+
+extern "C" int ancsh_ransac_workspace_bytes(int n_total, int n_parts, int niter, size_t *bytes)
+{
+    if (!bytes || n_total < 1 || (n_parts != 1 && n_parts != 2) || niter < 1) return ANCSH_ERR_INVALID_ARG;
+    DatasetLayout L;
+    ancsh_pose_ws_t pw;
+    int rc = dataset_layout(n_total, n_parts, n_parts == 1 ? niter : 1, n_parts == 2 ? niter : 1, &L, &pw);
+    if (rc) return rc;
+    *bytes = L.total;
+    return ANCSH_OK;
+}
+
+extern "C" int ancsh_ransac_single(int n, const float *source, const float *target, double inlier_th, int niter, const int *sample_idx,
+                                   unsigned long long seed, void *workspace, size_t workspace_bytes, double *R, double *scale,
+                                   double *t, int *score, unsigned char *inliers, int *status, void *stream)
+{
+    if (n < 1 || !source || !target || !workspace || !R || !scale || !t || !inliers || !status) return ANCSH_ERR_INVALID_ARG;
+    DatasetLayout L;
+    ancsh_pose_ws_t pw;
+    int rc = dataset_layout(n, 1, niter, 1, &L, &pw);
+    if (rc) return rc;
+    if (workspace_bytes < L.total) return ANCSH_ERR_WORKSPACE;
+    char *ws = (char *)workspace;
+    cudaStream_t st = (cudaStream_t)stream;
+    ransac_dataset_kernel<<<ancsh_cdiv(n, 256), 256, 0, st>>>(n, 0, source, target, nullptr, nullptr, 0, 0, 0, (float *)(ws + L.P),
+                                                              (float *)(ws + L.nocs), (float *)(ws + L.mask), nullptr, nullptr);
+    ANCSH_CHECK_LAUNCH();
+    ancsh_pose_cfg_t cfg{1, niter, 1, inlier_th, seed};
+    ancsh_pose_in_t in{};
+    in.P = (float *)(ws + L.P); in.nocs = (float *)(ws + L.nocs); in.mask = (float *)(ws + L.mask); in.idx_single = sample_idx;
+    ancsh_pose_out_t out{};
+    char *o = ws + L.out;
+    out.single_R = R; out.single_s = scale; out.single_t = t; out.single_inliers = inliers; out.status = status;
+    out.single_score = score ? score : (int *)(o + 0);
+    out.part_count = (int *)(o + 64);
+    // K == 1: the joint outputs are never written (ancsh_pose_solve skips the joint stage)
+    return ancsh_pose_solve(&cfg, &in, 1, n, ws + L.pose_ws, pw.total_bytes, &out, nullptr, stream);
+}
+
+extern "C" int ancsh_ransac_joint(int n0, const float *source0, const float *target0, int n1, const float *source1,
+                                  const float *target1, const double *joint_direction_host, double inlier_th, int niter,
+                                  const int *sample_idx0, const int *sample_idx1, unsigned long long seed, void *workspace,
+                                  size_t workspace_bytes, double *R0, double *s0, double *t0, double *R1, double *s1, double *t1,
+                                  double *score, unsigned char *inliers0, unsigned char *inliers1, int *status, void *stream)
+{
+    if (n0 < 1 || n1 < 1 || !source0 || !target0 || !source1 || !target1 || !joint_direction_host || !workspace || !R0 || !s0 ||
+        !t0 || !R1 || !s1 || !t1 || !inliers0 || !inliers1 || !status)
+        return ANCSH_ERR_INVALID_ARG;
+    const int n = n0 + n1;
+    DatasetLayout L;
+    ancsh_pose_ws_t pw;
+    int rc = dataset_layout(n, 2, 1, niter, &L, &pw);
+    if (rc) return rc;
+    if (workspace_bytes < L.total) return ANCSH_ERR_WORKSPACE;
+    char *ws = (char *)workspace;
+    cudaStream_t st = (cudaStream_t)stream;
+    ransac_dataset_kernel<<<ancsh_cdiv(n, 256), 256, 0, st>>>(n0, n1, source0, target0, source1, target1, joint_direction_host[0],
+                                                              joint_direction_host[1], joint_direction_host[2], (float *)(ws + L.P),
+                                                              (float *)(ws + L.nocs), (float *)(ws + L.mask), (float *)(ws + L.axis),
+                                                              (int *)(ws + L.jcls));
+    ANCSH_CHECK_LAUNCH();
+    ancsh_pose_cfg_t cfg{2, 1, niter, inlier_th, seed};
+    ancsh_pose_in_t in{};
+    in.P = (float *)(ws + L.P); in.nocs = (float *)(ws + L.nocs); in.mask = (float *)(ws + L.mask);
+    in.joint_axis = (float *)(ws + L.axis); in.joint_cls = (int *)(ws + L.jcls);
+    in.idx_joint0 = sample_idx0; in.idx_joint1 = sample_idx1;
+    ancsh_pose_out_t out{};
+    char *o = ws + L.out;
+    // single-part outputs of the two parts (one hypothesis each) go to scratch
+    out.single_R = (double *)(o + 256); out.single_s = (double *)(o + 512); out.single_t = (double *)(o + 640);
+    out.single_score = (int *)(o + 768); out.single_inliers = (unsigned char *)(o + 4096);
+    out.part_count = (int *)(o + 64);
+    out.joint_R0 = R0; out.joint_s0 = s0; out.joint_t0 = t0; out.joint_R1 = R1; out.joint_s1 = s1; out.joint_t1 = t1;
+    out.joint_score = score ? score : (double *)(o + 896);
+    out.joint_inliers0 = inliers0; out.joint_inliers1 = inliers1; out.status = status;
+    return ancsh_pose_solve(&cfg, &in, 1, n, ws + L.pose_ws, pw.total_bytes, &out, nullptr, stream);
+}
+
 extern "C" int ancsh_pose_sample_indices(unsigned long long seed, int stream_id, int nprob, int niter,
                                          const int *n_per_problem, int *idx, void *stream)
 {

@@ -38,6 +38,28 @@ def record_width(K):
     return K * 13 + (K - 1) * 27
 
 
+def records_from_arrays(h, K, k_max=None):
+    """The rows pack_records builds, straight from a batch's pose arrays (ancsh_pose_out_t fields as host ndarrays, e.g. one
+    entry of AncshPipeline.run_many(..., unpack=False)) without a Python loop over clouds.  With k_max the rows get the
+    stream layout of stream.record_matrix: [K, record zero-padded to the width of k_max parts]."""
+    B = h["single_s"].shape[0]
+    parts = np.concatenate([h["single_R"].reshape(B, K, 9), h["single_s"].reshape(B, K, 1), h["single_t"].reshape(B, K, 3)], 2)
+    cols = [parts.reshape(B, K * 13)]
+    if K > 1:
+        J = K - 1
+        joints = np.concatenate([h["joint_R0"].reshape(B, J, 9), h["joint_s0"].reshape(B, J, 1), h["joint_t0"].reshape(B, J, 3),
+                                 h["joint_R1"].reshape(B, J, 9), h["joint_s1"].reshape(B, J, 1), h["joint_t1"].reshape(B, J, 3),
+                                 h["joint_score"].reshape(B, J, 1)], 2)
+        cols.append(joints.reshape(B, J * 27))
+    rec = np.concatenate(cols, 1).astype(np.float64)
+    if k_max is None:
+        return rec
+    out = np.zeros((B, 1 + record_width(k_max)), np.float64)
+    out[:, 0] = K
+    out[:, 1:1 + rec.shape[1]] = rec
+    return out
+
+
 def gather_records(local, device=None):
     """All-gather the per-rank record matrices (ragged: the contiguous slices differ in length) into the full matrix in
     rank (= cloud) order on every rank.  One small all-gather of the row counts, one of the padded records."""

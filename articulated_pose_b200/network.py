@@ -44,12 +44,15 @@ _WS_VIEWS = {  # name -> (dtype, shape builder)
 
 class AncshNet:
     def __init__(self, weights, n_parts, mixed_pred=True, early_split_nocs=True, nsample=64, npoint1=512, npoint2=128,
-                 radius1=0.2, radius2=0.4, device="cuda:0", prefix="SPFN", precision="f16x3"):
+                 radius1=0.2, radius2=0.4, device="cuda:0", prefix="SPFN", precision="f16x3", packer="python"):
         """weights: dict TF-variable-name -> ndarray (see weights.variable_shapes).
         ANCSH (exp 3.9): mixed_pred=True, early_split_nocs=True (main.py:42-49);
         NPCS baseline (exp 3.91): mixed_pred=False, early_split_nocs=False.
         precision: "f16x3" = grouped MLPs on the tcgen05 tensor cores with the fp16 hi/lo split (3 products, f32-class accuracy,
-        default); "f32" = exact f32 FMA kernels on the CUDA cores."""
+        default); "f32" = exact f32 FMA kernels on the CUDA cores.  The f16x3 path needs |activation| < 65504 (larger
+        values are clipped, csrc/tc_common.cuh); weights of any magnitude are handled by per-layer power-of-two scales.
+        packer: "python" = weights.py builds the device buffers; "c" = the library's own import (ancsh_weights_pack +
+        ancsh_net_create, what a non-Python host uses) -- same buffers bit for bit (tests/test_weights_c_cpu.py)."""
         if precision not in ("f16x3", "f32"):
             raise ValueError("precision must be 'f16x3' or 'f32'")
         self.precision = precision
@@ -60,6 +63,16 @@ class AncshNet:
         self.npoint1, self.npoint2 = int(npoint1), int(npoint2)
         self.nsample1 = self.nsample2 = int(nsample)
         self.layers = pack_network(weights, n_parts, mixed_pred, early_split_nocs, prefix)
+        self._c_handles = None
+        if packer == "c":
+            if (npoint1, npoint2, float(radius1), float(radius2)) != (512, 128, 0.2, 0.4):
+                raise ValueError("the C packer builds the reference's level settings only")
+            flatten_tc_images(self.layers)                      # sets tc_exp on the metadata copies
+            self._net = self._create_in_c(weights, early_split_nocs, prefix, int(nsample), precision == "f16x3")
+            self._ws, self._host, self.last_workspace = {}, {}, None
+            return
+        if packer != "python":
+            raise ValueError("packer must be 'python' or 'c'")
         flat, offs = flatten_packed(self.layers)
         self._wbuf = torch.from_numpy(flat).to(self.device)
         base = self._wbuf.data_ptr()
@@ -92,6 +105,30 @@ class AncshNet:
         self._ws = {}       # (B,N) -> (workspace tensor, layout)
         self._host = {}     # (B,N) -> pinned staging buffers
         self.last_workspace = None
+
+    def _create_in_c(self, weights, early_split_nocs, prefix, nsample, use_tc):
+        names = list(weights)
+        arrs = [np.ascontiguousarray(weights[k], np.float32) for k in names]
+        n = len(names)
+        c_names = (ctypes.c_char_p * n)(*[k.encode() for k in names])
+        c_data = (ctypes.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        c_cnt = (ctypes.c_size_t * n)(*[a.size for a in arrs])
+        packed, handle = ctypes.c_void_p(), ctypes.c_void_p()
+        _lib.check(_lib.ancsh_weights_pack(n, c_names, c_data, c_cnt, self.n_parts, int(self.mixed_pred), int(early_split_nocs),
+                                           prefix.encode(), ctypes.byref(packed)), "ancsh_weights_pack")
+        try:
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.ancsh_net_create(packed, nsample, int(use_tc), ctypes.byref(handle)), "ancsh_net_create")
+        finally:
+            _lib.ancsh_packed_destroy(packed)
+        self._c_handles = handle
+        return ctypes.cast(_lib.ancsh_net_get(handle), ctypes.POINTER(_lib.Net)).contents
+
+    def __del__(self):
+        h = getattr(self, "_c_handles", None)
+        if h:
+            _lib.ancsh_net_destroy(h)
+            self._c_handles = None
 
     # ------------------------------------------------------------------------------------------
     def plan(self, B, N):

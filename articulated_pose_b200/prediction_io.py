@@ -1,11 +1,12 @@
 """Per-cloud prediction files: the hand-off between the network half and the pose half of the hot path.
 
 Mirror of lib/prediction_io.py:65-95 (`save_batch_nn`): same function name, argument order, dataset names, shapes and
-dtypes, one file per cloud named `<basename>.h5`.  The reference writes HDF5 through h5py; h5py is not part of this
-image, so the writer uses it when it is importable and otherwise writes `<basename>.npz` with the SAME dataset names
-(attributes are stored as `attrs/<name>` entries).  `load_prediction` reads whichever exists and returns a mapping
-that indexes like the reference's `h5py.File` (`f['nocs_per_point'][idx, 3*j:3*(j+1)]`,
-evaluation/parallel_ancsh_pose.py:224-260).
+dtypes, one HDF5 file per cloud named `<basename>.h5`.  The reference writes through h5py; where h5py is importable it
+is used, otherwise (this image) the files are written by `minih5` -- real HDF5 (superblock v2, contiguous datasets in
+the root group), which the unmodified evaluation scripts open with `h5py.File`.  `load_prediction` reads them back
+(h5py, else minih5) and returns a mapping that indexes like the reference's `h5py.File`
+(`f['nocs_per_point'][idx, 3*j:3*(j+1)]`, evaluation/parallel_ancsh_pose.py:224-260); `.npz` files of earlier versions
+of this package are still readable.
 
 `PredictionStore` is the in-memory version of the same hand-off: `save_batch_nn(..., save_dir=store)`
 keeps the per-cloud dicts in RAM so the pose stage can consume them without touching the disk.  The fully fused path
@@ -14,6 +15,8 @@ keeps the per-cloud dicts in RAM so the pose stage can consume them without touc
 import os
 
 import numpy as np
+
+from . import minih5
 
 try:  # pragma: no cover - h5py is absent in the build image
     import h5py
@@ -67,7 +70,7 @@ def _records(nn_name, pred_result, input_batch, basename_list, is_mixed, W_reduc
 
 def save_batch_nn(nn_name, pred_result, input_batch, basename_list, save_dir, sample_index=None, is_mixed=False,
                   W_reduced=True, two_stages=False):
-    """lib/prediction_io.py:65-95.  `save_dir`: directory (h5 if h5py is importable, else npz) or a PredictionStore."""
+    """lib/prediction_io.py:65-95.  `save_dir`: directory (one `<basename>.h5` per cloud) or a PredictionStore."""
     for base, attrs, d in _records(nn_name, pred_result, input_batch, basename_list, is_mixed, W_reduced, two_stages):
         if isinstance(save_dir, PredictionStore):
             save_dir[base] = dict({k: np.asarray(v) for k, v in d.items()}, attrs=attrs)
@@ -78,7 +81,7 @@ def save_batch_nn(nn_name, pred_result, input_batch, basename_list, save_dir, sa
                 for k, v in d.items():
                     f.create_dataset(k, data=v)
         else:
-            np.savez(os.path.join(save_dir, base + ".npz"), **d, **{"attrs/" + k: np.asarray(v) for k, v in attrs.items()})
+            minih5.write(os.path.join(save_dir, base + ".h5"), d, attrs)
 
 
 def load_prediction(save_dir, basename):
@@ -87,8 +90,11 @@ def load_prediction(save_dir, basename):
     if isinstance(save_dir, PredictionStore):
         return _ArrayFile(save_dir[basename])
     h5 = os.path.join(save_dir, basename + ".h5")
-    if h5py is not None and os.path.exists(h5):
-        return h5py.File(h5, "r")
+    if os.path.exists(h5):
+        if h5py is not None:
+            return h5py.File(h5, "r")
+        d, attrs = minih5.read(h5)
+        return _ArrayFile(dict(d, attrs=attrs))
     z = np.load(os.path.join(save_dir, basename + ".npz"))
     d = {k: z[k] for k in z.files if not k.startswith("attrs/")}
     d["attrs"] = {k[6:]: z[k].item() for k in z.files if k.startswith("attrs/")}

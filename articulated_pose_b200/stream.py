@@ -40,43 +40,62 @@ def record_matrix(results, parts, k_max):
 
 
 class MixedStream:
-    """pipelines: {category: AncshPipeline}; `load(category, payload)` -> (P (N,3) float32, joint_cls (N,) int32)."""
+    """pipelines: {category: AncshPipeline}; `load(category, payload)` -> (P (N,3) float32, joint_cls (N,) int32), or
+    `load_batch(category, [payloads])` -> (P (n,N,3), joint_cls (n,N)) when the caller can fetch a whole batch at once."""
 
-    def __init__(self, pipelines, load, batch=256, rank=0, world=1, pad=True):
-        self.pipelines, self.load = pipelines, load
+    def __init__(self, pipelines, load=None, batch=256, rank=0, world=1, pad=True, load_batch=None):
+        if load is None and load_batch is None:
+            raise ValueError("MixedStream needs load or load_batch")
+        self.pipelines, self.load, self.load_batch = pipelines, load, load_batch
         self.batch, self.rank, self.world, self.pad = int(batch), int(rank), int(world), bool(pad)
 
     def my_slice(self, n_items):
         return adist.shard_range(n_items, self.rank, self.world)
 
-    def run(self, items, unpack=True):
+    def _load_chunk(self, cat, payloads):
+        if self.load_batch is not None:
+            P, jc = self.load_batch(cat, payloads)
+            P, jc = np.asarray(P, np.float32), np.asarray(jc, np.int32)
+        else:
+            loaded = [self.load(cat, p) for p in payloads]
+            P = np.stack([l[0] for l in loaded]).astype(np.float32)
+            jc = np.stack([l[1] for l in loaded]).astype(np.int32)
+        # a ragged last batch is padded with copies of its last cloud (results dropped by the caller): every launch of a
+        # category then has ONE shape, so the pipelined path never allocates pinned / device buffers mid-stream
+        pad = self.batch - P.shape[0] if self.pad else 0
+        if pad > 0:
+            P = np.concatenate([P, np.repeat(P[-1:], pad, 0)])
+            jc = np.concatenate([jc, np.repeat(jc[-1:], pad, 0)])
+        return P, jc
+
+    def run(self, items, unpack=True, records_k_max=None):
         """items: the WHOLE stream [(category, payload)] (the same list on every rank).  Returns (start, end, results):
-        this rank's slice bounds and its per-cloud results in stream order."""
+        this rank's slice bounds and its per-cloud results in stream order -- result dicts (unpack=True: pose.unpack_results
+        entries, else per-cloud slices of the pose arrays), or, with records_k_max, ONE float64 matrix (n, 1 + width(k_max))
+        of gather-ready records (dist.records_from_arrays) built without any per-cloud Python work."""
         s, e = self.my_slice(len(items))
         mine = list(items[s:e])
+        as_records = records_k_max is not None
         results = [None] * len(mine)
+        rec = np.zeros((len(mine), 1 + adist.record_width(records_k_max)), np.float64) if as_records else None
         for cat, positions in bucket_by_category(mine).items():
             pipe = self.pipelines[cat]
-            work = []
-            for chunk in batches(positions, self.batch):
-                loaded = [self.load(cat, mine[p][1]) for p in chunk]
-                # a ragged last batch is padded with copies of its last cloud (results dropped below): every launch of
-                # a category then has ONE shape, so the pipelined path never allocates pinned / device buffers mid-stream
-                loaded += [loaded[-1]] * (self.batch - len(loaded) if self.pad else 0)
-                work.append((np.stack([l[0] for l in loaded]).astype(np.float32),
-                             np.stack([l[1] for l in loaded]).astype(np.int32)))
+            chunks = batches(positions, self.batch)
+            work = [self._load_chunk(cat, [mine[p][1] for p in chunk]) for chunk in chunks]
             full = [w for w in work if w[0].shape[0] == work[0][0].shape[0]]
-            outs = pipe.run_many(full, unpack=unpack)
+            outs = pipe.run_many(full, unpack=unpack and not as_records)
             for w in work[len(full):]:
-                outs += pipe.run_many([w], unpack=unpack)
-            for chunk, out in zip(batches(positions, self.batch), outs):
-                if unpack:
+                outs += pipe.run_many([w], unpack=unpack and not as_records)
+            for chunk, out in zip(chunks, outs):
+                if as_records:
+                    rec[np.asarray(chunk)] = adist.records_from_arrays(out, pipe.K, records_k_max)[:len(chunk)]
+                elif unpack:
                     for p, r in zip(chunk, out):
                         results[p] = r
                 else:
                     for i, p in enumerate(chunk):
                         results[p] = {k: v[i] for k, v in out.items()}
-        return s, e, results
+        return s, e, (rec if as_records else results)
 
     def gather(self, results, parts, k_max, device=None):
         """The path's single collective: every rank's records -> the full (n_clouds, 1 + width(k_max)) matrix."""

@@ -302,22 +302,22 @@ def run_mixed(args, rank, local_rank, world):
         w_a, w_n = synthetic_weight_sets(K, args, feats, category=cat)
         pipes[cat] = AncshPipeline(w_a, K, weights_npcs=w_n, nsample=args.nsample, niter_single=args.hyp,
                                    niter_joint=args.joint_hyp, seed=1234 + rank, device=dev, precision=args.precision)
-        pool[cat] = [synthetic.make_cloud(i, cat) for i in range(args.unique)]
+        cl = [synthetic.make_cloud(i, cat) for i in range(args.unique)]
+        pool[cat] = (np.stack([c["P"] for c in cl]).astype(np.float32), np.stack([c["joint_cls_gt"] for c in cl]).astype(np.int32))
     items = synthetic.mixed_stream(args.clouds)
     steps = max(1, args.steps)
     seg = [(len(items) * k // steps, len(items) * (k + 1) // steps) for k in range(steps)]
 
-    def load(cat, cid):
-        c = pool[cat][cid % args.unique]
-        return c["P"], c["joint_cls_gt"]
-    ms = stream.MixedStream(pipes, load, batch=args.batch, rank=rank, world=world)
+    def load_batch(cat, cids):
+        ids = np.asarray(cids) % args.unique
+        return pool[cat][0][ids], pool[cat][1][ids]
+    ms = stream.MixedStream(pipes, load_batch=load_batch, batch=args.batch, rank=rank, world=world)
     k_max = max(synthetic.n_parts(c) for c in synthetic.ALL_CATEGORIES)
 
     def one_step(part):
-        s, e, res = ms.run(part, unpack=True)
-        parts = [synthetic.n_parts(c) for c, _ in part[s:e]]
+        s, e, rec = ms.run(part, records_k_max=k_max)          # gather-ready records, no per-cloud Python work
         t1 = time.perf_counter()
-        full = ms.gather(res, parts, k_max, device=dev)
+        full = adist.gather_records(rec, device=dev)
         torch.cuda.synchronize()
         return int(full.shape[0]), int(full.shape[1]), time.perf_counter() - t1
 

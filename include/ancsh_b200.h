@@ -133,6 +133,35 @@ typedef struct {
                                     with these values in the kernel parameter (constant) bank */
 } ancsh_net_t;
 
+/* ---- weight import in C: TF1 checkpoint variables -> ancsh_net_t ---------------------------------------------
+ * The import contract is the checkpoint's variable names: `<prefix>/est_net/layer{1,2,3}/conv{0,1,2}`,
+ * `<prefix>/est_net/fa_layer{1,2,3}/conv_{i}`, `<prefix>/est_net/fc1`, `<prefix>/nocs_net/{fc11_1,fc2_i}`,
+ * `<prefix>/joint_net/{fc3_0,fc3_1,fc4_i}` (pointnet_util.py:128,234, architectures.py:65-90, lib/architecture.py:105-120,
+ * 195-208), each with `/weights`, `/biases` (tf_util.py:164,174) and, where the layer has batch norm,
+ * `/bn/{beta,gamma,moving_mean,moving_variance}` (tf_util.py:527-531).  articulated_pose_b200/weights.py is the Python
+ * mirror of the same steps (BN fold in f64, [xyz, features] -> [features, xyz] row permutation, fa_layer1 split, head
+ * packing incl. the fc11_1 fold, padding, tensor-core images). */
+typedef struct ancsh_packed ancsh_packed_t;         /* host-side packed network (owns its buffers) */
+typedef struct ancsh_net_handle ancsh_net_handle_t; /* device-resident network (owns the device buffers of its ancsh_net_t) */
+
+/* names[i] / data_host[i] / counts[i]: variable name, HOST f32 values, element count.  prefix NULL = "SPFN".
+ * ANCSH_ERR_INVALID_ARG: a variable is missing or has the wrong size; ANCSH_ERR_UNSUPPORTED: non-finite values. */
+int ancsh_weights_pack(int n_vars, const char *const *names, const float *const *data_host, const size_t *counts, int n_parts,
+                       int mixed_pred, int early_split_nocs, const char *prefix, ancsh_packed_t **out);
+void ancsh_packed_destroy(ancsh_packed_t *p);
+/* Introspection (host): the f32 buffer of all padded W / b, the fp16 buffer of all tensor-core images, and per slot
+ * ("sa1[0]" ... "joint_heads", the field names of ancsh_net_t) the element offsets into them, dims5 = {cin, cout, cin_pad,
+ * cout_pad, relu} and the image's power-of-two scale exponent.  tc_off = (size_t)-1: the slot has no image. */
+const float *ancsh_packed_flat(const ancsh_packed_t *p, size_t *count);
+const unsigned short *ancsh_packed_tc(const ancsh_packed_t *p, size_t *count);
+int ancsh_packed_layer(const ancsh_packed_t *p, const char *slot, size_t *w_off, size_t *b_off, size_t *tc_off, int *dims5,
+                       int *tc_exp);
+/* Uploads the packed buffers to the current device (cudaMalloc + synchronous copies) and fills an ancsh_net_t with the
+ * reference's level settings (npoint 512 / 128, radius 0.2 / 0.4, architectures.py:62-70) and nsample. */
+int ancsh_net_create(const ancsh_packed_t *p, int nsample, int use_tensor_cores, ancsh_net_handle_t **out);
+const ancsh_net_t *ancsh_net_get(const ancsh_net_handle_t *h);
+void ancsh_net_destroy(ancsh_net_handle_t *h);
+
 /* Output tensors of pred_dict (architecture.py:141-159), each (B,N,width) f32 dense.  gocs_per_point,
  * global_scale, global_translation are written only when mixed_pred (may be NULL otherwise). */
 typedef struct {
@@ -281,6 +310,26 @@ enum {
 /* Solves B clouds.  N <= 4096, K <= 8.  stage_events: NULL or ANCSH_POSE_NSTAGES+1 events (see ancsh_net_forward). */
 int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in_t *in, int B, int N, void *workspace,
                      size_t workspace_bytes, const ancsh_pose_out_t *out, void *const *stage_events, void *stream);
+
+/* ransac(dataset, estimator, verifier, inlier_th, niter) of evaluation/parallel_ancsh_pose.py:20 on a caller dataset, for
+ * hosts without the Python mirror (pose.ransac_single / ransac_joint do the same through ancsh_pose_solve).
+ * source / target: (n,3) f32 DEVICE arrays (dataset['source'], dataset['target']); sample_idx: NULL (Philox, `seed`) or
+ * DEVICE (niter,3) int32 sample positions (the reference draws np.random.randint(nsource, size=3), :38).
+ * Results (DEVICE): best_model = {R (9, row-major), scale, t (3)} refitted on the winner's inliers, score = its inlier count
+ * (may be NULL), inliers (n) bytes, status (1 int: ANCSH_POSE_* bits).  workspace: ancsh_ransac_workspace_bytes(n, 1, niter). */
+int ancsh_ransac_workspace_bytes(int n_total, int n_parts, int niter, size_t *bytes);
+int ancsh_ransac_single(int n, const float *source, const float *target, double inlier_th, int niter, const int *sample_idx,
+                        unsigned long long seed, void *workspace, size_t workspace_bytes, double *R, double *scale, double *t,
+                        int *score, unsigned char *inliers, int *status, void *stream);
+/* Joint variant (joint_transformation_estimator / _verifier, :106-194): dataset = {source0, target0, source1, target1,
+ * joint_direction (3 HOST doubles)} -> rotation0/scale0/translation0/rotation1/... (:177-184), score (may be NULL),
+ * inliers0 (n0) / inliers1 (n1) bytes, status (2 ints; entry 1 reports the joint).
+ * workspace: ancsh_ransac_workspace_bytes(n0 + n1, 2, niter). */
+int ancsh_ransac_joint(int n0, const float *source0, const float *target0, int n1, const float *source1, const float *target1,
+                       const double *joint_direction_host, double inlier_th, int niter, const int *sample_idx0,
+                       const int *sample_idx1, unsigned long long seed, void *workspace, size_t workspace_bytes, double *R0,
+                       double *s0, double *t0, double *R1, double *s1, double *t1, double *score, unsigned char *inliers0,
+                       unsigned char *inliers1, int *status, void *stream);
 
 /* Writes the sample positions the Philox generator produces for (seed, problem, hypothesis) so that a CPU
  * checker can replay them: idx (nprob,niter,3); n_per_problem (nprob) is the part size each problem samples

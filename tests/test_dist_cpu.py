@@ -62,3 +62,24 @@ def test_gather_records_world2_gloo():
     assert ref.shape == (n_total, adist.record_width(K))
     for rank, s, e, full in got:
         np.testing.assert_array_equal(full, ref)
+
+
+def test_records_from_arrays_equals_pack_records():
+    """The vectorised record builder of the mixed stream equals the per-cloud packer (same column order) and the padded
+    stream layout of stream.record_matrix."""
+    import numpy as np
+    from articulated_pose_b200 import dist as adist, stream
+    from articulated_pose_b200.pose import unpack_results
+    rng = np.random.default_rng(3)
+    for K in (2, 3, 4):
+        B, N, J = 5, 16, K - 1
+        h = {"single_R": rng.normal(size=(B, K, 3, 3)), "single_s": rng.normal(size=(B, K)), "single_t": rng.normal(size=(B, K, 3)),
+             "single_score": rng.integers(0, 9, size=(B, K)).astype(np.int32), "single_inliers": np.zeros((B, K, N), np.uint8),
+             "joint_R0": rng.normal(size=(B, J, 3, 3)), "joint_s0": rng.normal(size=(B, J)), "joint_t0": rng.normal(size=(B, J, 3)),
+             "joint_R1": rng.normal(size=(B, J, 3, 3)), "joint_s1": rng.normal(size=(B, J)), "joint_t1": rng.normal(size=(B, J, 3)),
+             "joint_score": rng.normal(size=(B, J)), "joint_inliers0": np.zeros((B, J, N), np.uint8),
+             "joint_inliers1": np.zeros((B, J, N), np.uint8), "part_count": np.full((B, K), 4, np.int32),
+             "status": np.zeros((B, K), np.int32)}
+        res = unpack_results(h, K)
+        np.testing.assert_array_equal(adist.records_from_arrays(h, K), adist.pack_records(res, K))
+        np.testing.assert_array_equal(adist.records_from_arrays(h, K, 4), stream.record_matrix(res, [K] * B, 4))

@@ -182,3 +182,20 @@ def test_fp16_split_survives_wide_dynamic_range():
         assert e_tc <= 1e-3 and e_tc <= 16 * e_32 + 1e-5, (k, e_tc, e_32)
         if k in ("W", "nocs_per_point", "confi_per_point", "heatmap_per_point", "index_per_point", "global_scale"):
             assert e_tc <= RTOL, (k, e_tc)
+
+
+def test_c_packed_network_equals_python_packed():
+    """ancsh_weights_pack + ancsh_net_create (the C-side import a non-Python host uses) give the same forward as the
+    Python-packed network, bit for bit except the nocs head (its fc11_1 fold sums in another order: 1e-6)."""
+    from articulated_pose_b200 import synthetic, weights
+    from articulated_pose_b200.network import AncshNet
+    P, _ = synthetic.make_batch(range(70, 73))
+    w = weights.synthetic_weights(3, True, True, seed=7)
+    a = AncshNet(w, 3, nsample=32).forward(P)
+    b = AncshNet(w, 3, nsample=32, packer="c").forward(P)
+    for k in a:
+        if k in ("joint_axis_per_point", "unitvec_per_point", "heatmap_per_point", "index_per_point", "W", "confi_per_point",
+                 "global_scale", "global_translation"):
+            np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+        else:
+            np.testing.assert_allclose(a[k], b[k], rtol=0, atol=2e-6, err_msg=k)

@@ -225,3 +225,69 @@ def test_reference_default_hypothesis_counts_match_oracle():
         np.testing.assert_array_equal(res["inliers_joint"][j - 1][1], ref["inliers_joint"][j - 1][1])
         for f in ("rotation0", "scale0", "translation0", "rotation1", "scale1", "translation1"):
             assert close(res["nonlinear"][j - 1][f], ref["nonlinear"][j - 1][f]), (j, f)
+
+
+def test_c_ransac_entries_equal_the_python_wrappers():
+    """ancsh_ransac_single / ancsh_ransac_joint (the ransac() entry points for non-Python hosts) against
+    pose.ransac_single / ransac_joint on the same datasets and explicit samples: identical results."""
+    import ctypes
+    import torch
+    from articulated_pose_b200 import _lib, synthetic
+    from articulated_pose_b200 import pose as gp
+    cloud = synthetic.make_cloud(5, "eyeglasses")
+    pred = synthetic.teacher_predictions(cloud)
+    cls = np.argmax(pred["W"], 1)
+    p0, p1 = np.where(cls == 0)[0], np.where(cls == 1)[0]
+    s0, t0 = pred["nocs_per_point"][p0, 0:3].astype(np.float32), cloud["P"][p0].astype(np.float32)
+    s1, t1 = pred["nocs_per_point"][p1, 3:6].astype(np.float32), cloud["P"][p1].astype(np.float32)
+    rng = np.random.default_rng(8)
+    dev = torch.device("cuda:0")
+    d = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dt)).to(dev)
+    st = torch.cuda.current_stream().cuda_stream
+    # ---- single ----
+    ns = 64
+    idx = rng.integers(0, len(p0), size=(ns, 3)).astype(np.int32)
+    m_py, inl_py = gp.ransac_single({"source": s0, "target": t0, "nsource": len(p0)}, 0.1, ns, sample_idx=idx)
+    nb = ctypes.c_size_t()
+    assert _lib.ancsh_ransac_workspace_bytes(len(p0), 1, ns, ctypes.byref(nb)) == 0
+    ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+    R, sc, t = (torch.zeros(n, dtype=torch.float64, device=dev) for n in (9, 1, 3))
+    score, status = torch.zeros(1, dtype=torch.int32, device=dev), torch.zeros(1, dtype=torch.int32, device=dev)
+    inl = torch.zeros(len(p0), dtype=torch.uint8, device=dev)
+    ds, dt_, di = d(s0, np.float32), d(t0, np.float32), d(idx, np.int32)
+    _lib.check(_lib.ancsh_ransac_single(len(p0), ds.data_ptr(), dt_.data_ptr(), 0.1, ns, di.data_ptr(), 0, ws.data_ptr(), nb.value,
+                                        R.data_ptr(), sc.data_ptr(), t.data_ptr(), score.data_ptr(), inl.data_ptr(),
+                                        status.data_ptr(), st), "ancsh_ransac_single")
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(R.cpu().numpy().reshape(3, 3), m_py["rotation"])
+    assert float(sc.cpu()[0]) == m_py["scale"] and int(status.cpu()[0]) == 0
+    np.testing.assert_array_equal(t.cpu().numpy(), m_py["translation"])
+    np.testing.assert_array_equal(inl.cpu().numpy().astype(bool), inl_py)
+    assert int(score.cpu()[0]) > 0
+    # ---- joint ----
+    nj = 24
+    i0 = rng.integers(0, len(p0), size=(nj, 3)).astype(np.int32)
+    i1 = rng.integers(0, len(p1), size=(nj, 3)).astype(np.int32)
+    axis = np.median(pred["joint_axis_per_point"][cloud["joint_cls_gt"] == 1].astype(np.float64), 0)
+    m_py, inl_py = gp.ransac_joint({"source0": s0, "target0": t0, "nsource0": len(p0), "source1": s1, "target1": t1,
+                                    "nsource1": len(p1), "joint_direction": axis}, 0.1, nj, sample_idx0=i0, sample_idx1=i1)
+    assert _lib.ancsh_ransac_workspace_bytes(len(p0) + len(p1), 2, nj, ctypes.byref(nb)) == 0
+    ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+    o = {k: torch.zeros(n, dtype=torch.float64, device=dev) for k, n in (("R0", 9), ("s0", 1), ("t0", 3), ("R1", 9), ("s1", 1), ("t1", 3), ("score", 1))}
+    in0, in1 = torch.zeros(len(p0), dtype=torch.uint8, device=dev), torch.zeros(len(p1), dtype=torch.uint8, device=dev)
+    status = torch.zeros(2, dtype=torch.int32, device=dev)
+    ds1, dt1, di0, di1 = d(s1, np.float32), d(t1, np.float32), d(i0, np.int32), d(i1, np.int32)
+    # the Python wrapper rounds the direction to f32 (it travels as a per-point f32 tensor); so does the C entry
+    ax = (ctypes.c_double * 3)(*axis.astype(np.float32).astype(np.float64))
+    _lib.check(_lib.ancsh_ransac_joint(len(p0), ds.data_ptr(), dt_.data_ptr(), len(p1), ds1.data_ptr(), dt1.data_ptr(), ax, 0.1, nj,
+                                       di0.data_ptr(), di1.data_ptr(), 0, ws.data_ptr(), nb.value, o["R0"].data_ptr(),
+                                       o["s0"].data_ptr(), o["t0"].data_ptr(), o["R1"].data_ptr(), o["s1"].data_ptr(),
+                                       o["t1"].data_ptr(), o["score"].data_ptr(), in0.data_ptr(), in1.data_ptr(),
+                                       status.data_ptr(), st), "ancsh_ransac_joint")
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(o["R0"].cpu().numpy().reshape(3, 3), m_py["rotation0"])
+    np.testing.assert_array_equal(o["R1"].cpu().numpy().reshape(3, 3), m_py["rotation1"])
+    np.testing.assert_array_equal(o["t1"].cpu().numpy(), m_py["translation1"])
+    assert float(o["s0"].cpu()[0]) == m_py["scale0"] and float(o["score"].cpu()[0]) == m_py["score"]
+    np.testing.assert_array_equal(in0.cpu().numpy().astype(bool), inl_py[0])
+    np.testing.assert_array_equal(in1.cpu().numpy().astype(bool), inl_py[1])
