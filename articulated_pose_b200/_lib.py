@@ -93,6 +93,21 @@ ancsh_ransac_single = _sig("ancsh_ransac_single", [c_int, vp, vp, ctypes.c_doubl
 ancsh_ransac_joint = _sig("ancsh_ransac_joint", [c_int, vp, vp, c_int, vp, vp, ctypes.POINTER(ctypes.c_double), ctypes.c_double,
                                                  c_int, vp, vp, ctypes.c_ulonglong, vp, c_size_t, vp, vp, vp, vp, vp, vp, vp, vp,
                                                  vp, vp, vp])
+UNIT_IN_FIELDS = ("pts", "cls", "heatmap", "unitvec", "orient", "joint_cls", "nocs_p", "nocs_g")
+UNIT_OUT_FIELDS = ("P", "cls_gt", "mask_array", "nocs_gt", "nocs_gt_g", "heatmap_gt", "unitvec_gt", "orient_gt", "joint_cls_gt",
+                   "joint_cls_mask")
+
+
+class UnitIn(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_void_p) for k in UNIT_IN_FIELDS]
+
+
+class UnitOut(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_void_p) for k in UNIT_OUT_FIELDS]
+
+
+ancsh_unit_data = _sig("ancsh_unit_data", [c_int, c_int, c_int, c_int, vp, vp, vp, vp, ctypes.POINTER(UnitIn),
+                                           ctypes.POINTER(UnitOut), vp])
 ancsh_fps = _sig("ancsh_fps", [c_int, c_int, c_int, vp, vp, vp, vp])
 ancsh_fps_two_level = _sig("ancsh_fps_two_level", [c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp])
 ancsh_gather_point = _sig("ancsh_gather_point", [c_int, c_int, c_int, vp, vp, vp, vp])

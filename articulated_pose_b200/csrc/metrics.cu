@@ -240,6 +240,60 @@ __global__ void __launch_bounds__(MT) joint_vote_kernel(const VoteArgs a)
     }
 }
 
+// ---- create_unit_data_from_hdf5's sampling / normalisation (lib/dataset.py:290-317, 346-372) -----------------------------------
+// one thread per output point: gathers every per-point array through perm (positions in the cloud tiled up to at least
+// num_points entries, dataset.py:290-317, i.e. index modulo n_total), scales the coordinates by the cloud's norm factor
+// (:351), builds the one-hot part mask (:360) and the joint mask (:356-358); `rot` = the sapien joint_rpy rotation applied
+// about 0.5 to the NOCS arrays and to the joint vectors (:369-377, f64 like np.dot with the f64 euler matrix).
+struct UnitArgs {
+    int n_max, num_points, K;
+    const int *n_total, *perm;
+    const float *norm;
+    const double *rot;
+    ancsh_unit_in_t in;
+    ancsh_unit_out_t out;
+};
+
+__device__ __forceinline__ void rot3(const double *R, const float *v, float shift, float *o)
+{
+    // np.dot(v - shift, R.T) + shift
+    const double a = (double)(v[0] - shift), b = (double)(v[1] - shift), c = (double)(v[2] - shift);
+    for (int i = 0; i < 3; ++i) o[i] = (float)(a * R[3 * i] + b * R[3 * i + 1] + c * R[3 * i + 2] + (double)shift);
+}
+
+__global__ void __launch_bounds__(256) unit_data_kernel(const UnitArgs a)
+{
+    const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.num_points) return;
+    const int nt = a.n_total[b];
+    const int src = nt > 0 ? a.perm[(size_t)b * a.num_points + i] % nt : 0;
+    const size_t s = (size_t)b * a.n_max + src, d = (size_t)b * a.num_points + i;
+    const double *R = a.rot ? a.rot + (size_t)b * 9 : nullptr;
+    const float nf = a.norm[b];
+    for (int c = 0; c < 3; ++c) a.out.P[d * 3 + c] = __fmul_rn(a.in.pts[s * 3 + c], nf);
+    const float cls = a.in.cls[s];
+    a.out.cls_gt[d] = cls;
+    if (a.out.mask_array) {
+        const int k = (int)(signed char)(int)cls;                                   // cls_arr.astype(np.int8), :360
+        for (int j = 0; j < a.K; ++j) a.out.mask_array[d * a.K + j] = (j == (k < 0 ? k + a.K : k)) ? 1.f : 0.f;
+    }
+    auto vec3 = [&](const float *in, float *out, float shift, bool rotate) {
+        if (!in || !out) return;
+        if (rotate && R) rot3(R, in + s * 3, shift, out + d * 3);
+        else for (int c = 0; c < 3; ++c) out[d * 3 + c] = in[s * 3 + c];
+    };
+    vec3(a.in.nocs_p, a.out.nocs_gt, 0.5f, true);
+    vec3(a.in.nocs_g, a.out.nocs_gt_g, 0.5f, true);
+    vec3(a.in.unitvec, a.out.unitvec_gt, 0.f, true);
+    vec3(a.in.orient, a.out.orient_gt, 0.f, true);
+    if (a.in.heatmap && a.out.heatmap_gt) a.out.heatmap_gt[d] = a.in.heatmap[s];
+    if (a.in.joint_cls) {
+        const float jc = a.in.joint_cls[s];
+        if (a.out.joint_cls_gt) a.out.joint_cls_gt[d] = jc;
+        if (a.out.joint_cls_mask) a.out.joint_cls_mask[d] = jc > 0.f ? 1.f : 0.f;
+    }
+}
+
 }  // namespace
 
 extern "C" int ancsh_amodal_extent(int B, int N, int K, const float *nocs, const float *mask, float *extent, int *count,
@@ -279,6 +333,20 @@ extern "C" int ancsh_joint_vote(int B, int N, int K, int gn_width, int n_index, 
     ANCSH_CUDA(cudaFuncSetAttribute(joint_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VoteArgs a{N, K, gn_width, n_index, gocs, mask, unitvec, heatmap, joint_axis, index_per_point, thres_r, axis_out, pt_out, count};
     joint_vote_kernel<<<B, MT, smem, (cudaStream_t)stream>>>(a);
+    ANCSH_CHECK_LAUNCH();
+    return ANCSH_OK;
+}
+
+extern "C" int ancsh_unit_data(int B, int n_max, int num_points, int n_parts, const int *n_total, const int *perm,
+                               const float *norm_factor, const double *rot, const ancsh_unit_in_t *in, const ancsh_unit_out_t *out,
+                               void *stream)
+{
+    if (B < 0 || n_max <= 0 || num_points <= 0 || n_parts < 1 || n_parts > 127 || !in || !out) return ANCSH_ERR_INVALID_ARG;
+    if (B == 0) return ANCSH_OK;
+    if (B > 65535) return ANCSH_ERR_UNSUPPORTED;
+    if (!n_total || !perm || !norm_factor || !in->pts || !in->cls || !out->P || !out->cls_gt) return ANCSH_ERR_INVALID_ARG;
+    UnitArgs a{n_max, num_points, n_parts, n_total, perm, norm_factor, rot, *in, *out};
+    unit_data_kernel<<<dim3(ancsh_cdiv(num_points, 256), B), 256, 0, (cudaStream_t)stream>>>(a);
     ANCSH_CHECK_LAUNCH();
     return ANCSH_OK;
 }

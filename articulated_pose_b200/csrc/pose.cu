@@ -1407,7 +1407,7 @@ int dataset_layout(int n, int K, int niter_single, int niter_joint, DatasetLayou
     auto take = [&](size_t bytes) { size_t o = off; off = align256(off + bytes); return o; };
     L->P = take((size_t)n * 3 * 4); L->nocs = take((size_t)n * 3 * K * 4); L->mask = take((size_t)n * K * 4);
     L->axis = take((size_t)n * 3 * 4); L->jcls = take((size_t)n * 4);
-    L->out = take(4096 + (size_t)3 * n);                 // scratch for the outputs the caller did not ask for
+    L->out = take(4096 + (size_t)4 * n);                 // scratch: outputs the caller did not ask for, N-strided inlier rows
     L->pose_ws = take(pw->total_bytes);
     L->total = off;
     return ANCSH_OK;
@@ -1487,8 +1487,14 @@ extern "C" int ancsh_ransac_joint(int n0, const float *source0, const float *tar
     out.part_count = (int *)(o + 64);
     out.joint_R0 = R0; out.joint_s0 = s0; out.joint_t0 = t0; out.joint_R1 = R1; out.joint_s1 = s1; out.joint_t1 = t1;
     out.joint_score = score ? score : (double *)(o + 896);
-    out.joint_inliers0 = inliers0; out.joint_inliers1 = inliers1; out.status = status;
-    return ancsh_pose_solve(&cfg, &in, 1, n, ws + L.pose_ws, pw.total_bytes, &out, nullptr, stream);
+    // the solver writes inlier rows of the cloud's length N = n0 + n1: scratch rows, then the leading n0 / n1 entries
+    unsigned char *row0 = (unsigned char *)(o + 4096 + (size_t)2 * n), *row1 = row0 + n;
+    out.joint_inliers0 = row0; out.joint_inliers1 = row1; out.status = status;
+    rc = ancsh_pose_solve(&cfg, &in, 1, n, ws + L.pose_ws, pw.total_bytes, &out, nullptr, stream);
+    if (rc) return rc;
+    ANCSH_CUDA(cudaMemcpyAsync(inliers0, row0, (size_t)n0, cudaMemcpyDeviceToDevice, st));
+    ANCSH_CUDA(cudaMemcpyAsync(inliers1, row1, (size_t)n1, cudaMemcpyDeviceToDevice, st));
+    return ANCSH_OK;
 }
 
 extern "C" int ancsh_pose_sample_indices(unsigned long long seed, int stream_id, int nprob, int niter,

@@ -383,6 +383,32 @@ int ancsh_joint_vote(int B, int N, int K, int gn_width, int n_index, const float
                      const float *unitvec, const float *heatmap, const float *joint_axis, const float *index_per_point,
                      float thres_r, float *axis_out, float *pt_out, int *count, void *stream);
 
+/* Sampling / normalisation of create_unit_data_from_hdf5 (lib/dataset.py:290-317, 346-372), the step in
+ * front of the network: per cloud b, output point i takes source point perm[b,i] % n_total[b] (the reference tiles clouds
+ * with fewer than num_points points, :290-317, and draws perm = np.random.permutation(n_total)[:num_points], :346 -- here
+ * the caller passes perm, like the RANSAC samples), P = pts * norm_factor[b] (:351), cls_gt, the one-hot mask_array (:360),
+ * joint_cls_mask = joint_cls > 0 (:356-358) and the gathered GT arrays.  rot: NULL, or (B,9) row-major f64 rotation of the
+ * sapien branch (:369-377): NOCS arrays are rotated about 0.5, unitvec / orient about 0.
+ * Inputs (B,n_max,width) f32, outputs (B,num_points,width) f32; optional arrays may be NULL on either side. */
+typedef struct {
+    const float *pts;       /* (B,n_max,3) required */
+    const float *cls;       /* (B,n_max)   required: part label per point */
+    const float *heatmap;   /* (B,n_max)   */
+    const float *unitvec;   /* (B,n_max,3) */
+    const float *orient;    /* (B,n_max,3) joint orientation per point */
+    const float *joint_cls; /* (B,n_max)   */
+    const float *nocs_p;    /* (B,n_max,3) part NOCS */
+    const float *nocs_g;    /* (B,n_max,3) global NOCS */
+} ancsh_unit_in_t;
+typedef struct {
+    float *P, *cls_gt;      /* (B,num_points,3), (B,num_points) required */
+    float *mask_array;      /* (B,num_points,n_parts) */
+    float *nocs_gt, *nocs_gt_g, *heatmap_gt, *unitvec_gt, *orient_gt, *joint_cls_gt, *joint_cls_mask;
+} ancsh_unit_out_t;
+int ancsh_unit_data(int B, int n_max, int num_points, int n_parts, const int *n_total, const int *perm,
+                    const float *norm_factor, const double *rot, const ancsh_unit_in_t *in, const ancsh_unit_out_t *out,
+                    void *stream);
+
 #ifdef __cplusplus
 }
 #endif
