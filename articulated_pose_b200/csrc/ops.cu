@@ -252,7 +252,8 @@ __global__ void __launch_bounds__(256) three_nn_kernel(int n, int m, const float
                                                        const float *__restrict__ xyz2, float *__restrict__ dist,
                                                        int *__restrict__ idx, float *__restrict__ weight)
 {
-    __shared__ float s_k[512 * 3];
+    // known points as float4 (x, y, z, pad): one 16-byte broadcast load per candidate
+    __shared__ float4 s_k[512];
     const int b = blockIdx.y;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const float *q = xyz1 + ((size_t)b * n + (j < n ? j : 0)) * 3;
@@ -262,10 +263,31 @@ __global__ void __launch_bounds__(256) three_nn_kernel(int n, int m, const float
     for (int base = 0; base < m; base += 512) {
         int cnt = min(512, m - base);
         __syncthreads();
-        for (int i = threadIdx.x; i < cnt * 3; i += blockDim.x) s_k[i] = xyz2[((size_t)b * m + base) * 3 + i];
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+            const float *p = xyz2 + ((size_t)b * m + base + i) * 3;
+            s_k[i] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+        }
         __syncthreads();
-        for (int k = 0; k < cnt; ++k)
-            best.insert(nn_dist_unfused(s_k[k * 3], s_k[k * 3 + 1], s_k[k * 3 + 2], x1, y1, z1), base + k);
+        // The strict '<' insertion chain of tf_interpolate.cpp:74-89 only acts when d < d3: one compare rejects almost
+        // every candidate once three near ones are known.  Four distances per trip are independent (ILP); the insertions
+        // stay in index order.
+        int k = 0;
+        for (; k + 4 <= cnt; k += 4) {
+            float d[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 p = s_k[k + u];
+                d[u] = nn_dist_unfused(p.x, p.y, p.z, x1, y1, z1);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (d[u] < best.d3) best.insert(d[u], base + k + u);
+        }
+        for (; k < cnt; ++k) {
+            const float4 p = s_k[k];
+            const float d = nn_dist_unfused(p.x, p.y, p.z, x1, y1, z1);
+            if (d < best.d3) best.insert(d, base + k);
+        }
     }
     if (j < n) {
         size_t o = ((size_t)b * n + j) * 3;

@@ -20,7 +20,7 @@
 namespace {
 
 constexpr int RT = 256;   // threads of the cooperative kernels
-constexpr int RJ = 128;   // threads of joint_refit_kernel: ~240 registers (LM control code) -> two blocks per SM
+constexpr int RJ = 128;   // threads of joint_refit_kernel: ~240 registers (LM control code) -> two blocks per SM (64 threads x 4 blocks: same 1.1 ms -- the serial LM control of warp 0 bounds it)
 
 // ------------------------------------------------------------------------------------------------
 // block reduction of NV doubles per thread (fixed order -> deterministic); result broadcast to all threads.
@@ -587,8 +587,13 @@ __global__ void __launch_bounds__(LMT, LM_BLOCKS_PER_SM) joint_lm_kernel(const J
                     const JointRec &r = recs[mine];
                     if (r.valid) {
                         t = mine;
-#pragma unroll 4
-                        for (int e = 0; e < 36; ++e) my[e * LMT] = r.pts[e];
+                        // all 36 coordinates in flight at once (18 x 16-byte loads): a claim used to pay 9 dependent L2 / DRAM
+                        // round trips here -- 12 % of the kernel's stall samples (profiles/r02_joint_lm_sass_stalls.txt)
+                        double2 pv[18];
+#pragma unroll
+                        for (int e = 0; e < 18; ++e) pv[e] = __ldg(reinterpret_cast<const double2 *>(r.pts) + e);
+#pragma unroll
+                        for (int e = 0; e < 18; ++e) { my[(2 * e) * LMT] = pv[e].x; my[(2 * e + 1) * LMT] = pv[e].y; }
                         const double *u = a.axis_med + (size_t)(mine / a.niter) * 3;
                         my[36 * LMT] = u[0]; my[37 * LMT] = u[1]; my[38 * LMT] = u[2];
                         pm::lm_tick_init(s, r.x, r.fnorm);
