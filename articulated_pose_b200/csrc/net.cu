@@ -652,7 +652,11 @@ static int net_forward_impl(const ancsh_net_t *net, int B, int N, const float *P
             c.S[3].out = pred->net; c.S[3].ldo = net->fc1.cout;                       // optional copy of the trunk feature
             c.S[4].dst = TC_DST_GLOBAL; c.S[4].act = TC_ACT_NOCS_HEADS;               // nocs_net heads (operand `net` kept)
             c.S[7].dst = TC_DST_GLOBAL; c.S[7].act = TC_ACT_JOINT_HEADS;              // joint_net heads
-            c.nsteps = 8;
+            // the joint branch (fc3_0, fc3_1, joint heads: 3 of the 8 layers) is skipped when none of its four outputs is
+            // requested -- e.g. the NPCS-baseline network of the pipeline, whose pose stage reads W and NOCS only
+            const bool want_joint = pred->joint_axis_per_point || pred->unitvec_per_point || pred->heatmap_per_point ||
+                                    pred->index_per_point;
+            c.nsteps = want_joint ? 8 : 5;
             if ((rc = chain_tc2_launch(c, (long)B * N, st))) return rc;
         } else if ((rc = fp_launch<128, true>(a, B, st))) return rc;
     }

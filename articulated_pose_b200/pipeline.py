@@ -16,7 +16,9 @@ from .pose import PoseSolver, unpack_results
 
 
 class AncshPipeline:
-    N_SLOTS = int(__import__('os').environ.get('ANCSH_SLOTS', '4'))      # batches in flight in submit()/run_many(): pose tails of several batches overlap later forwards
+    # batches in flight in submit()/run_many(): the pose tails of several batches overlap later forwards.  Measured on B200
+    # (256 clouds per batch): 4 slots 27.7k clouds/s, 6 slots 28.4k, 8 slots 28.5k
+    N_SLOTS = int(__import__('os').environ.get('ANCSH_SLOTS', '6'))
 
     def __init__(self, weights_ancsh, n_parts, weights_npcs=None, use_baseline=True, nsample=64, niter_single=10000,
                  niter_joint=200, inlier_th=0.1, seed=0, device="cuda:0", precision="f16x3"):
@@ -43,10 +45,16 @@ class AncshPipeline:
                  "hP": torch.empty((B, N, 3), dtype=torch.float32).pin_memory(),
                  "hjc": torch.empty((B, N), dtype=torch.int32).pin_memory()}
             if self.net_npcs is not None:
-                d["pred_b"] = self.net_npcs.alloc_outputs(B, N)
+                d["pred_b"] = self._npcs_outputs(B, N)
             d["hpose"] = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in d["pose"].items()}
             self._buf[key] = d
         return self._buf[key]
+
+    def _npcs_outputs(self, B, N):
+        """The pose stage reads only the segmentation and the NOCS of the baseline network (parallel_ancsh_pose.py:232-236):
+        its joint branch is not requested, so the forward skips it (csrc/net.cu)."""
+        full = self.net_npcs.alloc_outputs(B, N)
+        return {k: full[k] for k in ("W", "nocs_per_point", "confi_per_point")}
 
     def run_device(self, P, joint_cls, net_events=None, net_b_events=None, pose_events=None, seed=None):
         """P (B,N,3) f32 CUDA, joint_cls (B,N) int32 CUDA -> dict of CUDA pose tensors (ancsh_pose_out_t).
@@ -67,7 +75,7 @@ class AncshPipeline:
             d = {"pred": self.net.alloc_outputs(B, N), "pose": self.pose.alloc_outputs(B, N), "fwd_done": torch.cuda.Event(),
                  "pose_done": torch.cuda.Event(), "used": False}
             if self.net_npcs is not None:
-                d["pred_b"] = self.net_npcs.alloc_outputs(B, N)
+                d["pred_b"] = self._npcs_outputs(B, N)
             self._slots[key] = d
         return self._slots[key]
 

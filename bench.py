@@ -510,21 +510,23 @@ def main():
     # ---- end to end through the public host API (host buffers, H2D + D2H inside the timed region) ----
     host_batches = [(P_host[c], jc_host[c]) for c in range(C)]
 
-    def e2e_step(s):
+    def e2e_steps(first, count):
+        """`count` steps through the host API as ONE stream of device batches (AncshPipeline.run_many keeps the slot pipeline
+        full across step boundaries; every batch is copied H2D from pinned memory and its pose records are copied back)."""
         if full:
-            return pipe.run_many(host_batches, seeds=[seed_of(s, c) for c in range(C)])[-1]
+            seeds = [seed_of(first + s, c) for s in range(count) for c in range(C)]
+            return pipe.run_many(host_batches * count, seeds=seeds)[-1]
         r = None
-        for c in range(C):
-            r = pipe.net.forward(P_host[c], copy=False)
+        for _ in range(count):
+            for c in range(C):
+                r = pipe.net.forward(P_host[c], copy=False)
         return r
-    for s in range(W):   # warm-up of the timed call: run_many pins its staging buffers and creates its copy stream on first use
-        e2e_step(-1 - s)
+    e2e_steps(-W, W)   # warm-up of the timed call: run_many pins its staging buffers and creates its copy stream on first use
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    for s in range(args.steps):
-        r = e2e_step(s)
+    r = e2e_steps(0, args.steps)
     e2e_s = time.perf_counter() - t0
     h2d = C * (P_host[0].nbytes + (jc_host[0].nbytes if full else 0))
     d2h = C * sum(v.nbytes for v in r.values())
