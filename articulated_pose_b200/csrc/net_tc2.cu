@@ -21,7 +21,9 @@
 // Numerics as in net_tc.cu: hi*hi products and the cross terms hi*lo + lo*hi go to separate f32 accumulators (the tensor
 // core accumulates with truncation), long k ranges are split over several hi*hi accumulators, the epilogue adds them in
 // round-to-nearest f32.
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "net_tc.cuh"
@@ -76,6 +78,7 @@ struct Chain2Args {
     int nst;               // ring stages
     int nunits;
     uint32_t tmem_cols;
+    long long *trace;      // profiling aid (ANCSH_CHAIN_TRACE): per-CTA clock64 stamps, or NULL
     Unit U[MAX_UNITS];
 };
 
@@ -89,6 +92,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                  "r"(bytes), "r"(tc::smem_u32(bar))
                  : "memory");
 }
+
+// slot layout of a CTA's trace record: [0] start, [1] operand gathered, [2 + 2u] accumulators of unit u ready (worker warp 0),
+// [3 + 2u] its epilogue done; [40 + 2u] MMA warp starts unit u, [41 + 2u] has committed it
+constexpr int CTRACE_SLOTS = 80;
+#define CHAIN_TRACE(k)                                                                     \
+    do {                                                                                   \
+        if (a.trace && lane == 0) a.trace[(size_t)blockIdx.x * CTRACE_SLOTS + (k)] = clock64(); \
+    } while (0)
 
 // one lane of a converged warp (ptxas then knows that the tcgen05 / bulk-copy operands below are warp-uniform)
 __device__ __forceinline__ bool elect_one()
@@ -359,6 +370,7 @@ __global__ void __launch_bounds__(NTHR, MINB) chain2_kernel(const __grid_constan
         for (int u = 0; u < a.nunits; ++u) {
             const Unit &U = a.U[u];
             const int nk16 = U.K / 16;
+            CHAIN_TRACE(40 + 2 * u);
             const uint32_t idesc = tc::instr_desc_f16(TM, U.nc);
             const uint32_t sslab = 2u * (uint32_t)U.nc * 16u;
             const uint64_t ah0 = tc::smem_desc(a_hi0, 2048u, 128u), al0 = tc::smem_desc(a_lo0, 2048u, 128u);
@@ -391,12 +403,14 @@ __global__ void __launch_bounds__(NTHR, MINB) chain2_kernel(const __grid_constan
             }
             if (elect_one()) tc::mma_commit(bar_acc);         // accumulators of the unit complete
             __syncwarp();
+            CHAIN_TRACE(41 + 2 * u);
             tc::fence_before_sync();
             work_sync();                                      // epilogue done: operand rewritten, TMEM drained
         }
     } else {
         // =========================== workers ===========================
         const int r = tid & (TM - 1), h = tid >> 7, wq = warp & 3;
+        if (warp == 0) CHAIN_TRACE(0);
         long R;                 // global row (rows mode) / row inside the cloud (SA mode)
         int b = 0;
         if (SA) {
@@ -450,94 +464,96 @@ __global__ void __launch_bounds__(NTHR, MINB) chain2_kernel(const __grid_constan
                 }
                 split8(v, reinterpret_cast<uint4 *>(A_hi + (size_t)kc * 2048 + r * 16), reinterpret_cast<uint4 *>(A_lo + (size_t)kc * 2048 + r * 16));
             }
-        } else if (FP) {
-            // ---- (idx, weight) of the tile's rows: three_nn + inverse-distance weights (tf_interpolate.cpp:60-105,
-            // pointnet_util.py:217-222) come from the stage's 24-byte-per-row tables (ops.cu three_nn_kernel; evaluating
-            // them here put a 256-candidate insertion chain in front of every tile: +0.26 ms for fa_layer3) ----
+        } else {
+            // ---- rows mode: [X1 or three_interpolate(points2) (C1) | X2 (C2) | zero pad] (pointnet_util.py:223-228) ----
+            // Load mapping: 8 lanes per row (a 128-byte line per row and instruction), 4 rows per warp instruction; a warp
+            // owns 16 rows.  (One thread per row -- the store-friendly mapping -- touches 32 cache lines per load
+            // instruction: the L1 tag stage then bounds the gather, measured 38.8k of fa_layer3's 122.8k cycles per tile,
+            // and it slows the co-resident CTA's epilogues down as well.)  Lane (g, j) of the warp holds channels
+            // [32 i + 4 j, +4) of row 16 warp + 4 grp + g and stores them as 8-byte halves of the 16-byte operand pieces.
             const long row0 = (long)blockIdx.x * TM;
             const long cloud = row0 / a.rows_per_cloud;
-            for (int i = tid; i < TM * 3; i += NWORK) {
-                s_nni[i] = __ldg(a.fp_idx + (size_t)row0 * 3 + i);
-                s_nnw[i] = __ldg(a.fp_w + (size_t)row0 * 3 + i);
-            }
-            asm volatile("bar.sync 2, %0;" ::"n"(NWORK) : "memory");
-            // ---- rows: [three_interpolate(points2) (C1) | X2 (C2) | zero pad] (pointnet_util.py:223-228) ----
             R = row0 + r;
-            const float w1 = s_nnw[r * 3], w2 = s_nnw[r * 3 + 1], w3 = s_nnw[r * 3 + 2];
-            const float *p1 = a.fp_points2 + ((size_t)cloud * a.fp_m2 + s_nni[r * 3 + 0]) * a.C1;
-            const float *p2 = a.fp_points2 + ((size_t)cloud * a.fp_m2 + s_nni[r * 3 + 1]) * a.C1;
-            const float *p3 = a.fp_points2 + ((size_t)cloud * a.fp_m2 + s_nni[r * 3 + 2]) * a.C1;
-            const float *r2 = a.X2 ? a.X2 + (size_t)R * a.C2 : nullptr;
-            const int nkc1 = a.C1 / 8;                                // C1 % 8 == 0 (launcher)
-            for (int kc = h; kc < nkc1; kc += 4) {                    // two 8-channel pieces per trip: 12 loads in flight
-                const int kb = kc + 2;
-                float4 u[4], v[4], w[4];
-                u[0] = ldg4(p1 + kc * 8); u[1] = ldg4(p1 + kc * 8 + 4);
-                v[0] = ldg4(p2 + kc * 8); v[1] = ldg4(p2 + kc * 8 + 4);
-                w[0] = ldg4(p3 + kc * 8); w[1] = ldg4(p3 + kc * 8 + 4);
-                if (kb < nkc1) {
-                    u[2] = ldg4(p1 + kb * 8); u[3] = ldg4(p1 + kb * 8 + 4);
-                    v[2] = ldg4(p2 + kb * 8); v[3] = ldg4(p2 + kb * 8 + 4);
-                    w[2] = ldg4(p3 + kb * 8); w[3] = ldg4(p3 + kb * 8 + 4);
+            if (FP) {
+                // (idx, weight) of the tile's rows from the stage's three_nn table (ops.cu three_nn_kernel)
+                for (int i = tid; i < TM * 3; i += NWORK) {
+                    s_nni[i] = __ldg(a.fp_idx + (size_t)row0 * 3 + i);
+                    s_nnw[i] = __ldg(a.fp_w + (size_t)row0 * 3 + i);
                 }
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    const int kk = kc + 2 * t;
-                    if (kk >= nkc1) break;
-                    float x[8];
-                    x[0] = interp3_unfused(u[2 * t].x, v[2 * t].x, w[2 * t].x, w1, w2, w3);
-                    x[1] = interp3_unfused(u[2 * t].y, v[2 * t].y, w[2 * t].y, w1, w2, w3);
-                    x[2] = interp3_unfused(u[2 * t].z, v[2 * t].z, w[2 * t].z, w1, w2, w3);
-                    x[3] = interp3_unfused(u[2 * t].w, v[2 * t].w, w[2 * t].w, w1, w2, w3);
-                    x[4] = interp3_unfused(u[2 * t + 1].x, v[2 * t + 1].x, w[2 * t + 1].x, w1, w2, w3);
-                    x[5] = interp3_unfused(u[2 * t + 1].y, v[2 * t + 1].y, w[2 * t + 1].y, w1, w2, w3);
-                    x[6] = interp3_unfused(u[2 * t + 1].z, v[2 * t + 1].z, w[2 * t + 1].z, w1, w2, w3);
-                    x[7] = interp3_unfused(u[2 * t + 1].w, v[2 * t + 1].w, w[2 * t + 1].w, w1, w2, w3);
-                    split8(x, reinterpret_cast<uint4 *>(A_hi + (size_t)kk * 2048 + r * 16), reinterpret_cast<uint4 *>(A_lo + (size_t)kk * 2048 + r * 16));
-                }
+                asm volatile("bar.sync 2, %0;" ::"n"(NWORK) : "memory");
             }
-            for (int kc = nkc1 + h; kc < a.K0 / 8; kc += 2) {        // skip features and the zero padding
-                float x[8];
-                if (r2 && (a.C2 & 7) == 0 && kc * 8 + 8 <= a.C1 + a.C2) {
-                    const float4 q0 = ldg4(r2 + (kc * 8 - a.C1)), q1 = ldg4(r2 + (kc * 8 - a.C1) + 4);
-                    x[0] = q0.x; x[1] = q0.y; x[2] = q0.z; x[3] = q0.w; x[4] = q1.x; x[5] = q1.y; x[6] = q1.z; x[7] = q1.w;
+            const int g = lane >> 3, j = lane & 7;
+            const int nseg = (a.K0 + 31) / 32;
+            const bool x2vec = a.X2 && (a.C2 & 3) == 0 && (a.C1 & 3) == 0;
+            for (int grp = 0; grp < 4; ++grp) {
+                const int rr = warp * 16 + grp * 4 + g;                  // row of the tile this lane works on
+                const long Rr = row0 + rr;
+                const float *p1, *p2 = nullptr, *p3 = nullptr;
+                float w1 = 0.f, w2 = 0.f, w3 = 0.f;
+                if (FP) {
+                    w1 = s_nnw[rr * 3]; w2 = s_nnw[rr * 3 + 1]; w3 = s_nnw[rr * 3 + 2];
+                    p1 = a.fp_points2 + ((size_t)cloud * a.fp_m2 + s_nni[rr * 3 + 0]) * a.C1;
+                    p2 = a.fp_points2 + ((size_t)cloud * a.fp_m2 + s_nni[rr * 3 + 1]) * a.C1;
+                    p3 = a.fp_points2 + ((size_t)cloud * a.fp_m2 + s_nni[rr * 3 + 2]) * a.C1;
                 } else {
+                    p1 = a.X1 + (size_t)Rr * a.C1;
+                }
+                const float *q2 = a.X2 ? a.X2 + (size_t)Rr * a.C2 : nullptr;
+                for (int s0 = 0; s0 < nseg; s0 += 4) {                    // 4 segments (128 channels) per trip: up to 12 loads in flight
+                    float4 u[4], v[4], w[4];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int c = kc * 8 + i;
-                        x[i] = (r2 && c < a.C1 + a.C2) ? __ldg(r2 + (c - a.C1)) : 0.f;
+                    for (int t = 0; t < 4; ++t) {
+                        const int c = (s0 + t) * 32 + 4 * j;
+                        if (s0 + t < nseg && c + 4 <= a.C1) {
+                            u[t] = ldg4(p1 + c);
+                            if (FP) { v[t] = ldg4(p2 + c); w[t] = ldg4(p3 + c); }
+                        } else if (s0 + t < nseg && x2vec && c >= a.C1 && c + 4 <= a.C1 + a.C2) {
+                            u[t] = ldg4(q2 + (c - a.C1));
+                        }
+                    }
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int c = (s0 + t) * 32 + 4 * j;
+                        if (s0 + t >= nseg || c >= a.K0) continue;
+                        float x[4];
+                        if (c + 4 <= a.C1) {
+                            if (FP) {
+                                x[0] = interp3_unfused(u[t].x, v[t].x, w[t].x, w1, w2, w3);
+                                x[1] = interp3_unfused(u[t].y, v[t].y, w[t].y, w1, w2, w3);
+                                x[2] = interp3_unfused(u[t].z, v[t].z, w[t].z, w1, w2, w3);
+                                x[3] = interp3_unfused(u[t].w, v[t].w, w[t].w, w1, w2, w3);
+                            } else {
+                                x[0] = u[t].x; x[1] = u[t].y; x[2] = u[t].z; x[3] = u[t].w;
+                            }
+                        } else if (x2vec && c >= a.C1 && c + 4 <= a.C1 + a.C2) {
+                            x[0] = u[t].x; x[1] = u[t].y; x[2] = u[t].z; x[3] = u[t].w;
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int ce = c + e;
+                                x[e] = ce < a.C1 ? (FP ? 0.f : __ldg(p1 + ce)) : (q2 && ce < a.C1 + a.C2 ? __ldg(q2 + (ce - a.C1)) : 0.f);
+                            }
+                        }
+                        // 4 channels -> 8-byte halves of the hi and lo pieces (same split as split8)
+                        const __half2 h0 = __floats2half2_rn(x[0], x[1]), h1 = __floats2half2_rn(x[2], x[3]);
+                        const float2 b0 = __half22float2(h0), b1 = __half22float2(h1);
+                        const __half2 l0 = __floats2half2_rn((x[0] - b0.x) * tc::LO_SCALE, (x[1] - b0.y) * tc::LO_SCALE);
+                        const __half2 l1 = __floats2half2_rn((x[2] - b1.x) * tc::LO_SCALE, (x[3] - b1.y) * tc::LO_SCALE);
+                        const size_t off = (size_t)(c >> 3) * 2048 + rr * 16 + (j & 1) * 8;
+                        *reinterpret_cast<uint2 *>(A_hi + off) = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+                        *reinterpret_cast<uint2 *>(A_lo + off) = make_uint2(*reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
                     }
                 }
-                split8(x, reinterpret_cast<uint4 *>(A_hi + (size_t)kc * 2048 + r * 16), reinterpret_cast<uint4 *>(A_lo + (size_t)kc * 2048 + r * 16));
-            }
-        } else {
-            R = (long)blockIdx.x * TM + r;
-            const float *r1 = a.X1 + (size_t)R * a.C1;
-            const float *r2 = a.X2 ? a.X2 + (size_t)R * a.C2 : nullptr;
-            for (int kc = h; kc < a.K0 / 8; kc += 2) {
-                float v[8];
-                if (kc * 8 + 8 <= a.C1) {
-                    const float4 p0 = ldg4(r1 + kc * 8), p1 = ldg4(r1 + kc * 8 + 4);
-                    v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
-                } else if (r2 && (a.C2 & 7) == 0 && (a.C1 & 7) == 0 && kc * 8 >= a.C1 && kc * 8 + 8 <= a.C1 + a.C2) {
-                    const float4 p0 = ldg4(r2 + (kc * 8 - a.C1)), p1 = ldg4(r2 + (kc * 8 - a.C1) + 4);
-                    v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int c = kc * 8 + i;
-                        v[i] = c < a.C1 ? __ldg(r1 + c) : (r2 && c < a.C1 + a.C2 ? __ldg(r2 + (c - a.C1)) : 0.f);
-                    }
-                }
-                split8(v, reinterpret_cast<uint4 *>(A_hi + (size_t)kc * 2048 + r * 16), reinterpret_cast<uint4 *>(A_lo + (size_t)kc * 2048 + r * 16));
             }
         }
         tc::fence_proxy_async();
+        if (warp == 0) CHAIN_TRACE(1);
         work_sync();                                          // operand of unit 0 gathered
         const uint32_t trow = tmem + ((uint32_t)(wq * 32) << 16);
         for (int u = 0; u < a.nunits; ++u) {
             const Unit &U = a.U[u];
             tc::mbar_wait(bar_acc, (uint32_t)(u & 1));
+            if (warp == 0) CHAIN_TRACE(2 + 2 * u);
             tc::fence_after_sync();
             const float *bias = U.bias_stride ? U.bias + (size_t)(R / a.rows_per_cloud) * U.bias_stride : U.bias;
             const int groups = U.nc / CW;                     // CW-column groups per chunk
@@ -579,6 +595,7 @@ __global__ void __launch_bounds__(NTHR, MINB) chain2_kernel(const __grid_constan
             }
             tc::fence_proxy_async();
             tc::fence_before_sync();
+            if (warp == 0) CHAIN_TRACE(3 + 2 * u);
             work_sync();
         }
         if (warp == 0) tc::tmem_dealloc(tmem, a.tmem_cols);
@@ -754,10 +771,43 @@ int chain_tc2_launch(const ChainTcArgs &c, long rows_total, cudaStream_t st)
     int minb = 2;
     int rc = build_units(a, spec, c.nsteps, &smem, &minb);
     if (rc) return rc;
+    // profiling aid: ANCSH_CHAIN_TRACE=<file prefix> dumps the phase time stamps of the 12th .. 15th chain launch
+    static const char *trace_path = getenv("ANCSH_CHAIN_TRACE");
+    static int trace_calls = 0;
+    const unsigned nblk = (unsigned)(rows_total / TM);
+    long long *trace_dev = nullptr;
+    int trace_id = -1;
+    if (trace_path && ++trace_calls >= 12 && trace_calls < 16) {
+        trace_id = trace_calls;
+        if (cudaMalloc(&trace_dev, (size_t)nblk * CTRACE_SLOTS * sizeof(long long)) != cudaSuccess) trace_dev = nullptr;
+        else cudaMemsetAsync(trace_dev, 0, (size_t)nblk * CTRACE_SLOTS * sizeof(long long), st);
+    }
+    a.trace = trace_dev;
+    auto dump = [&]() {
+        if (!trace_dev) return;
+        std::vector<long long> hbuf((size_t)nblk * CTRACE_SLOTS);
+        cudaStreamSynchronize(st);
+        cudaMemcpy(hbuf.data(), trace_dev, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        cudaFree(trace_dev);
+        char name[512];
+        snprintf(name, sizeof name, "%s_%d.txt", trace_path, trace_id);
+        if (FILE *f = fopen(name, "w")) {
+            fprintf(f, "# chain launch %d: %u CTAs, %d units, fp %d, K0 %d; one line per sampled CTA: %d clock64 stamps\n", trace_id, nblk,
+                    a.nunits, (int)fp, a.K0, CTRACE_SLOTS);
+            for (unsigned c = 0; c < nblk; c += 13) {
+                for (int k = 0; k < CTRACE_SLOTS; ++k) fprintf(f, "%lld ", hbuf[(size_t)c * CTRACE_SLOTS + k]);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    };
     if (fp) {
         if (minb != 2) return ANCSH_ERR_UNSUPPORTED;
-        return launch_chain2<false, 2, true>(a, dim3((unsigned)(rows_total / TM)), smem, st);
+        rc = launch_chain2<false, 2, true>(a, dim3(nblk), smem, st);
+        dump();
+        return rc;
     }
-    if (minb == 3) return launch_chain2<false, 3>(a, dim3((unsigned)(rows_total / TM)), smem, st);
-    return launch_chain2<false, 2>(a, dim3((unsigned)(rows_total / TM)), smem, st);
+    rc = minb == 3 ? launch_chain2<false, 3>(a, dim3(nblk), smem, st) : launch_chain2<false, 2>(a, dim3(nblk), smem, st);
+    dump();
+    return rc;
 }
