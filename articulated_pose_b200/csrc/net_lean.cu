@@ -146,6 +146,21 @@ __device__ __forceinline__ void split8_lean(const float (&v)[8], uint8_t *dst_hi
     *reinterpret_cast<uint4 *>(dst_lo) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// 4 consecutive k of one row -> the 8-byte halves of the hi and lo pieces (no ReLU: gathered inputs)
+__device__ __forceinline__ void split4_lean(const float (&v)[4], uint8_t *dst_hi, uint8_t *dst_lo)
+{
+    uint32_t h[2], l[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float a = v[2 * i], b = v[2 * i + 1];
+        const float ha = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u), hb = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
+        h[i] = pack_f16x2<false>(hb, ha);
+        l[i] = pack_f16x2<false>((b - hb) * tc::LO_SCALE, (a - ha) * tc::LO_SCALE);
+    }
+    *reinterpret_cast<uint2 *>(dst_hi) = make_uint2(h[0], h[1]);
+    *reinterpret_cast<uint2 *>(dst_lo) = make_uint2(l[0], l[1]);
+}
+
 __device__ __forceinline__ float max3(float a, float b, float c)
 {
     float d;
@@ -293,6 +308,7 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
     int *s_cnt = reinterpret_cast<int *>(s_tmem + 4);                         // [2][8] hits found by each ball-query warp
     int *s_idx = s_cnt + 16;                                                  // [2][8 warps][S] ball-query hit lists (double buffered)
     float *s_xyz = reinterpret_cast<float *>(s_idx + 16 * S);                 // [XYZ_MAX][3] the cloud's coordinates (xyz-only stages)
+    int *s_rowid = reinterpret_cast<int *>(s_xyz + P::XYZ_MAX * 3);           // [2][TM] point index of every row of a tile (feature gather)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) tc::tmem_alloc(s_tmem, TMEM_COLS);
@@ -460,41 +476,55 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
         if (BALL) { ball_tile(tile0, 0); gather_sync(); }
         id = fetch_id(tile0, 0);
         load_rel(tile0, id, rel);
+        if (C != 0) {
+            if (h == 0) s_rowid[r] = id;
+            gather_sync();
+        }
         for (int t = 0; t < ntiles; ++t) {
             const int tile = tile0 + t;
             const bool has_next = t + 1 < ntiles;
             const int tb = (warp == 0 ? 0 : 32);                  // trace base (warps 0 and 4 record)
             if (warp == 0 || warp == 4) LEAN_TRACE(tb, 0);
-            if (C == 0) {
+            if constexpr (C == 0) {
                 if (h == 0) conv0_xyz<0>(a, rel, r, A_hi, A_lo);
                 else conv0_xyz<32>(a, rel, r, A_hi, A_lo);
             } else {
-                // channel order [features(C), xyz(3), zero pad] (pointnet_util.py:52-57 with the rows of W permuted)
-                const float *prow = a.points + ((size_t)b * a.n + id) * C;
-                constexpr int HALF = K0 / 16;                     // kc slices per thread
+                // channel order [features(C), xyz(3), zero pad] (pointnet_util.py:52-57 with the rows of W permuted).
+                // Feature rows: 8 lanes per row (one 128-byte line per row and load instruction), 4 rows per warp
+                // instruction, 16 rows per warp -- one thread per row touches 32 lines per instruction and made the gather
+                // 9.5k of the tile's 31k cycles.  Lane (g, j) holds channels [32 i + 4 j, +4) of row 16 warp + 4 grp + g.
+                static_assert(C % 32 == 0 && K0 == C + 16, "feature gather layout");
+                const int *rid = s_rowid + (t & 1) * TM;
+                const int g4 = lane >> 3, j = lane & 7;
 #pragma unroll
-                for (int q0 = 0; q0 < HALF; q0 += 4) {
-                    float4 p[8];
+                for (int grp0 = 0; grp0 < 4; grp0 += 2) {
+                    float4 p[2][C / 32];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int kc = h * HALF + q0 + q;
-                        if (q0 + q < HALF && kc * 8 < C) { p[2 * q] = ldg4(prow + kc * 8); p[2 * q + 1] = ldg4(prow + kc * 8 + 4); }
+                    for (int gi = 0; gi < 2; ++gi) {
+                        const int rr = warp * 16 + (grp0 + gi) * 4 + g4;
+                        const float *prow = a.points + ((size_t)b * a.n + rid[rr]) * C;
+#pragma unroll
+                        for (int i = 0; i < C / 32; ++i) p[gi][i] = ldg4(prow + 32 * i + 4 * j);
                     }
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int kc = h * HALF + q0 + q;
-                        if (q0 + q >= HALF) continue;
-                        float v[8];
-                        if (kc * 8 < C) {
-                            v[0] = p[2 * q].x; v[1] = p[2 * q].y; v[2] = p[2 * q].z; v[3] = p[2 * q].w;
-                            v[4] = p[2 * q + 1].x; v[5] = p[2 * q + 1].y; v[6] = p[2 * q + 1].z; v[7] = p[2 * q + 1].w;
-                        } else {
+                    for (int gi = 0; gi < 2; ++gi) {
+                        const int rr = warp * 16 + (grp0 + gi) * 4 + g4;
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] = 0.f;
-                            if (kc * 8 == C) { v[0] = rel[0]; v[1] = rel[1]; v[2] = rel[2]; }
+                        for (int i = 0; i < C / 32; ++i) {
+                            const float v[4] = {p[gi][i].x, p[gi][i].y, p[gi][i].z, p[gi][i].w};
+                            const size_t off = (size_t)(4 * i + (j >> 1)) * 2048 + rr * 16 + (j & 1) * 8;
+                            split4_lean(v, A_hi + off, A_lo + off);
                         }
-                        split8_lean<false>(v, A_hi + (size_t)kc * 2048 + r * 16, A_lo + (size_t)kc * 2048 + r * 16);
                     }
+                }
+                {
+                    // slab C/8: (rel xyz, 0 ...) by the row's first thread, slab C/8 + 1: zeros by its second
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+                    if (h == 0) { v[0] = rel[0]; v[1] = rel[1]; v[2] = rel[2]; }
+                    const int kc = C / 8 + h;
+                    split8_lean<false>(v, A_hi + (size_t)kc * 2048 + r * 16, A_lo + (size_t)kc * 2048 + r * 16);
                 }
             }
             if (warp == 0 || warp == 4) LEAN_TRACE(tb, 2);
@@ -502,6 +532,16 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
             // ball query of the NEXT tile while the tensor pipe runs this tile's first unit
             if (BALL && has_next) ball_tile(tile + 1, (t + 1) & 1);
             if (warp == 0 || warp == 4) LEAN_TRACE(tb, 3);
+            // index + relative coordinate of this thread's row of the NEXT tile (the loads fly under this tile's units); the
+            // row-index table of the feature gather is published by the ready() arrivals that follow
+            int id_n = 0;
+            float rel_n[3] = {0.f, 0.f, 0.f};
+            if (has_next) {
+                if (BALL) gather_sync();                          // every warp's hit list of the next tile is complete
+                id_n = fetch_id(tile + 1, (t + 1) & 1);
+                load_rel(tile + 1, id_n, rel_n);
+                if (C != 0 && h == 0) s_rowid[((t + 1) & 1) * TM + r] = id_n;
+            }
             // ---- in-place layers ----
             if (NSTD == 2) {
                 tc::mbar_wait(bar_acc, uc & 1u); ++uc;
@@ -518,14 +558,6 @@ __global__ void __launch_bounds__(NTHR, 2) sa_lean_kernel(const __grid_constant_
                 epi_inplace<N1>(trow, h, r, a.descale[1], A_hi, A_lo);
                 if (warp == 0 || warp == 4) LEAN_TRACE(tb, 7);
                 ready();
-            }
-            // index + relative coordinate of this thread's row of the NEXT tile: the loads fly under the pooled units
-            int id_n = 0;
-            float rel_n[3] = {0.f, 0.f, 0.f};
-            if (has_next) {
-                if (BALL) gather_sync();                          // every warp's hit list of the next tile is complete
-                id_n = fetch_id(tile + 1, (t + 1) & 1);
-                load_rel(tile + 1, id_n, rel_n);
             }
             // ---- pooled layer, transposed: lane = output channel ----
 #pragma unroll
@@ -563,7 +595,7 @@ int launch(const SaLeanArgs &a, dim3 grid, cudaStream_t st)
 {
     using P = Plan<C, N0, N1, N2>;
     const size_t smem = (size_t)2 * P::K8 * 2048 + 4096 + (size_t)P::RING_BYTES + (2 * MAX_STAGES + 2) * sizeof(uint64_t) + 16 +
-                        16 * sizeof(int) + 16 * S * sizeof(int) + (size_t)P::XYZ_MAX * 3 * sizeof(float);
+                        16 * sizeof(int) + 16 * S * sizeof(int) + (size_t)P::XYZ_MAX * 3 * sizeof(float) + (C != 0 ? 2 * TM * sizeof(int) : 0);
     auto k = sa_lean_kernel<C, N0, N1, N2, S, BALL>;
     ANCSH_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ANCSH_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
