@@ -212,95 +212,101 @@ __device__ __forceinline__ void pool_store2(float *orow, int S, int lane, const 
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-// Head activations of one row (lib/architecture.py:122-139, 150-157) on a 32-column group of a packed head layer:
+// Head activations of one row (lib/architecture.py:122-139, 150-157) on the first 32 columns of a packed head layer:
 //   nocs_net  [W(K) | nocs(3K) | scale(K) | trans(3K) | confi(1)]  (MIXED)  /  [W(K) | nocs(3K) | confi(1)]
 //   joint_net [joint_axis(3) | unitvec(3) | heatmap(1) | index(3)]
-// c0 = first column held in x (0 or 32); every output pointer may be NULL (not requested).  K and MIXED are compile-time
-// so that every index into x is static (a dynamically indexed x would push the accumulator rows of ALL epilogues of the
-// kernel into local memory: measured 0.61 -> 0.87 ms for fa_layer3 + heads).
+// The row's TWO worker threads (h = 0 / 1) share the transcendental work: parts are dealt out by parity (each part's
+// nocs / scale / trans / gocs are independent of the other parts), the segmentation softmax and the confidence go to the
+// thread with fewer parts.  Every output pointer may be NULL (not requested).  K and MIXED are compile-time so that every
+// index into x is static (a dynamically indexed x would push the accumulator rows of ALL epilogues of the kernel into
+// local memory: measured 0.61 -> 0.87 ms for fa_layer3 + heads).  confi32: the confidence column (only when it is column 32,
+// K = 4 mixed) read from the second column group by thread h = 1.
 template <int K, bool MIXED>
-__device__ __forceinline__ void nocs_head_act(int c0, const float (&x)[32], long r, const ancsh_pred_t &o)
+__device__ __forceinline__ void nocs_head_act(int h, const float (&x)[32], float confi32, long r, const ancsh_pred_t &o)
 {
     constexpr int CONFI = MIXED ? 8 * K : 4 * K;
     static_assert((MIXED ? 8 * K : 4 * K) <= 32, "W | nocs | scale | trans of a row must share one 32-column group");
-    if (c0 == 0) {
+    constexpr int H_EXTRA = (K & 1) ? 1 : 0;                 // thread that also does the softmax (h = 1 has fewer parts when K is odd)
+#pragma unroll
+    for (int p = 0; p < K; ++p) {
+        if ((p & 1) != h) continue;
+        float nocs[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) nocs[c] = sigmoidf_(x[K + 3 * p + c]);
+        if (o.nocs_per_point) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) o.nocs_per_point[(size_t)r * 3 * K + 3 * p + c] = nocs[c];
+        }
+        if (MIXED) {
+            const float sc = sigmoidf_(x[4 * K + p]);
+            float tr[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) tr[c] = tanhf(x[5 * K + 3 * p + c]);
+            if (o.global_scale) o.global_scale[(size_t)r * K + p] = sc;
+            if (o.global_translation) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) o.global_translation[(size_t)r * 3 * K + 3 * p + c] = tr[c];
+            }
+            if (o.gocs_per_point) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) o.gocs_per_point[(size_t)r * 3 * K + 3 * p + c] = __fadd_rn(__fmul_rn(nocs[c], sc), tr[c]);
+            }
+        }
+    }
+    if (h == H_EXTRA && o.W) {
         float e[K], mx = x[0], sum = 0.f;
 #pragma unroll
         for (int k = 1; k < K; ++k) mx = fmaxf(mx, x[k]);
 #pragma unroll
         for (int k = 0; k < K; ++k) { e[k] = expf(x[k] - mx); sum += e[k]; }
-        if (o.W) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) o.W[(size_t)r * K + k] = e[k] / sum;
-        }
-        float nocs[3 * K];
-#pragma unroll
-        for (int k = 0; k < 3 * K; ++k) nocs[k] = sigmoidf_(x[K + k]);
-        if (o.nocs_per_point) {
-#pragma unroll
-            for (int k = 0; k < 3 * K; ++k) o.nocs_per_point[(size_t)r * 3 * K + k] = nocs[k];
-        }
-        if (MIXED) {
-            float sc[K], tr[3 * K];
-#pragma unroll
-            for (int k = 0; k < K; ++k) sc[k] = sigmoidf_(x[4 * K + k]);
-#pragma unroll
-            for (int k = 0; k < 3 * K; ++k) tr[k] = tanhf(x[5 * K + k]);
-            if (o.global_scale) {
-#pragma unroll
-                for (int k = 0; k < K; ++k) o.global_scale[(size_t)r * K + k] = sc[k];
-            }
-            if (o.global_translation) {
-#pragma unroll
-                for (int k = 0; k < 3 * K; ++k) o.global_translation[(size_t)r * 3 * K + k] = tr[k];
-            }
-            if (o.gocs_per_point) {
-#pragma unroll
-                for (int k = 0; k < 3 * K; ++k) o.gocs_per_point[(size_t)r * 3 * K + k] = __fadd_rn(__fmul_rn(nocs[k], sc[k / 3]), tr[k]);
-            }
-        }
+        for (int k = 0; k < K; ++k) o.W[(size_t)r * K + k] = e[k] / sum;
     }
-    if (CONFI >= 32 ? c0 == 32 : c0 == 0) {
-        if (o.confi_per_point) o.confi_per_point[r] = sigmoidf_(x[CONFI & 31]);
+    if (o.confi_per_point) {
+        if (CONFI < 32) { if (h == H_EXTRA) o.confi_per_point[r] = sigmoidf_(x[CONFI & 31]); }
+        else if (h == 1) o.confi_per_point[r] = sigmoidf_(confi32);
     }
 }
 
-__device__ __forceinline__ void joint_head_act(int c0, const float (&x)[32], long r, const ancsh_pred_t &o)
+__device__ __forceinline__ void joint_head_act(int h, const float (&x)[32], long r, const ancsh_pred_t &o)
 {
-    if (c0 != 0) return;
-    if (o.joint_axis_per_point) {
+    if (h == 0) {
+        if (o.joint_axis_per_point) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) o.joint_axis_per_point[(size_t)r * 3 + k] = tanhf(x[k]);
-    }
-    if (o.unitvec_per_point) {
+            for (int k = 0; k < 3; ++k) o.joint_axis_per_point[(size_t)r * 3 + k] = tanhf(x[k]);
+        }
+        if (o.heatmap_per_point) o.heatmap_per_point[r] = sigmoidf_(x[6]);
+    } else {
+        if (o.unitvec_per_point) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) o.unitvec_per_point[(size_t)r * 3 + k] = tanhf(x[3 + k]);
-    }
-    if (o.heatmap_per_point) o.heatmap_per_point[r] = sigmoidf_(x[6]);
-    if (o.index_per_point) {
-        const float m2 = fmaxf(x[7], fmaxf(x[8], x[9]));
-        const float e0 = expf(x[7] - m2), e1 = expf(x[8] - m2), e2 = expf(x[9] - m2), es = e0 + e1 + e2;
-        o.index_per_point[(size_t)r * 3 + 0] = e0 / es;
-        o.index_per_point[(size_t)r * 3 + 1] = e1 / es;
-        o.index_per_point[(size_t)r * 3 + 2] = e2 / es;
+            for (int k = 0; k < 3; ++k) o.unitvec_per_point[(size_t)r * 3 + k] = tanhf(x[3 + k]);
+        }
+        if (o.index_per_point) {
+            const float m2 = fmaxf(x[7], fmaxf(x[8], x[9]));
+            const float e0 = expf(x[7] - m2), e1 = expf(x[8] - m2), e2 = expf(x[9] - m2), es = e0 + e1 + e2;
+            o.index_per_point[(size_t)r * 3 + 0] = e0 / es;
+            o.index_per_point[(size_t)r * 3 + 1] = e1 / es;
+            o.index_per_point[(size_t)r * 3 + 2] = e2 / es;
+        }
     }
 }
 
 // Out of line on purpose: the transcendental-heavy head code must not share the register budget (96) of the epilogue loop.
-__device__ __noinline__ void head_activations(int act, int c0, const float (&x)[32], long r, int K, int mixed, const ancsh_pred_t &o)
+__device__ __noinline__ void head_activations(int act, int h, const float (&x)[32], float confi32, long r, int K, int mixed,
+                                              const ancsh_pred_t &o)
 {
-    if (act == TC_ACT_JOINT_HEADS) { joint_head_act(c0, x, r, o); return; }
+    if (act == TC_ACT_JOINT_HEADS) { joint_head_act(h, x, r, o); return; }
     if (mixed) {
-        if (K == 2) nocs_head_act<2, true>(c0, x, r, o);
-        else if (K == 3) nocs_head_act<3, true>(c0, x, r, o);
-        else nocs_head_act<4, true>(c0, x, r, o);
+        if (K == 2) nocs_head_act<2, true>(h, x, confi32, r, o);
+        else if (K == 3) nocs_head_act<3, true>(h, x, confi32, r, o);
+        else nocs_head_act<4, true>(h, x, confi32, r, o);
     } else {
-        if (K == 2) nocs_head_act<2, false>(c0, x, r, o);
-        else if (K == 3) nocs_head_act<3, false>(c0, x, r, o);
-        else if (K == 4) nocs_head_act<4, false>(c0, x, r, o);
-        else if (K == 5) nocs_head_act<5, false>(c0, x, r, o);
-        else if (K == 6) nocs_head_act<6, false>(c0, x, r, o);
-        else nocs_head_act<7, false>(c0, x, r, o);
+        if (K == 2) nocs_head_act<2, false>(h, x, confi32, r, o);
+        else if (K == 3) nocs_head_act<3, false>(h, x, confi32, r, o);
+        else if (K == 4) nocs_head_act<4, false>(h, x, confi32, r, o);
+        else if (K == 5) nocs_head_act<5, false>(h, x, confi32, r, o);
+        else if (K == 6) nocs_head_act<6, false>(h, x, confi32, r, o);
+        else nocs_head_act<7, false>(h, x, confi32, r, o);
     }
 }
 
@@ -557,6 +563,33 @@ __global__ void __launch_bounds__(NTHR, MINB) chain2_kernel(const __grid_constan
             tc::fence_after_sync();
             const float *bias = U.bias_stride ? U.bias + (size_t)(R / a.rows_per_cloud) * U.bias_stride : U.bias;
             const int groups = U.nc / CW;                     // CW-column groups per chunk
+            if constexpr (FP) {
+                if (U.act) {
+                    // packed head layer (64 columns, one chunk): BOTH threads of the row read the first 32 columns and share
+                    // the activations; the thread of the second half also reads column 32 (the confidence when K = 4, mixed)
+                    float x[32];
+                    load_acc2(trow, U.G, 0, x, U.nc);
+                    const float4 *b4 = reinterpret_cast<const float4 *>(bias + U.n0);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 bb = __ldg(b4 + i);
+                        x[4 * i] = fmaf(x[4 * i], U.descale, bb.x); x[4 * i + 1] = fmaf(x[4 * i + 1], U.descale, bb.y);
+                        x[4 * i + 2] = fmaf(x[4 * i + 2], U.descale, bb.z); x[4 * i + 3] = fmaf(x[4 * i + 3], U.descale, bb.w);
+                    }
+                    float confi32 = 0.f;
+                    if (h == 1 && U.act == TC_ACT_NOCS_HEADS && a.mixed && a.n_parts == 4) {
+                        float y[32];
+                        load_acc2(trow, U.G, 32, y, U.nc);
+                        confi32 = fmaf(y[0], U.descale, __ldg(bias + U.n0 + 32));
+                    }
+                    head_activations(U.act, h, x, confi32, R, a.n_parts, a.mixed, a.pred);
+                    tc::fence_proxy_async();
+                    tc::fence_before_sync();
+                    if (warp == 0) CHAIN_TRACE(3 + 2 * u);
+                    work_sync();
+                    continue;
+                }
+            }
             for (int j = 0; j < U.nchunks; ++j) {
                 for (int q = 0; q < groups; ++q) {
                     if (((j * groups + q) & 1) != h) continue;        // the two halves alternate column groups
@@ -575,14 +608,7 @@ __global__ void __launch_bounds__(NTHR, MINB) chain2_kernel(const __grid_constan
 #pragma unroll
                         for (int i = 0; i < CW; ++i) v[i] = fmaxf(v[i], 0.f);
                     }
-                    if (FP && U.act) {
-                        if constexpr (FP) {
-                            float x[32];                              // a copy: v itself must stay in registers (see nocs_head_act)
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) x[i] = v[i];
-                            head_activations(U.act, col, x, R, a.n_parts, a.mixed, a.pred);
-                        }
-                    } else if (U.pool) {
+                    if (U.pool) {
                         const long g = ((long)blockIdx.x * TM + wq * 32) / a.S;
                         pool_store2<CW>(U.out + ((size_t)b * a.m + g) * U.Nfull + col, a.S, lane, v);
                     } else if (U.out) {
