@@ -547,23 +547,22 @@ static int net_forward_impl(const ancsh_net_t *net, int B, int N, const float *P
         a.L[0] = net->sa3[0]; a.L[1] = net->sa3[1]; a.L[2] = net->sa3[2];
         a.n = m2; a.m = 1; a.S = m2; a.C = net->sa2[2].cout;
         if (net->use_tensor_cores && net->sa3[0].W_tc && net->sa3[2].W_tc) {
-            // group_all over the B*npoint2 rows; conv1's output is the only temporary (workspace slot `interp3`)
-            float *t2 = (float *)(ws + L.interp3);
-            if (m2 % 32 != 0 || net->sa3[2].cout != net->sa3[2].cout_pad) return ANCSH_ERR_UNSUPPORTED;
-            // conv0 (in place) + conv1 -> t2 as one warp-specialised chain: each 128-row CTA converts its operand once
-            // and streams the weights through the TMA ring (the streaming GEMM re-converts the rows for every
-            // 128-column chunk and serialises load / MMA).  conv2 (K = 512: its operand images would need 256 KB of
-            // shared memory) stays a streaming GEMM with the max over the cloud's npoint2 rows in its epilogue.
+            // group_all over the B*npoint2 rows.  conv0 (in place) + conv1 as one warp-specialised chain whose last epilogue
+            // writes conv1's rows directly as the fp16 hi/lo operand image of conv2 (workspace slot `interp3`, 4 bytes per
+            // element like the f32 rows); conv2 (K = 512: a resident operand would need 256 KB of shared memory) streams
+            // image and weights through a TMA ring, with the max over the cloud's npoint2 rows in its epilogue.
+            void *img = ws + L.interp3;
+            if (m2 % 32 != 0 || ((long)B * m2) % 128 != 0 || net->sa3[2].cout != net->sa3[2].cout_pad) return ANCSH_ERR_UNSUPPORTED;
+            if (net->sa3[2].cin_pad != net->sa3[1].cout_pad) return ANCSH_ERR_INVALID_ARG;
             ChainTcArgs c{};
             c.X1 = l2_points; c.C1 = net->sa2[2].cout; c.X2 = l2_xyz; c.C2 = 3; c.rows_per_cloud = m2;
             c.S[0].L = tc_layer(net->sa3[0]); c.S[0].dst = TC_DST_INPLACE;
-            c.S[1].L = tc_layer(net->sa3[1]); c.S[1].dst = TC_DST_GLOBAL; c.S[1].out = t2; c.S[1].ldo = net->sa3[1].cout_pad;
+            c.S[1].L = tc_layer(net->sa3[1]); c.S[1].dst = TC_DST_IMAGE; c.S[1].out = (float *)img;
             c.nsteps = 2;
             if ((rc = chain_tc2_launch(c, (long)B * m2, st))) return rc;
-            GemmTcArgs g{};
-            g.X1 = t2; g.C1 = net->sa3[1].cout_pad; g.X2 = nullptr; g.C2 = 0; g.L = tc_layer(net->sa3[2]);
-            g.out = l3_points; g.ldo = 0; g.pool_S = m2;
-            if ((rc = gemm_tc_launch(g, (long)B * m2, st))) return rc;
+            GemmImgArgs g{};
+            g.Aimg = img; g.L = tc_layer(net->sa3[2]); g.out = l3_points; g.pool_S = m2;
+            if ((rc = gemm_img_launch(g, (long)B * m2, st))) return rc;
         } else if ((rc = sa_launch<64>(a, B, st))) return rc;
     }
     // fa_layer1

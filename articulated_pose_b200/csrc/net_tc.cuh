@@ -41,13 +41,15 @@ struct SaLeanArgs2 {
 int sa_lean_launch(const SaLeanArgs2 &a, int B, cudaStream_t st);
 
 // ---- generic row-tile chain (feature propagation / heads) ------------------------------------------------------
-enum { TC_DST_INPLACE = 0, TC_DST_GLOBAL = 1 };
+enum { TC_DST_INPLACE = 0, TC_DST_GLOBAL = 1, TC_DST_IMAGE = 2 };
 
 enum { TC_ACT_NONE = 0, TC_ACT_NOCS_HEADS = 1, TC_ACT_JOINT_HEADS = 2 };
 
 struct ChainStep {
     TcLayer L;
-    int dst;        // TC_DST_INPLACE: output becomes the next step's operand; TC_DST_GLOBAL: rows go to `out`, operand kept
+    int dst;        // TC_DST_INPLACE: output becomes the next step's operand; TC_DST_GLOBAL: rows go to `out`, operand kept;
+                    // TC_DST_IMAGE: as GLOBAL, but `out` receives the rows as the fp16 hi/lo operand image of a following
+                    // gemm_img_launch (GemmImgArgs::Aimg; rows_total * N * 4 bytes, ldo unused)
     float *out;     // [rows_total][ldo] f32; with TC_DST_INPLACE and out != NULL the rows are written as well
     int ldo;
     int act;        // TC_DST_GLOBAL only: TC_ACT_*_HEADS = the step is a packed head layer; its activations
@@ -89,14 +91,12 @@ __host__ __device__ inline int tc_num_acc(int K, int max_acc)
 int chain_tc2_launch(const ChainTcArgs &a, long rows_total, cudaStream_t st);   // net_tc2.cu
 
 // ---- streaming GEMM (layers whose K or N do not fit the operand-resident chain: layer3 / group_all) -------------
-struct GemmTcArgs {
-    const float *X1, *X2;     // rows [rows_total][C1] (+ [rows_total][C2] appended), f32
-    int C1, C2;
-    TcLayer L;                // K >= C1 + C2 (zero padded), N arbitrary multiple of 32 (processed in chunks of <= 256)
-    float *out;               // pool_S == 0: [rows_total][ldo] rows;  pool_S > 0: [rows_total / pool_S][N] zero-initialised max-pool
-    int ldo;
-    int pool_S;               // rows per pooled group (multiple of 32), 0 = no pooling
-    uint32_t tmem_cols;       // filled by the launcher
-    int max_acc;              // hi*hi accumulators (k range split), see tc_num_acc
+// Image of a [rows][K] operand as the chain's TC_DST_IMAGE steps write it and gemm_img_launch reads it: per 128-row tile
+// [K/8][hi | lo][128][8] fp16, tile stride K * 512 bytes -- 4 bytes per element, the size of the f32 rows.
+struct GemmImgArgs {
+    const void *Aimg;         // [rows_total / 128] tiles
+    TcLayer L;                // K = image width (multiple of 16), N multiple of 128, ReLU
+    float *out;               // [rows_total / pool_S][N] max over each group of pool_S consecutive rows
+    int pool_S;               // multiple of 32
 };
-int gemm_tc_launch(const GemmTcArgs &a, long rows_total, cudaStream_t st);
+int gemm_img_launch(const GemmImgArgs &a, long rows_total, cudaStream_t st);

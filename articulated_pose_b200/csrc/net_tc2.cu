@@ -35,7 +35,8 @@ constexpr int TM = 128;                 // rows per CTA
 constexpr int NWORK = 256;              // worker threads
 constexpr int NTHR = NWORK + 64;        // + MMA warp + producer warp
 constexpr int STAGE_BYTES = 8192;       // one ring stage of weights
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 8;        // one-CTA-per-SM plans (operand > 80 KB): the ring is all that hides the L2 latency
+constexpr int DEF_STAGES = 4;        // two / three CTAs per SM
 constexpr int MAX_UNITS = 16;
 
 struct Unit {
@@ -52,6 +53,7 @@ struct Unit {
     int nsl;               // ring stages (slices) per chunk
     int relu, inplace, pool, ldo;
     int act;               // TC_ACT_*: head activations in the epilogue
+    int image;             // out is the fp16 hi/lo operand image of a following streaming GEMM (TC_DST_IMAGE)
     float descale;         // accumulators * descale = the layer's output (TcLayer::descale)
 };
 
@@ -611,6 +613,18 @@ __global__ void __launch_bounds__(NTHR, MINB) chain2_kernel(const __grid_constan
                     if (U.pool) {
                         const long g = ((long)blockIdx.x * TM + wq * 32) / a.S;
                         pool_store2<CW>(U.out + ((size_t)b * a.m + g) * U.Nfull + col, a.S, lane, v);
+                    } else if (U.image) {
+                        // tile image [Nfull/8][hi|lo][128][8] (net_tc.cuh, GemmImgArgs): consecutive rows -> consecutive
+                        // 16-byte pieces, coalesced
+                        uint8_t *img = reinterpret_cast<uint8_t *>(U.out) + (size_t)blockIdx.x * ((size_t)U.Nfull * 512) + r * 16;
+#pragma unroll
+                        for (int q8 = 0; q8 < CW / 8; ++q8) {
+                            float w[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) w[i] = v[q8 * 8 + i];
+                            uint8_t *p = img + (size_t)((col >> 3) + q8) * 4096;
+                            split8(w, reinterpret_cast<uint4 *>(p), reinterpret_cast<uint4 *>(p + 2048));
+                        }
                     } else if (U.out) {
                         float4 *o = reinterpret_cast<float4 *>(U.out + (size_t)R * U.ldo + col);
 #pragma unroll
@@ -638,6 +652,7 @@ struct LayerSpec {
     const float *bias_override;
     long bias_stride;
     int act;
+    int image;
 };
 
 int build_units(Chain2Args &a, const LayerSpec *spec, int nspec, size_t *smem_out, int *minb_out)
@@ -658,20 +673,21 @@ int build_units(Chain2Args &a, const LayerSpec *spec, int nspec, size_t *smem_ou
     const size_t tail = (2 * MAX_STAGES + 1) * sizeof(uint64_t) + 16 + (a.fp_points2 ? (size_t)TM * 3 * 8 : 0);
     size_t limit = 113 * 1024;                                 // two CTAs per SM when the operand is small enough
     a.tmem_cols = 256;
-    a.nst = MAX_STAGES;
+    a.nst = DEF_STAGES;
     // Narrow chains (every accumulator set fits 128 TMEM columns when the layers are cut into 64-column chunks, operand
     // + ring <= 1/3 of the shared memory): three CTAs per SM -- these chains are bound by the latency of the
     // gather -> MMA -> epilogue sequence of one tile, not by any pipe, so residency is what buys throughput.
     static const bool narrow_off = getenv("ANCSH_CHAIN_NARROW_OFF") != nullptr;   // A/B switch for profiling
-    bool narrow = !narrow_off && opbytes + (size_t)MAX_STAGES * STAGE_BYTES + tail <= 74 * 1024;
+    bool narrow = !narrow_off && opbytes + (size_t)DEF_STAGES * STAGE_BYTES + tail <= 74 * 1024;
     for (int i = 0; i < nspec && narrow; ++i) {
         const TcLayer &L = spec[i].L;
         if (L.K > 144 || L.N % 32 != 0 || (spec[i].inplace ? L.N > 64 : (L.N > 64 && L.N % 64 != 0))) narrow = false;
     }
     if (narrow) { limit = 74 * 1024; a.tmem_cols = 128; *minb_out = 3; }
-    if (opbytes + (size_t)MAX_STAGES * STAGE_BYTES + tail > limit) {
+    if (opbytes + (size_t)DEF_STAGES * STAGE_BYTES + tail > limit) {
         limit = 227 * 1024;
         a.tmem_cols = 512;
+        a.nst = MAX_STAGES;
         while (a.nst > 2 && opbytes + (size_t)a.nst * STAGE_BYTES + tail > limit) --a.nst;
     }
     const size_t smem = opbytes + (size_t)a.nst * STAGE_BYTES + tail;
@@ -699,7 +715,7 @@ int build_units(Chain2Args &a, const LayerSpec *spec, int nspec, size_t *smem_ou
             U.G = 1;                                           // filled below (needs the final tmem_cols)
             U.ksl = STAGE_BYTES / (64 * nc);
             U.nsl = (L.K / 16 + U.ksl - 1) / U.ksl;
-            U.relu = L.relu; U.inplace = spec[i].inplace; U.pool = spec[i].pool; U.act = spec[i].act;
+            U.relu = L.relu; U.inplace = spec[i].inplace; U.pool = spec[i].pool; U.act = spec[i].act; U.image = spec[i].image;
             U.descale = L.descale;
         }
     }
@@ -777,10 +793,12 @@ int chain_tc2_launch(const ChainTcArgs &c, long rows_total, cudaStream_t st)
         spec[i].inplace = c.S[i].dst == TC_DST_INPLACE;
         spec[i].out = c.S[i].out; spec[i].ldo = c.S[i].ldo;
         spec[i].act = c.S[i].act;
+        spec[i].image = c.S[i].dst == TC_DST_IMAGE;
         if (c.S[i].act != TC_ACT_NONE && (c.S[i].dst != TC_DST_GLOBAL || c.S[i].L.N != 64 || c.S[i].L.relu)) return ANCSH_ERR_INVALID_ARG;
-        if (c.S[i].dst == TC_DST_GLOBAL && !c.S[i].out && c.S[i].act == TC_ACT_NONE) return ANCSH_ERR_INVALID_ARG;
+        if (c.S[i].dst != TC_DST_INPLACE && !c.S[i].out && c.S[i].act == TC_ACT_NONE) return ANCSH_ERR_INVALID_ARG;
+        if (c.S[i].dst == TC_DST_IMAGE && ((c.pool_S > 0 && i == c.nsteps - 1) || c.S[i].L.N % 16 != 0)) return ANCSH_ERR_INVALID_ARG;
         const bool pooled = c.pool_S > 0 && i == c.nsteps - 1;
-        if (!pooled && c.S[i].out && (c.S[i].ldo < c.S[i].L.N || c.S[i].ldo % 4 != 0)) return ANCSH_ERR_INVALID_ARG;
+        if (!pooled && c.S[i].out && c.S[i].dst != TC_DST_IMAGE && (c.S[i].ldo < c.S[i].L.N || c.S[i].ldo % 4 != 0)) return ANCSH_ERR_INVALID_ARG;
     }
     if (c.bias0) { spec[0].bias_override = c.bias0; spec[0].bias_stride = c.bias0_stride; }
     if (c.pool_S > 0) {
