@@ -49,6 +49,7 @@ struct Unit {
     int nc;                // chunk width == accumulator stride in TMEM columns (32 / 64 / 128)
     int nchunks;
     int G;                 // hi*hi accumulators per chunk
+    int kb[8];             // kb[g] = first k-step of hi*hi accumulator g + 1 (k-step kk goes to accumulator kk * G / nk16)
     int ksl;               // k16 steps per ring stage
     int nsl;               // ring stages (slices) per chunk
     int relu, inplace, pool, ldo;
@@ -349,24 +350,27 @@ __global__ void __launch_bounds__(NTHR, MINB) chain2_kernel(const __grid_constan
             const Unit &U = a.U[u];
             const int nk16 = U.K / 16;
             const uint32_t piece = (uint32_t)U.nc * 16u;                               // one (kc, hi|lo) block of the chunk
-            const uint8_t *src = reinterpret_cast<const uint8_t *>(U.Wimg);
+            const size_t slab = (size_t)U.Nfull * 16;                                  // one (kc, hi|lo) slab of the image
+            const bool whole = U.nc == U.Nfull;                                        // a stage is one contiguous slice
             for (int j = 0; j < U.nchunks; ++j) {
-                const int ncol0 = U.n0 + j * U.nc;
-                for (int i = 0; i < U.nsl; ++i) {
+                const uint8_t *src = reinterpret_cast<const uint8_t *>(U.Wimg) + (size_t)(U.n0 + j * U.nc) * 16;
+                int left = nk16;
+                for (int i = 0; i < U.nsl; ++i, left -= U.ksl) {
                     if (round > 0) tc::mbar_wait(bar_empty + slot, (uint32_t)((round - 1) & 1));
                     if (elect_one()) {
-                        const int k0 = i * U.ksl, steps = min(U.ksl, nk16 - k0);
-                        mbar_expect_tx(bar_full + slot, (uint32_t)steps * 4u * piece);
+                        const int steps = min(U.ksl, left);
+                        const uint32_t bytes = (uint32_t)steps * 4u * piece;
+                        mbar_expect_tx(bar_full + slot, bytes);
                         const uint32_t dst = ring0 + (uint32_t)slot * STAGE_BYTES;
-                        if (U.nc == U.Nfull) {                                         // contiguous slice
-                            bulk_g2s(dst, src + (size_t)(2 * k0) * 2 * U.Nfull * 16, (uint32_t)steps * 4u * piece, bar_full + slot);
+                        if (whole) {
+                            bulk_g2s(dst, src, bytes, bar_full + slot);
                         } else {
                             for (int p = 0; p < steps * 4; ++p)                        // p = kc_local * 2 + (hi|lo)
-                                bulk_g2s(dst + (uint32_t)p * piece,
-                                         src + ((size_t)(2 * k0) * 2 + p) * U.Nfull * 16 + (size_t)ncol0 * 16, piece, bar_full + slot);
+                                bulk_g2s(dst + (uint32_t)p * piece, src + (size_t)p * slab, piece, bar_full + slot);
                         }
                     }
                     __syncwarp();
+                    src += (size_t)U.ksl * 4 * slab;
                     if (++slot == a.nst) { slot = 0; ++round; }
                 }
             }
@@ -381,30 +385,33 @@ __global__ void __launch_bounds__(NTHR, MINB) chain2_kernel(const __grid_constan
             CHAIN_TRACE(40 + 2 * u);
             const uint32_t idesc = tc::instr_desc_f16(TM, U.nc);
             const uint32_t sslab = 2u * (uint32_t)U.nc * 16u;
+            // descriptors differ only in the start-address field (address >> 4, low word): bases + 32-bit offsets
             const uint64_t ah0 = tc::smem_desc(a_hi0, 2048u, 128u), al0 = tc::smem_desc(a_lo0, 2048u, 128u);
+            const uint64_t bh00 = tc::smem_desc(ring0, sslab, 128u);
+            const uint32_t accB = (uint32_t)(U.G * U.nc);
             tc::fence_after_sync();
             for (int j = 0; j < U.nchunks; ++j) {
                 const uint32_t tbase = tmem + (uint32_t)(j * (U.G + 1) * U.nc);
-                uint32_t startedA = 0, startedB = 0;
+                int kk = 0;                                   // k-step; gnext = first k-step of the next hi*hi accumulator
+                int g = 0, gnext = U.kb[0];
+                uint32_t freshA = 1u;                         // the next hi*hi MMA starts its accumulator
                 for (int i = 0; i < U.nsl; ++i) {
                     tc::mbar_wait(bar_full + slot, (uint32_t)(round & 1));
-                    if (elect_one()) {
-                        const int k0 = i * U.ksl, steps = min(U.ksl, nk16 - k0);
-                        // descriptors differ only in the start-address field (address >> 4): add offsets to a base
-                        const uint64_t bh0 = tc::smem_desc(ring0 + (uint32_t)slot * STAGE_BYTES, sslab, 128u);
-                        for (int s = 0; s < steps; ++s) {
-                            const int kk = k0 + s;
-                            const uint64_t ah = ah0 + (uint64_t)(kk * 256), al = al0 + (uint64_t)(kk * 256);   // 2 * 2048 / 16
-                            const uint64_t bh = bh0 + (uint64_t)(s * (int)(sslab >> 3)), bl = bh + (uint64_t)U.nc;
-                            const int g = U.G == 1 ? 0 : kk * U.G / nk16;
-                            tc::mma_f16(tbase + (uint32_t)(g * U.nc), ah, bh, idesc, (startedA >> g) & 1u);
-                            startedA |= 1u << g;
-                            tc::mma_f16(tbase + (uint32_t)(U.G * U.nc), ah, bl, idesc, startedB);
-                            startedB = 1u;
-                            tc::mma_f16(tbase + (uint32_t)(U.G * U.nc), al, bh, idesc, 1u);
+                    // the bookkeeping below is warp-uniform; only the elected lane issues
+                    const bool lead = elect_one();
+                    const int steps = min(U.ksl, nk16 - kk);
+                    uint64_t bh = bh00 + (uint64_t)(uint32_t)(slot * (STAGE_BYTES >> 4));
+                    uint64_t ah = ah0 + (uint64_t)(uint32_t)(kk * 256), al = al0 + (uint64_t)(uint32_t)(kk * 256);   // 2 * 2048 / 16
+                    for (int s = 0; s < steps; ++s, ++kk, ah += 256, al += 256, bh += sslab >> 3) {
+                        if (kk == gnext) { ++g; gnext = U.kb[g]; freshA = 1u; }
+                        if (lead) {
+                            tc::mma_f16(tbase + (uint32_t)(g * U.nc), ah, bh, idesc, freshA ^ 1u);
+                            tc::mma_f16(tbase + accB, ah, bh + (uint64_t)U.nc, idesc, kk > 0);
+                            tc::mma_f16(tbase + accB, al, bh, idesc, 1u);
                         }
-                        tc::mma_commit(bar_empty + slot);     // the stage may be refilled once these MMAs have read it
+                        freshA = 0u;
                     }
+                    if (lead) tc::mma_commit(bar_empty + slot);   // the stage may be refilled once these MMAs have read it
                     __syncwarp();
                     if (++slot == a.nst) { slot = 0; ++round; }
                 }
@@ -722,6 +729,9 @@ int build_units(Chain2Args &a, const LayerSpec *spec, int nspec, size_t *smem_ou
     for (int u = 0; u < a.nunits; ++u) {
         Unit &U = a.U[u];
         U.G = tc_num_acc(U.K, (int)a.tmem_cols / (U.nc * U.nchunks) - 1);
+        if (U.G > 8) return ANCSH_ERR_UNSUPPORTED;
+        const int nk16 = U.K / 16;
+        for (int g = 0; g < 8; ++g) U.kb[g] = g < U.G - 1 ? ((g + 1) * nk16 + U.G - 1) / U.G : 0x7FFFFFFF;
     }
     *smem_out = smem;
     return ANCSH_OK;
