@@ -500,7 +500,11 @@ __global__ void __launch_bounds__(JIT) joint_init_kernel(const JointArgs a, Join
     r.valid = 1;
 }
 
-constexpr int LMT = 64;          // threads per block of joint_lm_kernel
+// Threads per block of joint_lm_kernel (template parameter).  The lanes are latency bound and independent, so the block
+// shape does not change a solve; it decides how many SMs hold an LM block while the forward kernels of the next batches
+// run beside it: a forward CTA needs ~31k registers and ~100 KB of shared memory, two fit an SM only when no LM block
+// (216 registers per lane) is resident.  Fewer, larger blocks leave more SMs entirely to the forward kernels.
+constexpr int LMT_DEFAULT = 256;
 constexpr int LM_SOLVES_PER_LANE = 3;
 constexpr int LM_PHASES = 3;
 constexpr int LM_BUDGET[LM_PHASES] = {32, 160, 0x7fffffff};   // evaluations after which a solve moves to the next phase
@@ -513,6 +517,7 @@ constexpr int LM_SLOTS = 39;     // doubles per lane in shared memory: 36 point 
 constexpr int LM_STAT_NJEV = 60, LM_STAT_NLM = 61;
 
 // objective_eval over one lane's 3+3 points; element e of the lane lives at pts[e * LMT] (conflict-free)
+template <int LMT>
 struct LaneProb {
     const double *pts;
     __device__ __forceinline__ void load3(int e, double *v) const
@@ -556,15 +561,16 @@ struct LaneProb {
 // phase ph+1.  Later phases claim from the list the previous phase wrote.  Re-packing keeps the lanes of a warp busy:
 // without it the few solves that run to MINPACK's maxfev = 600 each pin a warp at 1/32 utilisation (measured: 9.8 of 32
 // lanes active on average, 8.3 ms per 256 clouds; the median solve needs 12 evaluations).
-__global__ void __launch_bounds__(LMT, LM_BLOCKS_PER_SM) joint_lm_kernel(const JointArgs a, JointRec *recs, int total, int ph,
-                                                                         int budget, const int *in_list, int *out_list)
+template <int LMT>
+__global__ void __launch_bounds__(LMT, 256 / LMT) joint_lm_kernel(const JointArgs a, JointRec *recs, int total, int ph,
+                                                                  int budget, const int *in_list, int *out_list)
 {
-    __shared__ double s_pts[LM_SLOTS * LMT];
+    extern __shared__ double s_pts[];            // [LM_SLOTS][LMT]
     double *my = s_pts + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     int *claim = a.tail_count + 2 * ph;          // [2 ph] claim counter of this phase, [2 ph + 1] length of its work list
     const int avail = in_list ? a.tail_count[2 * ph + 1] : total;
-    LaneProb P;
+    LaneProb<LMT> P;
     P.pts = my;
     pm::LmTick s;
     int t = -1;             // record this lane is solving
@@ -1324,13 +1330,22 @@ extern "C" int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in
             int dev = 0, sms = 148;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            // Resident LM blocks per SM.  Measured (B200, 256 clouds): the first phase takes 6.9 / 6.7 / 6.7 / 7.2 ms of
-            // joint stage with 4 / 3 / 2 / 1 blocks per SM -- it is bound by the latency of each lane's serial solve, not by
-            // the number of lanes -- while one block per SM leaves three quarters of the register file to the forward CTAs
-            // of the overlapped batches: 25.1k instead of 24.4k clouds/s in the pipelined run.  ANCSH_LM_BLOCKS_PER_SM
-            // (1..4) overrides.
+            // Lanes in flight and their packing.  The lanes are independent serial solves (latency bound: ~20% issue
+            // utilisation), so the joint stage alone gets faster with more lanes -- but an SM that holds LM lanes (216
+            // registers each) has no room for the second forward CTA of the batches that overlap this stage, and the
+            // pipelined throughput is what counts.  Measured (B200, 256 clouds per batch, bench.py default):
+            //   64 / 128 / 256 threads per block at 64 lanes per SM:   32.0k / 33.5k / 34.9k clouds/s
+            //   256 threads, 135 / 100 / 75 / 50 / 35 / 25 % of those lanes:  34.6k / 34.8k / 35.4k / 35.9k / 35.8k / 35.1k
+            //   (joint stage alone: 8.5 / 8.8 / 9.6 / 11.2 / 13.3 / 15.6 ms)
+            // Default: 256-thread blocks, 32 lanes per SM -> 18 blocks on a 148-SM part.  ANCSH_LM_THREADS (64 / 128 / 256),
+            // ANCSH_LM_LANE_PCT and ANCSH_LM_BLOCKS_PER_SM (multiplier 1..4) override -- more lanes for latency, fewer for
+            // throughput.
             static const int lm_cap = getenv("ANCSH_LM_BLOCKS_PER_SM") ? atoi(getenv("ANCSH_LM_BLOCKS_PER_SM")) : 1;
-            const long cap = (long)sms * (lm_cap >= 1 && lm_cap <= LM_BLOCKS_PER_SM ? lm_cap : 1);
+            static const int lmt_env = getenv("ANCSH_LM_THREADS") ? atoi(getenv("ANCSH_LM_THREADS")) : LMT_DEFAULT;
+            const int lmt = lmt_env == 64 || lmt_env == 128 ? lmt_env : 256;
+            static const int lane_pct = getenv("ANCSH_LM_LANE_PCT") ? atoi(getenv("ANCSH_LM_LANE_PCT")) : 50;
+            long cap = (long)sms * 64 * (lm_cap >= 1 && lm_cap <= LM_BLOCKS_PER_SM ? lm_cap : 1) * (lane_pct >= 10 ? lane_pct : 100) / 100 / lmt;
+            if (cap < 1) cap = 1;
             int *lists = (int *)(recs + nsolves);              // 2 x nsolves work-list entries behind the records
             // debugging aid: ANCSH_LM_TRACE=1 prints the duration of every LM phase (synchronises the stream)
             static const bool lm_trace = getenv("ANCSH_LM_TRACE") != nullptr;
@@ -1339,11 +1354,19 @@ extern "C" int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in
             for (int ph = 0; ph < LM_PHASES; ++ph) {
                 const long items = ph == 0 ? nsolves : nsolves / LM_PHASE_SHARE[ph] + 1;
                 const long per_lane = ph == 0 ? LM_SOLVES_PER_LANE : 1;     // later phases: few, long solves -> one lane each
-                long blocks = (items + (long)LMT * per_lane - 1) / ((long)LMT * per_lane);
+                long blocks = (items + (long)lmt * per_lane - 1) / ((long)lmt * per_lane);
                 blocks = blocks < 1 ? 1 : (blocks > cap ? cap : blocks);
-                joint_lm_kernel<<<(unsigned)blocks, LMT, 0, st>>>(a, recs, (int)nsolves, ph, LM_BUDGET[ph],
-                                                                 ph == 0 ? nullptr : lists + (size_t)((ph - 1) & 1) * nsolves,
-                                                                 lists + (size_t)(ph & 1) * nsolves);
+                const int *in_list = ph == 0 ? nullptr : lists + (size_t)((ph - 1) & 1) * nsolves;
+                int *out_list = lists + (size_t)(ph & 1) * nsolves;
+                const size_t lm_smem = (size_t)LM_SLOTS * lmt * sizeof(double);
+                if (lmt == 64) {
+                    joint_lm_kernel<64><<<(unsigned)blocks, 64, lm_smem, st>>>(a, recs, (int)nsolves, ph, LM_BUDGET[ph], in_list, out_list);
+                } else if (lmt == 128) {
+                    joint_lm_kernel<128><<<(unsigned)blocks, 128, lm_smem, st>>>(a, recs, (int)nsolves, ph, LM_BUDGET[ph], in_list, out_list);
+                } else {
+                    ANCSH_CUDA(cudaFuncSetAttribute(joint_lm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lm_smem));
+                    joint_lm_kernel<256><<<(unsigned)blocks, 256, lm_smem, st>>>(a, recs, (int)nsolves, ph, LM_BUDGET[ph], in_list, out_list);
+                }
                 ANCSH_CHECK_LAUNCH();
                 if (lm_trace) cudaEventRecord(tev[ph + 1], st);
             }
