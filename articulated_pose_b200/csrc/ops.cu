@@ -25,8 +25,7 @@ __global__ void __launch_bounds__(NT) fps_kernel(int n, int m, const float *__re
                                                  float *__restrict__ new_xyz2)
 {
     extern __shared__ float s_xyz[];  // n*3 floats
-    __shared__ uint32_t s_val[2][NT / 32];
-    __shared__ uint32_t s_key[2][NT / 32];
+    __shared__ unsigned long long s_best[2][NT / 32];
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
@@ -36,8 +35,12 @@ __global__ void __launch_bounds__(NT) fps_kernel(int n, int m, const float *__re
     for (int i = tid; i < n * 3; i += NT) s_xyz[i] = p[i];
     __syncthreads();
 
+    // Candidate order as ONE unsigned 64-bit key per point: (distance bits) << 32 | ~tie key.  Distances are >= 0, so their
+    // bit patterns are monotone; the larger key is the farther point and, among equals, the one the reference's reduction
+    // keeps (smallest tie key).  Padding lanes carry distance 0 and ~key 0: key 0 loses against every real point (whose
+    // ~tie key is >= 1).  The whole update is branch-free (the previous compare-and-branch chain cost ~60 cycles a point).
     float px[PPT], py[PPT], pz[PPT], pd[PPT];
-    uint32_t pkey[PPT];
+    uint32_t nkey[PPT];
 #pragma unroll
     for (int i = 0; i < PPT; ++i) {
         int k = tid + i * NT;
@@ -45,8 +48,8 @@ __global__ void __launch_bounds__(NT) fps_kernel(int n, int m, const float *__re
         px[i] = v ? s_xyz[k * 3 + 0] : 0.f;
         py[i] = v ? s_xyz[k * 3 + 1] : 0.f;
         pz[i] = v ? s_xyz[k * 3 + 2] : 0.f;
-        pd[i] = 1e38f;                           // tf_sampling_g.cu:117-119
-        pkey[i] = v ? fps_tie_key(k) : 0xFFFFFFFFu;
+        pd[i] = v ? 1e38f : 0.f;                 // tf_sampling_g.cu:117-119
+        nkey[i] = v ? ~fps_tie_key(k) : 0u;
     }
 
     int old = 0;
@@ -66,31 +69,34 @@ __global__ void __launch_bounds__(NT) fps_kernel(int n, int m, const float *__re
     }
     for (int j = 1; j < m; ++j) {
         const float x1 = s_xyz[old * 3 + 0], y1 = s_xyz[old * 3 + 1], z1 = s_xyz[old * 3 + 2];
-        uint32_t bv = 0u, bk = 0xFFFFFFFFu;
-        bool any = false;
+        unsigned long long key[PPT];
 #pragma unroll
         for (int i = 0; i < PPT; ++i) {
             float dx = px[i] - x1, dy = py[i] - y1, dz = pz[i] - z1;
             float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));   // SASS contract of :142
             float d2 = fminf(d, pd[i]);
             pd[i] = d2;
-            uint32_t u = __float_as_uint(d2);                                     // d2 >= 0: bits are monotone
-            bool valid = pkey[i] != 0xFFFFFFFFu;
-            bool better = valid && (!any || u > bv || (u == bv && pkey[i] < bk));
-            if (better) { bv = u; bk = pkey[i]; any = true; }
+            key[i] = ((unsigned long long)__float_as_uint(d2) << 32) | nkey[i];
         }
-        // warp arg-max of (bv, smallest bk)
-        uint32_t wv = __reduce_max_sync(0xFFFFFFFFu, any ? bv : 0u);
-        uint32_t wk = __reduce_min_sync(0xFFFFFFFFu, (any && bv == wv) ? bk : 0xFFFFFFFFu);
-        const int buf = j & 1;
-        if (lane == 0) { s_val[buf][warp] = wv; s_key[buf][warp] = wk; }
-        __syncthreads();
-        uint32_t fv = 0u, fk = 0xFFFFFFFFu;
 #pragma unroll
-        for (int w = 0; w < NT / 32; ++w) {
-            uint32_t v = s_val[buf][w], k = s_key[buf][w];
-            if (k != 0xFFFFFFFFu && (fk == 0xFFFFFFFFu || v > fv || (v == fv && k < fk))) { fv = v; fk = k; }
+        for (int s = PPT / 2; s > 0; s >>= 1) {
+#pragma unroll
+            for (int i = 0; i < s; ++i) key[i] = key[i] > key[i + s] ? key[i] : key[i + s];
         }
+        // warp arg-max: distance part first, then the ~tie key among the lanes that hold it
+        const uint32_t bv = (uint32_t)(key[0] >> 32), bn = (uint32_t)key[0];
+        const uint32_t wv = __reduce_max_sync(0xFFFFFFFFu, bv);
+        const uint32_t wn = __reduce_max_sync(0xFFFFFFFFu, bv == wv ? bn : 0u);
+        const int buf = j & 1;
+        if (lane == 0) s_best[buf][warp] = ((unsigned long long)wv << 32) | wn;
+        __syncthreads();
+        unsigned long long fb = s_best[buf][0];
+#pragma unroll
+        for (int w = 1; w < NT / 32; ++w) {
+            const unsigned long long o = s_best[buf][w];
+            fb = o > fb ? o : fb;
+        }
+        const uint32_t fk = ~(uint32_t)fb;
         old = fps_key_to_index(fk);
         if (tid == 0) {
             idx_out[(size_t)b * m + j] = old;
