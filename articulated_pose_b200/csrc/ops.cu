@@ -1,7 +1,6 @@
 // ops.cu -- op-level kernels of the PointNet++ hot path (sm_100a): farthest point sampling, gather,
 // ball query, group, three_nn, three_interpolate.  Arithmetic contracts: SURVEY.md section 8(a).
 #include <atomic>
-#include <cstdlib>
 #include "common.cuh"
 #include "ops.cuh"
 
@@ -152,8 +151,9 @@ int ancsh_fps2_impl(int b, int n, int m, const float *xyz, int *idx, float *new_
     if (b == 0 || m == 0) return ANCSH_OK;
     if (n <= 256) return fps_launch<128, 2>(b, n, m, xyz, idx, new_xyz, m2, idx2, new_xyz2, st);
     if (n <= 512) return fps_launch<128, 4>(b, n, m, xyz, idx, new_xyz, m2, idx2, new_xyz2, st);
-    // block shape for n <= 1024 measured on B200 (256 clouds, m = 512): 512x2 0.79 ms, 256x4 0.366, 128x8 0.356, 64x16 0.55,
-    // 32x32 1.03 -- fewer warps shorten the barrier and the cross-warp scan until the per-warp distance updates dominate
+    // block shape for n <= 1024 measured on B200 (256 clouds, m = 512, branch-free update): 256x4 0.205 ms, 128x8 0.165,
+    // 64x16 0.196, 32x32 0.219 -- fewer warps shorten the barrier and the cross-warp scan until the per-warp distance
+    // updates dominate (with the earlier compare-and-branch update: 0.366 / 0.356 / 0.55 / 1.03 ms)
     if (n <= 1024) return fps_launch<128, 8>(b, n, m, xyz, idx, new_xyz, m2, idx2, new_xyz2, st);
     if (n <= 2048) return fps_launch<256, 8>(b, n, m, xyz, idx, new_xyz, m2, idx2, new_xyz2, st);
     if (n <= 4096) return fps_launch<512, 8>(b, n, m, xyz, idx, new_xyz, m2, idx2, new_xyz2, st);
