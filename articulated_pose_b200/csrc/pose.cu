@@ -135,8 +135,8 @@ __global__ void __launch_bounds__(RT) partition_kernel(const PartitionArgs a)
 {
     extern __shared__ unsigned char s_raw[];
     const int N = a.N, K = a.K, b = blockIdx.x, tid = threadIdx.x;
-    int npow2 = 1;
-    while (npow2 < N) npow2 <<= 1;
+    int npow2 = 1, lg2 = 0;
+    while (npow2 < N) { npow2 <<= 1; ++lg2; }
     unsigned char *s_label = s_raw;                                      // N
     int *s_cnt = reinterpret_cast<int *>(s_raw + ((N + 15) & ~15));      // RT * 8
     float *s_val = reinterpret_cast<float *>(s_cnt + RT * 8);            // 3 * npow2
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(RT) partition_kernel(const PartitionArgs a)
         for (int k = 2; k <= npow2; k <<= 1)
             for (int jj = k >> 1; jj > 0; jj >>= 1) {
                 for (int t = tid; t < 3 * npow2; t += RT) {
-                    const int c = t / npow2, i = t - c * npow2, ixj = i ^ jj;
+                    const int c = t >> lg2, i = t & (npow2 - 1), ixj = i ^ jj;        // npow2 is a power of two
                     if (ixj > i) {
                         float *v = s_val + c * npow2;
                         const bool up = (i & k) == 0;
@@ -1337,6 +1337,7 @@ extern "C" int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in
             //   64 / 128 / 256 threads per block at 64 lanes per SM:   32.0k / 33.5k / 34.9k clouds/s
             //   256 threads, 135 / 100 / 75 / 50 / 35 / 25 % of those lanes:  34.6k / 34.8k / 35.4k / 35.9k / 35.8k / 35.1k
             //   (joint stage alone: 8.5 / 8.8 / 9.6 / 11.2 / 13.3 / 15.6 ms)
+            //   512 threads at 128 registers (2 KB of spills per lane): 35.1k -- rejected
             // Default: 256-thread blocks, 32 lanes per SM -> 18 blocks on a 148-SM part.  ANCSH_LM_THREADS (64 / 128 / 256),
             // ANCSH_LM_LANE_PCT and ANCSH_LM_BLOCKS_PER_SM (multiplier 1..4) override -- more lanes for latency, fewer for
             // throughput.

@@ -1,9 +1,9 @@
 #!/bin/bash
-# persistent joint_refit: blocks per SM vs pipelined throughput
-echo "== pytest pose/pipeline"; timeout 900 python -m pytest tests/test_pose_gpu.py tests/test_pipeline_gpu.py tests/test_pose_f32_reference.py -q -x --tb=short 2>&1 | tail -4
+# LM 512-thread blocks (128 registers, spills) vs 256-thread blocks
 run() { echo "== $*"; env "$@" timeout 600 python bench.py --no-cpu-baseline 2>&1 | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); s=d['roofline']['stage_ms']; print(round(d['value']), 'e2e', round(d['e2e']['value']), d['ms_per_step'], {k:v for k,v in s.items() if k.startswith('pose_joint')})"; }
-run ANCSH_REFIT_BLOCKS_PCT=200
-run ANCSH_REFIT_BLOCKS_PCT=100
-run ANCSH_REFIT_BLOCKS_PCT=50
+echo "== pytest pose"; timeout 900 env ANCSH_LM_THREADS=512 python -m pytest tests/test_pose_gpu.py -q -x --tb=short 2>&1 | tail -3
+run ANCSH_LM_THREADS=512
+run ANCSH_LM_THREADS=512 ANCSH_LM_LANE_PCT=100
+run ANCSH_LM_THREADS=256

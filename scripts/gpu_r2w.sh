@@ -1,7 +1,3 @@
 #!/bin/bash
-# FPS block shape sweep (n = 1024, m = 512, 256 clouds) with the branch-free update
-for S in 32 64 128 256; do
-echo "== shape $S" ; ANCSH_FPS_SHAPE=$S timeout 300 python bench.py --workload forward --no-cpu-baseline --steps 6 2>&1 | tail -1 | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(round(d['value']), d['roofline']['stage_ms']['fps1'])"
-done
+# launch list of one full step (both forwards + pose), cold-cache serialised times
+timeout 600 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none -c 120 --csv --log-file gpurun_out/r2w_launches.csv python bench.py --no-cpu-baseline --steps 1 --warmup 1 --chunks 1 > /dev/null 2>&1; wc -l gpurun_out/r2w_launches.csv
