@@ -77,6 +77,7 @@ vp = ctypes.c_void_p
 ancsh_version = _sig("ancsh_version", [], ctypes.c_char_p)
 ancsh_launch_count = _sig("ancsh_launch_count", [], ctypes.c_ulonglong)
 ancsh_diag_fp64_fma = _sig("ancsh_diag_fp64_fma", [c_int, c_int, vp, vp])
+ancsh_pose_lm_shape = _sig("ancsh_pose_lm_shape", [ctypes.POINTER(c_int), ctypes.POINTER(c_int)])
 ancsh_weights_pack = _sig("ancsh_weights_pack", [c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(vp), ctypes.POINTER(c_size_t),
                                                  c_int, c_int, c_int, ctypes.c_char_p, ctypes.POINTER(vp)])
 ancsh_packed_destroy = _sig("ancsh_packed_destroy", [vp], None)

@@ -135,8 +135,8 @@ __global__ void __launch_bounds__(RT) partition_kernel(const PartitionArgs a)
 {
     extern __shared__ unsigned char s_raw[];
     const int N = a.N, K = a.K, b = blockIdx.x, tid = threadIdx.x;
-    int npow2 = 1, lg2 = 0;
-    while (npow2 < N) { npow2 <<= 1; ++lg2; }
+    int npow2 = 1;
+    while (npow2 < N) npow2 <<= 1;
     unsigned char *s_label = s_raw;                                      // N
     int *s_cnt = reinterpret_cast<int *>(s_raw + ((N + 15) & ~15));      // RT * 8
     float *s_val = reinterpret_cast<float *>(s_cnt + RT * 8);            // 3 * npow2
@@ -194,10 +194,13 @@ __global__ void __launch_bounds__(RT) partition_kernel(const PartitionArgs a)
         }
         __syncthreads();
         const int nj = s_nj;
-        for (int k = 2; k <= npow2; k <<= 1)
+        // bitonic sort of the first npj = 2^lgj >= nj entries of each component (the rest is +inf padding)
+        int npj = 2, lgj = 1;
+        while (npj < nj) { npj <<= 1; ++lgj; }
+        for (int k = 2; k <= npj; k <<= 1)
             for (int jj = k >> 1; jj > 0; jj >>= 1) {
-                for (int t = tid; t < 3 * npow2; t += RT) {
-                    const int c = t >> lg2, i = t & (npow2 - 1), ixj = i ^ jj;        // npow2 is a power of two
+                for (int t = tid; t < 3 * npj; t += RT) {
+                    const int c = t >> lgj, i = t & (npj - 1), ixj = i ^ jj;
                     if (ixj > i) {
                         float *v = s_val + c * npow2;
                         const bool up = (i & k) == 0;
@@ -639,6 +642,18 @@ __global__ void __launch_bounds__(LMT, 256 / LMT) joint_lm_kernel(const JointArg
             }
         }
     }
+}
+
+// Launch shape of joint_lm_kernel: threads per block and the most blocks a phase uses (see the measurements at the launch).
+static long lm_launch_shape(int sms, int *threads)
+{
+    static const int lm_cap = getenv("ANCSH_LM_BLOCKS_PER_SM") ? atoi(getenv("ANCSH_LM_BLOCKS_PER_SM")) : 1;
+    static const int lmt_env = getenv("ANCSH_LM_THREADS") ? atoi(getenv("ANCSH_LM_THREADS")) : LMT_DEFAULT;
+    static const int lane_pct = getenv("ANCSH_LM_LANE_PCT") ? atoi(getenv("ANCSH_LM_LANE_PCT")) : 50;
+    const int lmt = lmt_env == 64 || lmt_env == 128 ? lmt_env : 256;
+    long cap = (long)sms * 64 * (lm_cap >= 1 && lm_cap <= LM_BLOCKS_PER_SM ? lm_cap : 1) * (lane_pct >= 10 ? lane_pct : 100) / 100 / lmt;
+    *threads = lmt;
+    return cap < 1 ? 1 : cap;
 }
 
 __global__ void __launch_bounds__(JIT) joint_model_kernel(const JointArgs a, const JointRec *recs)
@@ -1341,12 +1356,8 @@ extern "C" int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in
             // Default: 256-thread blocks, 32 lanes per SM -> 18 blocks on a 148-SM part.  ANCSH_LM_THREADS (64 / 128 / 256),
             // ANCSH_LM_LANE_PCT and ANCSH_LM_BLOCKS_PER_SM (multiplier 1..4) override -- more lanes for latency, fewer for
             // throughput.
-            static const int lm_cap = getenv("ANCSH_LM_BLOCKS_PER_SM") ? atoi(getenv("ANCSH_LM_BLOCKS_PER_SM")) : 1;
-            static const int lmt_env = getenv("ANCSH_LM_THREADS") ? atoi(getenv("ANCSH_LM_THREADS")) : LMT_DEFAULT;
-            const int lmt = lmt_env == 64 || lmt_env == 128 ? lmt_env : 256;
-            static const int lane_pct = getenv("ANCSH_LM_LANE_PCT") ? atoi(getenv("ANCSH_LM_LANE_PCT")) : 50;
-            long cap = (long)sms * 64 * (lm_cap >= 1 && lm_cap <= LM_BLOCKS_PER_SM ? lm_cap : 1) * (lane_pct >= 10 ? lane_pct : 100) / 100 / lmt;
-            if (cap < 1) cap = 1;
+            int lmt = 0;
+            const long cap = lm_launch_shape(sms, &lmt);
             int *lists = (int *)(recs + nsolves);              // 2 x nsolves work-list entries behind the records
             // debugging aid: ANCSH_LM_TRACE=1 prints the duration of every LM phase (synchronises the stream)
             static const bool lm_trace = getenv("ANCSH_LM_TRACE") != nullptr;
@@ -1561,5 +1572,17 @@ extern "C" int ancsh_similarity_ransac(int nprob, int nmax, int niter, const flo
     ANCSH_CUDA(cudaFuncSetAttribute(similarity_ransac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     similarity_ransac_kernel<<<nprob, RT, smem, (cudaStream_t)stream>>>(a);
     ANCSH_CHECK_LAUNCH();
+    return ANCSH_OK;
+}
+
+// Launch shape of the joint LM solve on the current device (diagnostics: the stage is deliberately narrow, bench.py reports
+// the SMs it occupies next to its roofline fraction).
+extern "C" int ancsh_pose_lm_shape(int *threads_per_block, int *max_blocks)
+{
+    if (!threads_per_block || !max_blocks) return ANCSH_ERR_INVALID_ARG;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    *max_blocks = (int)lm_launch_shape(sms, threads_per_block);
     return ANCSH_OK;
 }

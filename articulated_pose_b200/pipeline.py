@@ -17,8 +17,8 @@ from .pose import PoseSolver, unpack_results
 
 class AncshPipeline:
     # batches in flight in submit()/run_many(): the pose tails of several batches overlap later forwards.  Measured on B200
-    # (256 clouds per batch): 4 slots 27.7k clouds/s, 6 slots 28.4k, 8 slots 28.5k
-    N_SLOTS = int(__import__('os').environ.get('ANCSH_SLOTS', '6'))
+    # (256 clouds per batch, narrow joint-LM grid of csrc/pose.cu): 4 slots 33.1k clouds/s, 6 slots 36.8k, 8 slots 37.2k
+    N_SLOTS = int(__import__('os').environ.get('ANCSH_SLOTS', '8'))
 
     def __init__(self, weights_ancsh, n_parts, weights_npcs=None, use_baseline=True, nsample=64, niter_single=10000,
                  niter_joint=200, inlier_th=0.1, seed=0, device="cuda:0", precision="f16x3"):

@@ -576,8 +576,10 @@ def main():
                 "avg_launch_ms": stage_ms[dom], "flops_per_launch": fl[dom],
                 "note": "algorithmic FLOPs (2*MAC, unpadded) of the stage for one device batch / its CUDA-event duration in a "
                         "serialized pass of this run; the fp16 hi/lo split issues 3 MMAs per algorithmic product"}
-    dom_t = max(("sa1", "sa2", "sa3", "fp1", "fp2", "fp3_heads"), key=lambda k: stage_ms[k])
+    tensor_stages = ("sa1", "sa2", "sa3", "fp1", "fp2", "fp3_heads")
+    dom_t = max(tensor_stages, key=lambda k: stage_ms[k])
     roofline_tensor = tensor_roofline(dom_t)
+    roofline_tensor["frac_by_stage"] = {k: round(fl[k] / (stage_ms[k] * 1e-3) / 1e12 / tensor_peak, 4) for k in tensor_stages}
     dom = max(all_ms, key=lambda k: all_ms[k])
     if dom == "pose_joint_score" and lm_tot["nfev"] > 0:
         flops = (lm_tot["nfev"] * (LM_FLOPS["cost"] + LM_FLOPS["finish"]) + lm_tot["njev"] * (LM_FLOPS["jacobian"] + LM_FLOPS["jac_phase"]) +
@@ -590,7 +592,14 @@ def main():
                     "model": {"flops": LM_FLOPS, "evaluations": lm_tot["nfev"] / n_prof, "jacobians": lm_tot["njev"] / n_prof,
                               "lmpar_iterations": lm_tot["nlm"] / n_prof},
                     "note": "latency bound: MINPACK's lmder is a strictly sequential chain per solve (profiles/r02_lm_experiments.md); "
-                            "the tail phases run on a handful of warps and overlap later batches in the pipelined run"}
+                            "the stage is kept narrow on purpose (lm_grid) so that the forwards of the overlapped batches keep the "
+                            "other SMs: more lanes shorten this stage and lower the pipelined throughput"}
+        import ctypes
+        lm_thr, lm_blk = ctypes.c_int(0), ctypes.c_int(0)
+        _lib.check(_lib.ancsh_pose_lm_shape(ctypes.byref(lm_thr), ctypes.byref(lm_blk)), "ancsh_pose_lm_shape")
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        roofline["lm_grid"] = {"threads_per_block": lm_thr.value, "max_blocks": lm_blk.value, "sms": sms}
+        roofline["frac_of_occupied_sms"] = ach / (fp64_peak * min(lm_blk.value, sms) / sms)
     elif dom in fl:
         roofline = tensor_roofline(dom)
     else:

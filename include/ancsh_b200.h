@@ -40,6 +40,11 @@ unsigned long long ancsh_launch_count(void);
  * denominator of the f64 pose kernels.  sink: one device double (never written in practice). */
 int ancsh_diag_fp64_fma(int blocks, int iters, double *sink, void *stream);
 
+/* Diagnostic: launch shape of the joint LM solve (joint_lm_kernel) on the current device: threads per block and the most
+ * blocks one of its phases uses.  The stage is deliberately narrow (the lanes are latency bound; SMs without LM blocks keep
+ * two forward CTAs of the overlapped batches); bench.py reports the SMs it occupies next to its roofline fraction. */
+int ancsh_pose_lm_shape(int *threads_per_block, int *max_blocks);
+
 /* ------------------------------------------------------------------------------------------------
  * Op level -- one entry point per native op on the path.
  * ---------------------------------------------------------------------------------------------- */

@@ -6,7 +6,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 1 --warmup 3 --chunks 2 --no-cpu-baseline > $OUT/${TAG}_ncu_launches.log 2>&1
 tail -2 $OUT/${TAG}_ncu_launches.log | cut -c1-300
 echo "== ncu full: forward kernels (batch 256)"
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'sa_lean_kernel|chain2_kernel|gemm_tc_kernel|fps_kernel|three_nn_kernel' -s 22 -c 12 -f -o $OUT/${TAG}_fwd \
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'sa_lean_kernel|chain2_kernel|gemm_img_kernel|fps_kernel|three_nn_kernel' -s 22 -c 12 -f -o $OUT/${TAG}_fwd \
     python bench.py --workload forward --steps 1 --warmup 3 --chunks 1 --no-cpu-baseline > $OUT/${TAG}_ncu_fwd.log 2>&1
 tail -2 $OUT/${TAG}_ncu_fwd.log | cut -c1-300
 # summaries are extracted on the box (gpurun copies back at most 64 MiB): raw metrics of every captured launch, SASS-level
@@ -29,7 +29,7 @@ python scripts/ncu_stalls.py $OUT/${TAG}_pose_src_lm.csv joint_lm 60 > $OUT/${TA
 rm -f $OUT/${TAG}_pose.ncu-rep $OUT/${TAG}_pose_src_lm.csv
 echo "== ncu dram traffic of the forward kernels at the bench batch"
 timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,lts__t_bytes.sum \
-    --clock-control none -k regex:'sa_lean_kernel|chain2_kernel|gemm_tc_kernel|three_nn_kernel|fps_kernel|cloud_bias' -s 33 -c 11 --csv --log-file $OUT/${TAG}_fwd_traffic.csv \
+    --clock-control none -k regex:'sa_lean_kernel|chain2_kernel|gemm_img_kernel|three_nn_kernel|fps_kernel|cloud_bias' -s 33 -c 11 --csv --log-file $OUT/${TAG}_fwd_traffic.csv \
     python bench.py --workload forward --steps 1 --warmup 3 --chunks 1 --no-cpu-baseline > $OUT/${TAG}_ncu_traffic.log 2>&1
 tail -2 $OUT/${TAG}_ncu_traffic.log | cut -c1-300
 ls -la $OUT | grep ${TAG}_
