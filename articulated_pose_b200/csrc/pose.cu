@@ -1352,7 +1352,8 @@ extern "C" int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in
             //   64 / 128 / 256 threads per block at 64 lanes per SM:   32.0k / 33.5k / 34.9k clouds/s
             //   256 threads, 135 / 100 / 75 / 50 / 35 / 25 % of those lanes:  34.6k / 34.8k / 35.4k / 35.9k / 35.8k / 35.1k
             //   (joint stage alone: 8.5 / 8.8 / 9.6 / 11.2 / 13.3 / 15.6 ms)
-            //   512 threads at 128 registers (2 KB of spills per lane): 35.1k -- rejected
+            //   512 threads at 128 registers (2 KB of spills per lane): 35.1k -- rejected; 384 threads at 168 registers: 37.4k vs
+            //   36.9k in the same session (+1 %, joint stage 14.4 instead of 11.4 ms) -- not worth the spills
             // Default: 256-thread blocks, 32 lanes per SM -> 18 blocks on a 148-SM part.  ANCSH_LM_THREADS (64 / 128 / 256),
             // ANCSH_LM_LANE_PCT and ANCSH_LM_BLOCKS_PER_SM (multiplier 1..4) override -- more lanes for latency, fewer for
             // throughput.
