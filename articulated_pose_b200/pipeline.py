@@ -79,6 +79,43 @@ class AncshPipeline:
             self._slots[key] = d
         return self._slots[key]
 
+    def prepare(self, B, N):
+        """Allocate everything submit() / run_many() create lazily for (B, N) batches -- the per-slot prediction and pose
+        buffers, pose workspaces and side streams, the network workspaces, the pinned staging buffers -- so that the first
+        pass over all N_SLOTS slots does not pay for cudaMalloc / cudaHostAlloc in the middle of a stream."""
+        with torch.cuda.device(self.device):
+            for slot in range(self.N_SLOTS):
+                self._slot(B, N, slot)
+                self._pose_stream(slot)
+                self.pose._plan(B, N, slot)
+            self.net._workspace(B, N)
+            if self.net_npcs is not None:
+                self.net_npcs._workspace(B, N)
+            self._many_buffers(B, N)
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+
+    def _pose_stream(self, slot):
+        if slot not in self._pose_streams:
+            # same priority as the caller's stream: measured on B200 (256 clouds/step) a high-priority pose stream gives
+            # 24.8-24.9k clouds/s, equal priority 25.4k -- the pose kernels are latency-bound and fill the gaps anyway,
+            # while pre-empting the block scheduler only stretches the forwards.  ANCSH_POSE_PRIORITY overrides (-1 = high).
+            import os
+            self._pose_streams[slot] = torch.cuda.Stream(device=self.device, priority=int(os.environ.get("ANCSH_POSE_PRIORITY", "0")))
+        return self._pose_streams[slot]
+
+    def _many_buffers(self, B, N):
+        key = ("many", B, N)
+        if key not in self._buf:
+            self._buf[key] = [{"hP": torch.empty((B, N, 3), dtype=torch.float32).pin_memory(),
+                               "hjc": torch.empty((B, N), dtype=torch.int32).pin_memory(),
+                               "P": torch.empty((B, N, 3), dtype=torch.float32, device=self.device),
+                               "jc": torch.empty((B, N), dtype=torch.int32, device=self.device),
+                               "hpose": {k: torch.empty(v.shape, dtype=v.dtype).pin_memory()
+                                         for k, v in self.pose.alloc_outputs(B, N).items()},
+                               "copied": torch.cuda.Event()} for _ in range(self.N_SLOTS)]
+        return self._buf[key]
+
     def submit(self, P, joint_cls, slot=0, net_events=None, net_b_events=None, pose_events=None, seed=None):
         """Asynchronous run_device: the forwards are enqueued on the current stream, the pose stage on an
         internal side stream (one per slot) that waits for them; buffers are per `slot` (cycle through
@@ -88,13 +125,7 @@ class AncshPipeline:
         B, N, _ = P.shape
         sl = self._slot(B, N, slot)
         main = torch.cuda.current_stream()
-        if slot not in self._pose_streams:
-            # same priority as the caller's stream: measured on B200 (256 clouds/step) a high-priority pose stream gives
-            # 24.8-24.9k clouds/s, equal priority 25.4k -- the pose kernels are latency-bound and fill the gaps anyway,
-            # while pre-empting the block scheduler only stretches the forwards.  ANCSH_POSE_PRIORITY overrides (-1 = high).
-            import os
-            self._pose_streams[slot] = torch.cuda.Stream(device=self.device, priority=int(os.environ.get("ANCSH_POSE_PRIORITY", "0")))
-        ps = self._pose_streams[slot]
+        ps = self._pose_stream(slot)
         if sl["used"]:
             main.wait_event(sl["pose_done"])          # the slot's prediction buffers are still being read
         pred = self.net.forward_device(P, sl["pred"], stage_events=net_events)
@@ -121,43 +152,39 @@ class AncshPipeline:
         """Host API for a stream of batches [(P, joint_cls), ...] (all the same shape): pinned H2D, forwards and
         pose stages pipelined over N_SLOTS slots, D2H of the pose records.  Returns one result per batch.
         seeds: optional Philox key per batch."""
+        return self.run_many_begin(batches, unpack=unpack, seeds=seeds)()
+
+    def run_many_begin(self, batches, unpack=False, seeds=None):
+        """run_many in two halves: enqueues every batch (collecting older results only where a slot has to be reused) and
+        returns `finish`, which waits for the rest and returns the per-batch results.  Work enqueued by the caller in
+        between -- e.g. another category's pipeline (stream.MixedStream) -- overlaps this stream's pose tails."""
         if not batches:
-            return []
+            return lambda: []
         B, N, _ = batches[0][0].shape
-        key = ("many", B, N)
-        if key not in self._buf:
-            self._buf[key] = [{"hP": torch.empty((B, N, 3), dtype=torch.float32).pin_memory(),
-                               "hjc": torch.empty((B, N), dtype=torch.int32).pin_memory(),
-                               "P": torch.empty((B, N, 3), dtype=torch.float32, device=self.device),
-                               "jc": torch.empty((B, N), dtype=torch.int32, device=self.device),
-                               "hpose": {k: torch.empty(v.shape, dtype=v.dtype).pin_memory()
-                                         for k, v in self.pose.alloc_outputs(B, N).items()},
-                               "copied": torch.cuda.Event()} for _ in range(self.N_SLOTS)]
-        bufs = self._buf[key]
+        bufs = self._many_buffers(B, N)
         results = [None] * len(batches)
         pending = [None] * self.N_SLOTS
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        copy_stream = self._copy_stream
+
+        def drain(slot):
+            if pending[slot] is None:
+                return
+            i, out = pending[slot]
+            # D2H on its own stream behind the slot's pose stage only: on the main stream the copy would queue behind
+            # the forwards of the newer batches and the host would fall a whole pipeline depth behind the device
+            copy_stream.wait_event(self._slot(B, N, slot)["pose_done"])
+            with torch.cuda.stream(copy_stream):
+                for k, v in out.items():
+                    bufs[slot]["hpose"][k].copy_(v, non_blocking=True)
+                bufs[slot]["copied"].record(copy_stream)
+            bufs[slot]["copied"].synchronize()
+            h = {k: v.numpy().copy() for k, v in bufs[slot]["hpose"].items()}
+            results[i] = unpack_results(h, self.K) if unpack else h
+            pending[slot] = None
+
         with torch.cuda.device(self.device):
-            main = torch.cuda.current_stream()
-            if getattr(self, "_copy_stream", None) is None:
-                self._copy_stream = torch.cuda.Stream(device=self.device)
-            copy_stream = self._copy_stream
-
-            def drain(slot):
-                if pending[slot] is None:
-                    return
-                i, out = pending[slot]
-                # D2H on its own stream behind the slot's pose stage only: on the main stream the copy would queue behind
-                # the forwards of the newer batches and the host would fall a whole pipeline depth behind the device
-                copy_stream.wait_event(self._slot(B, N, slot)["pose_done"])
-                with torch.cuda.stream(copy_stream):
-                    for k, v in out.items():
-                        bufs[slot]["hpose"][k].copy_(v, non_blocking=True)
-                    bufs[slot]["copied"].record(copy_stream)
-                bufs[slot]["copied"].synchronize()
-                h = {k: v.numpy().copy() for k, v in bufs[slot]["hpose"].items()}
-                results[i] = unpack_results(h, self.K) if unpack else h
-                pending[slot] = None
-
             for i, (P, jc) in enumerate(batches):
                 slot = i % self.N_SLOTS
                 drain(slot)                              # results of the batch that used this slot last
@@ -167,9 +194,13 @@ class AncshPipeline:
                 bufs[slot]["jc"].copy_(bufs[slot]["hjc"], non_blocking=True)
                 pending[slot] = (i, self.submit(bufs[slot]["P"], bufs[slot]["jc"], slot=slot,
                                                 seed=None if seeds is None else seeds[i]))
-            for k in range(self.N_SLOTS):              # oldest first
-                drain((len(batches) + k) % self.N_SLOTS)
-        return results
+
+        def finish():
+            with torch.cuda.device(self.device):
+                for k in range(self.N_SLOTS):              # oldest first
+                    drain((len(batches) + k) % self.N_SLOTS)
+            return results
+        return finish
 
     def run(self, P, joint_cls, unpack=True):
         """Host arrays in, host results out: pinned H2D of the clouds, all stages on the device, D2H of the poses

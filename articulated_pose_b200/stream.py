@@ -78,12 +78,20 @@ class MixedStream:
         as_records = records_k_max is not None
         results = [None] * len(mine)
         rec = np.zeros((len(mine), 1 + adist.record_width(records_k_max)), np.float64) if as_records else None
+        # enqueue every category before collecting any: the forwards of the next category overlap the pose tail of the
+        # previous one (each pipeline has its own slots and pose streams)
+        started = []
         for cat, positions in bucket_by_category(mine).items():
             pipe = self.pipelines[cat]
             chunks = batches(positions, self.batch)
             work = [self._load_chunk(cat, [mine[p][1] for p in chunk]) for chunk in chunks]
             full = [w for w in work if w[0].shape[0] == work[0][0].shape[0]]
-            outs = pipe.run_many(full, unpack=unpack and not as_records)
+            begin = getattr(pipe, "run_many_begin", None)       # any object with run_many() works; the split form overlaps
+            finish = begin(full, unpack=unpack and not as_records) if begin else \
+                (lambda r=pipe.run_many(full, unpack=unpack and not as_records): r)
+            started.append((pipe, chunks, work, full, finish))
+        for pipe, chunks, work, full, finish in started:
+            outs = finish()
             for w in work[len(full):]:
                 outs += pipe.run_many([w], unpack=unpack and not as_records)
             for chunk, out in zip(chunks, outs):

@@ -304,6 +304,7 @@ def run_mixed(args, rank, local_rank, world):
                                    niter_joint=args.joint_hyp, seed=1234 + rank, device=dev, precision=args.precision)
         cl = [synthetic.make_cloud(i, cat) for i in range(args.unique)]
         pool[cat] = (np.stack([c["P"] for c in cl]).astype(np.float32), np.stack([c["joint_cls_gt"] for c in cl]).astype(np.int32))
+        pipes[cat].prepare(args.batch, pool[cat][0].shape[1])     # all slots' buffers / workspaces before the stream starts
     items = synthetic.mixed_stream(args.clouds)
     steps = max(1, args.steps)
     seg = [(len(items) * k // steps, len(items) * (k + 1) // steps) for k in range(steps)]
