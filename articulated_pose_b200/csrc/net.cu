@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(256) cloud_bias_kernel(const float *__restrict
     }
 }
 
-// Tiled variant for the usual shapes (cin % 64 == 0, cout_pad % 64 == 0): a block owns CB_G clouds x 64 columns, its 256
+// Tiled variant for the usual shapes (cin % 128 == 0, cout_pad % 64 == 0): a block owns CB_G clouds x 64 columns, its 256
 // threads = 64 columns x 4 quarters of the k range.  Every weight is loaded once per 8 clouds (the one-cloud-per-block
 // kernel above streams the whole matrix per cloud: 256 MB of L2 reads per 256 clouds, 0.060 ms), the features come from
 // shared memory as 16-byte broadcasts.  The four partial sums of a column are added in a fixed order.
@@ -227,9 +227,25 @@ __global__ void __launch_bounds__(256) cloud_bias_tiled_kernel(const float *__re
     float *s_part = s_f + (size_t)CB_G * cin;
     const int b0 = blockIdx.x * CB_G, c0 = blockIdx.y * 64;
     const int col = threadIdx.x & 63, kq = threadIdx.x >> 6;
-    for (int i = threadIdx.x; i < CB_G * cin; i += 256) {
-        const int g = i / cin, k = i - g * cin;
-        s_f[i] = b0 + g < nclouds ? feat[(size_t)(b0 + g) * cin + k] : 0.f;
+    // the CB_G feature rows are consecutive in memory: one linear float4 copy, 8 loads in flight per thread
+    {
+        const int rows = min(CB_G, nclouds - b0);
+        const float4 *src = reinterpret_cast<const float4 *>(feat + (size_t)b0 * cin);
+        float4 *dst = reinterpret_cast<float4 *>(s_f);
+        const int n4 = rows * cin / 4, all4 = CB_G * cin / 4;
+        for (int i0 = threadIdx.x; i0 < all4; i0 += 256 * 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * 256;
+                v[u] = i < n4 ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * 256;
+                if (i < all4) dst[i] = v[u];
+            }
+        }
     }
     __syncthreads();
     const int kn = cin / 4, k0 = kq * kn;
@@ -237,19 +253,26 @@ __global__ void __launch_bounds__(256) cloud_bias_tiled_kernel(const float *__re
 #pragma unroll
     for (int g = 0; g < CB_G; ++g) acc[g] = 0.f;
     const float *w = W + (size_t)k0 * cout_pad + c0 + col;
-    for (int k = 0; k < kn; k += 16) {                           // cin % 64 == 0: 16 loads in flight per thread
-        float wv[16];
+    // cin % 128 == 0: two groups of 16 weights per trip, the second group's loads fly under the first group's FMAs
+    for (int k = 0; k < kn; k += 32) {
+        float wa[16], wb[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) wv[i] = __ldg(w + (size_t)(k + i) * cout_pad);
+        for (int i = 0; i < 16; ++i) wa[i] = __ldg(w + (size_t)(k + i) * cout_pad);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int i = 0; i < 16; ++i) wb[i] = __ldg(w + (size_t)(k + 16 + i) * cout_pad);
 #pragma unroll
-            for (int g = 0; g < CB_G; ++g) {
-                const float4 f = *reinterpret_cast<const float4 *>(s_f + (size_t)g * cin + k0 + k + 4 * q);
-                acc[g] = fmaf(f.x, wv[4 * q], acc[g]);
-                acc[g] = fmaf(f.y, wv[4 * q + 1], acc[g]);
-                acc[g] = fmaf(f.z, wv[4 * q + 2], acc[g]);
-                acc[g] = fmaf(f.w, wv[4 * q + 3], acc[g]);
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                for (int g = 0; g < CB_G; ++g) {
+                    const float4 f = *reinterpret_cast<const float4 *>(s_f + (size_t)g * cin + k0 + k + 16 * half + 4 * q);
+                    const float *wv = half ? wb : wa;
+                    acc[g] = fmaf(f.x, wv[4 * q], acc[g]);
+                    acc[g] = fmaf(f.y, wv[4 * q + 1], acc[g]);
+                    acc[g] = fmaf(f.z, wv[4 * q + 2], acc[g]);
+                    acc[g] = fmaf(f.w, wv[4 * q + 3], acc[g]);
+                }
             }
         }
     }
@@ -268,7 +291,7 @@ __global__ void __launch_bounds__(256) cloud_bias_tiled_kernel(const float *__re
 static int cloud_bias_launch(int B, const float *feat, const ancsh_layer_t &G, float *out, cudaStream_t st)
 {
     const size_t smem = ((size_t)CB_G * G.cin + 4 * CB_G * 64) * sizeof(float);
-    if (G.cin % 64 == 0 && G.cout_pad % 64 == 0 && smem <= 200 * 1024) {
+    if (G.cin % 128 == 0 && G.cout_pad % 64 == 0 && smem <= 200 * 1024) {
         if (smem > 48 * 1024)
             ANCSH_CUDA(cudaFuncSetAttribute(cloud_bias_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cloud_bias_tiled_kernel<<<dim3((B + CB_G - 1) / CB_G, G.cout_pad / 64), 256, smem, st>>>(feat, G.cin, B, G.W, G.b,

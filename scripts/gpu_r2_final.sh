@@ -11,4 +11,3 @@ echo "== bench drawer" ; timeout 600 python bench.py --workload drawer --no-cpu-
 echo "== bench cpu64" ; timeout 900 python bench.py --workload cpu64 2>/dev/null | tail -1 | tee $OUT/${TAG}_bench_cpu64.json | cut -c1-300
 echo "== bench reference settings (nsample 64, 10000 hyp)" ; timeout 900 python bench.py --nsample 64 --hyp 10000 --no-cpu-baseline --steps 4 --chunks 6 2>/dev/null | tail -1 | tee $OUT/${TAG}_bench_ref_settings.json | cut -c1-300
 echo "== timeline" ; timeout 300 python scripts/timeline_probe.py 2>&1 | tail -24 | tee $OUT/${TAG}_timeline.txt | tail -6
-echo "== bench, 8 slots" ; ANCSH_SLOTS=8 timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline 2>/dev/null | tail -1 | tee $OUT/${TAG}_bench_slots8.json | cut -c1-200
