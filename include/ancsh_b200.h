@@ -200,8 +200,9 @@ typedef struct {
     size_t fp1_bias;  /* f32 (B,256)          per-cloud bias of fa_layer1/conv_0 */
     size_t l2_points_fp; /* f32 (B,npoint2,256) fa_layer1 output */
     size_t l1_points_fp; /* f32 (B,npoint1,128) fa_layer2 output */
-    size_t interp3;      /* f32 (B,npoint2,512) scratch: layer3 conv_1 output (tensor-core path only; the name is historic --
-                            the interpolated rows of the fa layers are built on chip and never stored) */
+    size_t interp3;      /* (B*npoint2*512*4 bytes) scratch: layer3 conv_1 output as the fp16 hi/lo operand image of conv_2, per
+                            128-row tile [512/8][hi|lo][128][8] (tensor-core path only; the name is historic -- the interpolated
+                            rows of the fa layers are built on chip and never stored) */
     size_t raw_heads;    /* unused (0 bytes): the head activations run in the epilogue of the head layers */
     size_t nn_idx2;      /* int32 (B,npoint1,3) three_nn of l1_xyz in l2_xyz (fa_layer2); geometry, shared like the FPS indices */
     size_t nn_w2;        /* f32   (B,npoint1,3) inverse-distance weights (pointnet_util.py:219-222) */

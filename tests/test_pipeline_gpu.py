@@ -95,3 +95,31 @@ def test_shared_geometry_forward_is_bit_identical():
     torch.cuda.synchronize()
     for k in alone:
         assert torch.equal(alone[k], shared[k]), k
+
+
+def test_run_many_begin_overlaps_pipelines_without_changing_results():
+    """run_many_begin / finish (the mixed stream enqueues every category's pipeline before it collects any result) with
+    more batches than buffer slots and two pipelines interleaved: bit-identical to one run() per batch; prepare() only
+    pre-allocates."""
+    from articulated_pose_b200 import synthetic
+    from articulated_pose_b200.pipeline import AncshPipeline
+    K, ns, B = 3, 32, 2
+    w_a, w_n = _weights(K, ns)
+    pipes = [AncshPipeline(w_a, K, weights_npcs=w_n, nsample=ns, niter_single=64, niter_joint=8, seed=11 + i) for i in range(2)]
+    n_batches = AncshPipeline.N_SLOTS + 3                       # forces slot reuse inside the enqueue loop
+    work = []
+    for i in range(n_batches):
+        P, clouds = synthetic.make_batch(range(300 + B * i, 300 + B * (i + 1)))
+        work.append((P, np.stack([c["joint_cls_gt"] for c in clouds]).astype(np.int32)))
+    seeds = list(range(1000, 1000 + n_batches))
+    pipes[0].prepare(B, work[0][0].shape[1])
+    fins = [p.run_many_begin(work, seeds=seeds) for p in pipes]  # both pipelines enqueued before either is collected
+    outs = [f() for f in fins]
+    for p, out in zip(pipes, outs):
+        assert len(out) == n_batches
+        for i in (0, AncshPipeline.N_SLOTS, n_batches - 1):
+            Pd, jd = torch.from_numpy(work[i][0]).cuda(), torch.from_numpy(work[i][1]).cuda()
+            ref = {k: v.cpu().numpy() for k, v in p.run_device(Pd, jd, seed=seeds[i]).items()}
+            assert set(ref) == set(out[i])
+            for k in ref:
+                np.testing.assert_array_equal(out[i][k], ref[k], err_msg="batch %d %s" % (i, k))
