@@ -282,10 +282,11 @@ __global__ void __launch_bounds__(RT, 2) single_score_kernel(const SingleArgs a)
 }
 
 // first maximum of an int score array (ransac keeps the FIRST best: strict '>' at parallel_ancsh_pose.py:28)
+template <int NTH>
 __device__ int block_first_argmax_int(const int *scores, int n, unsigned long long *s_key)
 {
     unsigned long long best = 0ull;
-    for (int h = threadIdx.x; h < n; h += RT) {
+    for (int h = threadIdx.x; h < n; h += NTH) {
         const unsigned long long key = ((unsigned long long)(unsigned)(scores[h] + 1) << 32) | (unsigned)(0xFFFFFFFFu - (unsigned)h);
         best = key > best ? key : best;
     }
@@ -296,18 +297,22 @@ __device__ int block_first_argmax_int(const int *scores, int n, unsigned long lo
     if ((threadIdx.x & 31) == 0) s_key[threadIdx.x >> 5] = best;
     __syncthreads();
     best = 0ull;
-    for (int w = 0; w < RT / 32; ++w) best = s_key[w] > best ? s_key[w] : best;
+    for (int w = 0; w < NTH / 32; ++w) best = s_key[w] > best ? s_key[w] : best;
     __syncthreads();
     return (int)(0xFFFFFFFFu - (unsigned)(best & 0xFFFFFFFFull));
 }
 
-__global__ void __launch_bounds__(RT) single_refit_kernel(const SingleArgs a)
+// Threads per block: the kernel alternates block-wide passes with thread 0's 3x3 SVDs (45 % of the warp time of a 256-thread
+// block was spent at barriers behind them, profiles/r02_single_refit_sass_stalls.txt); smaller blocks -- more of them resident
+// per SM -- overlap one block's serial section with the others' passes.
+constexpr int RSR = 128;
+__global__ void __launch_bounds__(RSR, 4) single_refit_kernel(const SingleArgs a)
 {
     extern __shared__ double s_pts[];
-    __shared__ double s_red[(RT / 32 + 1) * 11];
-    __shared__ unsigned long long s_key[RT / 32];
+    __shared__ double s_red[(RSR / 32 + 1) * 11];
+    __shared__ unsigned long long s_key[RSR / 32];
     __shared__ double s_model[13];
-    __shared__ int s_scan[RT / 32];
+    __shared__ int s_scan[RSR / 32];
     const int prob = blockIdx.x, tid = threadIdx.x;
     const int n = a.part_count[prob];
     double *s_src = s_pts, *s_tgt = s_pts + (size_t)a.N * 3;
@@ -316,7 +321,7 @@ __global__ void __launch_bounds__(RT) single_refit_kernel(const SingleArgs a)
     unsigned char *g_inl = a.inliers + (size_t)prob * a.N;
     double *oR = a.R + (size_t)prob * 9, *ot = a.t + (size_t)prob * 3;
     if (n <= 0) {
-        for (int i = tid; i < a.N; i += RT) g_inl[i] = 0;
+        for (int i = tid; i < a.N; i += RSR) g_inl[i] = 0;
         if (tid == 0) {
             for (int i = 0; i < 9; ++i) oR[i] = nan("");
             for (int i = 0; i < 3; ++i) ot[i] = nan("");
@@ -328,7 +333,7 @@ __global__ void __launch_bounds__(RT) single_refit_kernel(const SingleArgs a)
         return;
     }
     load_part_f64(a.part_src + (size_t)prob * a.N * 3, a.part_tgt + (size_t)prob * a.N * 3, n, s_src, s_tgt);
-    const int hbest = block_first_argmax_int(a.scores + (size_t)prob * a.niter, a.niter, s_key);   // syncs inside
+    const int hbest = block_first_argmax_int<RSR>(a.scores + (size_t)prob * a.niter, a.niter, s_key);   // syncs inside
     if (tid == 0) {
         int id[3];
         fetch_sample(a.idx, a.seed, prob, hbest, 0u, a.niter, n, id);
@@ -341,7 +346,7 @@ __global__ void __launch_bounds__(RT) single_refit_kernel(const SingleArgs a)
     __syncthreads();
     // inlier mask of the best hypothesis + sums over the inliers
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-    for (int i = tid; i < a.N; i += RT) {
+    for (int i = tid; i < a.N; i += RSR) {
         unsigned char in = 0;
         if (i < n) {
             in = is_inlier(s_model, s_model[9], s_model + 10, s_src + 3 * i, s_tgt + 3 * i, a.th2) ? 1 : 0;
@@ -353,7 +358,7 @@ __global__ void __launch_bounds__(RT) single_refit_kernel(const SingleArgs a)
         }
         g_inl[i] = in;
     }
-    block_sum<7, RT>(acc, s_red);
+    block_sum<7, RSR>(acc, s_red);
     const int nin = (int)acc[6];
     if (nin == 0) {
         if (tid == 0) {
@@ -368,23 +373,23 @@ __global__ void __launch_bounds__(RT) single_refit_kernel(const SingleArgs a)
     double ms[3], mt[3];
     for (int c = 0; c < 3; ++c) { ms[c] = acc[c] / nin; mt[c] = acc[3 + c] / nin; }
     // centre in place (transform_pts, d3_utils.py:226-227)
-    for (int i = tid; i < n; i += RT)
+    for (int i = tid; i < n; i += RSR)
         for (int c = 0; c < 3; ++c) { s_src[3 * i + c] -= ms[c]; s_tgt[3 * i + c] -= mt[c]; }
     __syncthreads();
     // M = target_c^T source_c (9) and the pairwise sums of scale_pts over unordered inlier pairs (2)
-    block_compact_indices<RT>(s_inl, n, s_list, s_scan);
+    block_compact_indices<RSR>(s_inl, n, s_list, s_scan);
     double v[11];
     for (int k = 0; k < 9; ++k) v[k] = 0.0;
-    for (int c = tid; c < nin; c += RT) {
+    for (int c = tid; c < nin; c += RSR) {
         const double *si = s_src + 3 * s_list[c], *ti = s_tgt + 3 * s_list[c];
         for (int p = 0; p < 3; ++p)
             for (int q = 0; q < 3; ++q) v[3 * p + q] += ti[p] * si[q];
     }
     {
         double bb;
-        pair_sums<RT>(s_src, s_tgt, s_list, nin, v[9], v[10], bb);
+        pair_sums<RSR>(s_src, s_tgt, s_list, nin, v[9], v[10], bb);
     }
-    block_sum<11, RT>(v, s_red);
+    block_sum<11, RSR>(v, s_red);
     if (tid == 0) {
         double R[9];
         pm::kabsch_rotation(v, R);
@@ -1313,7 +1318,7 @@ extern "C" int ancsh_pose_solve(const ancsh_pose_cfg_t *cfg, const ancsh_pose_in
         size_t smem2 = smem + (size_t)5 * N;           // + inlier index list (int) + mask (byte)
         ANCSH_CUDA(cudaFuncSetAttribute(single_refit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         ANCSH_CUDA(cudaFuncSetAttribute(single_refit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        single_refit_kernel<<<B * K, RT, smem2, st>>>(a);
+        single_refit_kernel<<<B * K, RSR, smem2, st>>>(a);
         ANCSH_CHECK_LAUNCH();
     }
     STAGE_MARK();
