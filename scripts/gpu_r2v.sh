@@ -1,8 +1,5 @@
 #!/bin/bash
-# single_refit with 128-thread blocks
-run() { echo "== $*"; env "$@" timeout 600 python bench.py --no-cpu-baseline 2>&1 | tail -1 | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); s=d['roofline']['stage_ms']; print(round(d['value']), 'e2e', round(d['e2e']['value']), d['ms_per_step'], {k:v for k,v in s.items() if k.startswith('pose')})"; }
-echo "== pytest pose"; timeout 900 python -m pytest tests/test_pose_gpu.py tests/test_pipeline_gpu.py tests/test_pose_f32_reference.py tests/test_stream_gpu.py -q -x --tb=short 2>&1 | tail -3
-run A=1
-run A=2
+# documented run-time switches still work: LM block shapes, separate ball query, generic chain for layer1/2
+for E in ANCSH_LM_THREADS=64 ANCSH_LM_THREADS=128 ANCSH_BALL_FUSED_OFF=1 ANCSH_SA_LEAN_OFF=1 ANCSH_FPS_PREFIX_OFF=1; do
+echo "== $E"; env $E timeout 900 python -m pytest tests/test_pose_gpu.py tests/test_network_gpu.py tests/test_pipeline_gpu.py -q -x --tb=short -k "not reference_default_hypothesis and not bench_batch" 2>&1 | tail -2
+done
